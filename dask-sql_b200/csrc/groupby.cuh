@@ -1,0 +1,388 @@
+// groupby.cuh — group tables fused with the predicate scan:
+//   dense  (direct-address, key range known from ingest statistics)
+//   hash1  (open addressing, one 64-bit key stored in the table, CAS insert)
+//   hashk  (open addressing, 1..4 key columns of any type, per-slot state word)
+// plus the fused star pipeline (filter -> key lookup -> aggregate).
+#pragma once
+#include "common.cuh"
+
+#define B2_GB_R 8
+#define B2_GB_ROWS_PER_BLOCK (B2_BLOCK * B2_GB_R)
+#define B2_MAX_PROBE 1024
+
+// ---- dense ------------------------------------------------------------------------------
+__global__ void __launch_bounds__(B2_BLOCK)
+b2_groupby_dense_kernel(const __grid_constant__ b2_scan_t s, int key_col, int64_t kmin, int64_t nslots,
+                        const __grid_constant__ b2_aggs_arg aggs, const __grid_constant__ b2_aggstate_t st) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const b2_col_t& kc = s.cols[key_col];
+  for (int64_t base = (int64_t)blockIdx.x * B2_GB_ROWS_PER_BLOCK; base < s.n;
+       base += (int64_t)gridDim.x * B2_GB_ROWS_PER_BLOCK) {
+    const int64_t row0 = base + (int64_t)warp * (32 * B2_GB_R) + lane;
+    const uint32_t bits = b2_eval_terms<B2_GB_R>(s, row0);
+    int64_t key[B2_GB_R];
+#pragma unroll
+    for (int j = 0; j < B2_GB_R; ++j)
+      key[j] = (bits >> j) & 1 ? b2_load_raw(kc, row0 + (int64_t)j * 32) : 0;
+    int64_t slot[B2_GB_R];
+#pragma unroll
+    for (int j = 0; j < B2_GB_R; ++j) {
+      slot[j] = -1;
+      if ((bits >> j) & 1) {
+        if (kc.valid && !b2_bit(kc.valid, row0 + (int64_t)j * 32)) slot[j] = nslots - 1;
+        else {
+          const uint64_t d = (uint64_t)key[j] - (uint64_t)kmin;
+          slot[j] = d < (uint64_t)(nslots - 1) ? (int64_t)d : -1;  // out of range cannot happen if stats are right
+        }
+      }
+    }
+    b2_apply_aggs<B2_GB_R>(s, aggs.a, aggs.n, st, row0, slot);
+  }
+}
+
+// ---- hash, single 64-bit key ----------------------------------------------------------------
+__device__ __forceinline__ int64_t b2_hash1_slot(int64_t* __restrict__ tk, int64_t cap, int64_t key,
+                                                 int32_t* __restrict__ flags) {
+  uint64_t h = b2_mix64((uint64_t)key) & (uint64_t)(cap - 1);
+  for (int probe = 0; probe < B2_MAX_PROBE; ++probe) {
+    const int64_t cur = b2_ld_cg_i64(tk + h);
+    if (cur == key) return (int64_t)h;
+    if (cur == B2_EMPTY_KEY) {
+      const unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long*>(tk + h),
+                                               (unsigned long long)B2_EMPTY_KEY, (unsigned long long)key);
+      if (old == (unsigned long long)B2_EMPTY_KEY || old == (unsigned long long)key) return (int64_t)h;
+    }
+    h = (h + 1) & (uint64_t)(cap - 1);
+  }
+  flags[0] = 1;  // overflow: caller retries with a larger table
+  return -1;
+}
+
+__global__ void __launch_bounds__(B2_BLOCK)
+b2_groupby_hash1_kernel(const __grid_constant__ b2_scan_t s, int key_col, int64_t* __restrict__ tk,
+                        int64_t cap, const __grid_constant__ b2_aggs_arg aggs,
+                        const __grid_constant__ b2_aggstate_t st, int32_t* __restrict__ flags) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const b2_col_t& kc = s.cols[key_col];
+  for (int64_t base = (int64_t)blockIdx.x * B2_GB_ROWS_PER_BLOCK; base < s.n;
+       base += (int64_t)gridDim.x * B2_GB_ROWS_PER_BLOCK) {
+    const int64_t row0 = base + (int64_t)warp * (32 * B2_GB_R) + lane;
+    const uint32_t bits = b2_eval_terms<B2_GB_R>(s, row0);
+    int64_t key[B2_GB_R];
+#pragma unroll
+    for (int j = 0; j < B2_GB_R; ++j)
+      key[j] = (bits >> j) & 1 ? b2_load_raw(kc, row0 + (int64_t)j * 32) : 0;
+    int64_t slot[B2_GB_R];
+#pragma unroll
+    for (int j = 0; j < B2_GB_R; ++j) {
+      slot[j] = -1;
+      if (!((bits >> j) & 1)) continue;
+      int64_t k = key[j];
+      if (b2_is_null(kc, row0 + (int64_t)j * 32, k)) { slot[j] = cap; flags[1] = 1; continue; }
+      if (kc.dtype == B2_F64 && k == (int64_t)0x8000000000000000LL) k = 0;  // -0.0 groups with 0.0
+      else if (k == B2_EMPTY_KEY) { slot[j] = cap + 1; flags[2] = 1; continue; }
+      slot[j] = b2_hash1_slot(tk, cap, k, flags);
+    }
+    b2_apply_aggs<B2_GB_R>(s, aggs.a, aggs.n, st, row0, slot);
+  }
+}
+
+// ---- hash, composite keys -------------------------------------------------------------------
+struct b2_keys_arg {
+  int32_t cols[B2_MAX_KEYS];
+  int32_t n;
+};
+
+__device__ __forceinline__ int64_t b2_hashk_slot(int64_t* __restrict__ tk, uint8_t* __restrict__ tnull,
+                                                 int32_t* __restrict__ tstate, int64_t cap, int nkeys,
+                                                 const int64_t* key, uint32_t nullmask,
+                                                 int32_t* __restrict__ flags) {
+  uint64_t hv = 0x9e3779b97f4a7c15ULL ^ nullmask;
+  for (int k = 0; k < nkeys; ++k) hv = b2_mix64(hv ^ (uint64_t)key[k]);
+  uint64_t h = hv & (uint64_t)(cap - 1);
+  int probe = 0;
+  while (probe < B2_MAX_PROBE) {
+    int32_t stt = __ldcg(tstate + h);
+    if (stt == 0) {
+      const int32_t old = atomicCAS(tstate + h, 0, 1);
+      if (old == 0) {  // we own the slot: publish the key, then mark ready
+        for (int k = 0; k < nkeys; ++k) tk[(int64_t)k * cap + h] = key[k];
+        tnull[h] = (uint8_t)nullmask;
+        __threadfence();
+        atomicExch(tstate + h, 2);
+        return (int64_t)h;
+      }
+      stt = old;
+    }
+    if (stt == 1) continue;  // another thread is publishing this slot: re-read (ITS guarantees progress)
+    // ready: compare
+    bool same = __ldcg(reinterpret_cast<const unsigned char*>(tnull) + h) == (uint8_t)nullmask;
+    for (int k = 0; same && k < nkeys; ++k) same = b2_ld_cg_i64(tk + (int64_t)k * cap + h) == key[k];
+    if (same) return (int64_t)h;
+    h = (h + 1) & (uint64_t)(cap - 1);
+    ++probe;
+  }
+  flags[0] = 1;
+  return -1;
+}
+
+__global__ void __launch_bounds__(B2_BLOCK)
+b2_groupby_hashk_kernel(const __grid_constant__ b2_scan_t s, const __grid_constant__ b2_keys_arg keys,
+                        int64_t* __restrict__ tk, uint8_t* __restrict__ tnull, int32_t* __restrict__ tstate,
+                        int64_t cap, const __grid_constant__ b2_aggs_arg aggs,
+                        const __grid_constant__ b2_aggstate_t st, int32_t* __restrict__ flags) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int64_t base = (int64_t)blockIdx.x * B2_GB_ROWS_PER_BLOCK; base < s.n;
+       base += (int64_t)gridDim.x * B2_GB_ROWS_PER_BLOCK) {
+    const int64_t row0 = base + (int64_t)warp * (32 * B2_GB_R) + lane;
+    const uint32_t bits = b2_eval_terms<B2_GB_R>(s, row0);
+    int64_t slot[B2_GB_R];
+#pragma unroll
+    for (int j = 0; j < B2_GB_R; ++j) {
+      slot[j] = -1;
+      if (!((bits >> j) & 1)) continue;
+      const int64_t row = row0 + (int64_t)j * 32;
+      int64_t key[B2_MAX_KEYS];
+      uint32_t nullmask = 0;
+#pragma unroll
+      for (int k = 0; k < B2_MAX_KEYS; ++k) {
+        key[k] = 0;
+        if (k < keys.n) {
+          const b2_col_t& kc = s.cols[keys.cols[k]];
+          int64_t v = b2_load_raw(kc, row);
+          if (b2_is_null(kc, row, v)) { nullmask |= 1u << k; v = 0; }
+          else if (kc.dtype == B2_F64 && v == (int64_t)0x8000000000000000LL) v = 0;
+          key[k] = v;
+        }
+      }
+      slot[j] = b2_hashk_slot(tk, tnull, tstate, cap, keys.n, key, nullmask, flags);
+    }
+    b2_apply_aggs<B2_GB_R>(s, aggs.a, aggs.n, st, row0, slot);
+  }
+}
+
+// ---- fused star pipeline ----------------------------------------------------------------------
+__global__ void __launch_bounds__(B2_BLOCK)
+b2_dense_slots_kernel(const __grid_constant__ b2_col_t key, int64_t n, int64_t kmin, int32_t null_slot,
+                      int32_t* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * B2_BLOCK + threadIdx.x; i < n; i += (int64_t)gridDim.x * B2_BLOCK) {
+    const int64_t raw = b2_load_raw(key, i);
+    out[i] = b2_is_null(key, i, raw) ? null_slot : (int32_t)(raw - kmin);
+  }
+}
+
+__global__ void __launch_bounds__(B2_BLOCK)
+b2_star_build_dense_kernel(const __grid_constant__ b2_col_t pk, const int32_t* __restrict__ sel, int64_t n_sel,
+                           const int32_t* __restrict__ slot_of_row, int64_t kmin, int64_t range,
+                           int32_t* __restrict__ lookup, int32_t* __restrict__ flags) {
+  for (int64_t i = (int64_t)blockIdx.x * B2_BLOCK + threadIdx.x; i < n_sel; i += (int64_t)gridDim.x * B2_BLOCK) {
+    const int64_t r = sel ? sel[i] : i;
+    const int64_t raw = b2_load_raw(pk, r);
+    if (b2_is_null(pk, r, raw)) continue;  // NULL keys never join (join.py:202-213)
+    const uint64_t d = (uint64_t)raw - (uint64_t)kmin;
+    if (d >= (uint64_t)range) continue;
+    const int32_t old = atomicExch(lookup + d, slot_of_row[i]);
+    if (old != -1) flags[0] = 1;  // duplicate build key
+  }
+}
+
+__global__ void __launch_bounds__(B2_BLOCK)
+b2_star_build_hash_kernel(const __grid_constant__ b2_col_t pk, const int32_t* __restrict__ sel, int64_t n_sel,
+                          const int32_t* __restrict__ slot_of_row, int64_t* __restrict__ tk,
+                          int32_t* __restrict__ ts, int64_t cap, int32_t* __restrict__ flags) {
+  for (int64_t i = (int64_t)blockIdx.x * B2_BLOCK + threadIdx.x; i < n_sel; i += (int64_t)gridDim.x * B2_BLOCK) {
+    const int64_t r = sel ? sel[i] : i;
+    const int64_t key = b2_load_raw(pk, r);
+    if (b2_is_null(pk, r, key)) continue;
+    if (key == B2_EMPTY_KEY) { flags[1] = 1; continue; }  // caller falls back to the general join
+    uint64_t h = b2_mix64((uint64_t)key) & (uint64_t)(cap - 1);
+    bool done = false;
+    for (int probe = 0; probe < B2_MAX_PROBE && !done; ++probe) {
+      const unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long*>(tk + h),
+                                               (unsigned long long)B2_EMPTY_KEY, (unsigned long long)key);
+      if (old == (unsigned long long)B2_EMPTY_KEY) { ts[h] = slot_of_row[i]; done = true; }
+      else if (old == (unsigned long long)key) { flags[0] = 1; done = true; }
+      else h = (h + 1) & (uint64_t)(cap - 1);
+    }
+    if (!done) flags[1] = 1;
+  }
+}
+
+__device__ __forceinline__ int32_t b2_star_lookup(const b2_starlookup_t& lk, int64_t key) {
+  if (lk.dense) {
+    const uint64_t d = (uint64_t)key - (uint64_t)lk.kmin;
+    return d < (uint64_t)lk.range ? b2_ld_keep_i32(lk.lookup + d) : -1;
+  }
+  uint64_t h = b2_mix64((uint64_t)key) & (uint64_t)(lk.cap - 1);
+  for (int probe = 0; probe < B2_MAX_PROBE; ++probe) {
+    const int64_t cur = __ldg(reinterpret_cast<const long long*>(lk.table_keys) + h);
+    if (cur == key) return b2_ld_keep_i32(lk.table_slots + h);
+    if (cur == B2_EMPTY_KEY) return -1;
+    h = (h + 1) & (uint64_t)(lk.cap - 1);
+  }
+  return -1;
+}
+
+__global__ void __launch_bounds__(B2_BLOCK)
+b2_star_agg_kernel(const __grid_constant__ b2_scan_t s, int fk_col, const __grid_constant__ b2_starlookup_t lk,
+                   const __grid_constant__ b2_aggs_arg aggs, const __grid_constant__ b2_aggstate_t st) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const b2_col_t& kc = s.cols[fk_col];
+  for (int64_t base = (int64_t)blockIdx.x * B2_GB_ROWS_PER_BLOCK; base < s.n;
+       base += (int64_t)gridDim.x * B2_GB_ROWS_PER_BLOCK) {
+    const int64_t row0 = base + (int64_t)warp * (32 * B2_GB_R) + lane;
+    const uint32_t bits = b2_eval_terms<B2_GB_R>(s, row0);
+    int64_t key[B2_GB_R];
+#pragma unroll
+    for (int j = 0; j < B2_GB_R; ++j)
+      key[j] = (bits >> j) & 1 ? b2_load_raw(kc, row0 + (int64_t)j * 32) : 0;
+    int32_t found[B2_GB_R];
+#pragma unroll
+    for (int j = 0; j < B2_GB_R; ++j) {
+      found[j] = -1;
+      if (((bits >> j) & 1) && !b2_is_null(kc, row0 + (int64_t)j * 32, key[j]) &&
+          !(lk.dense == 0 && key[j] == B2_EMPTY_KEY))
+        found[j] = b2_star_lookup(lk, key[j]);
+    }
+    int64_t slot[B2_GB_R];
+#pragma unroll
+    for (int j = 0; j < B2_GB_R; ++j) slot[j] = found[j];
+    b2_apply_aggs<B2_GB_R>(s, aggs.a, aggs.n, st, row0, slot);
+  }
+}
+
+extern "C" {
+
+static int32_t b2_check_state(const b2_aggs_arg& aa, const b2_aggstate_t* st) {
+  B2_REQUIRE(st, "null aggstate");
+  for (int a = 0; a < aa.n; ++a) {
+    if (aa.a[a].col < 0) { B2_REQUIRE(st->rows, "COUNT(*) needs aggstate.rows"); continue; }
+    if (aa.a[a].op == B2_AGG_COUNT) B2_REQUIRE(st->cnt[a], "COUNT needs a cnt array");
+    else B2_REQUIRE(st->acc[a], "aggregate needs an acc array");
+  }
+  return B2_OK;
+}
+static inline bool b2_pow2(int64_t x) { return x > 0 && (x & (x - 1)) == 0; }
+
+int32_t b2_groupby_dense(const b2_scan_t* scan, int32_t key_col, int64_t kmin, int64_t nslots,
+                         const b2_agg_t* aggs, int32_t naggs, const b2_aggstate_t* st, void* stream) {
+  int32_t rc = b2_check_scan(scan);
+  if (rc) return rc;
+  b2_aggs_arg aa;
+  if ((rc = b2_check_aggs(scan, aggs, naggs, &aa))) return rc;
+  if ((rc = b2_check_state(aa, st))) return rc;
+  B2_REQUIRE(key_col >= 0 && key_col < scan->ncols, "key column out of range");
+  B2_REQUIRE(scan->cols[key_col].dtype == B2_I64 || scan->cols[key_col].dtype == B2_U8, "dense keys must be integers");
+  B2_REQUIRE(nslots >= 2, "nslots must cover the key range plus the NULL slot");
+  if (scan->n == 0) return B2_OK;
+  int64_t nblk = (scan->n + B2_GB_ROWS_PER_BLOCK - 1) / B2_GB_ROWS_PER_BLOCK;
+  int grid = b2_wave_grid(b2_groupby_dense_kernel, B2_BLOCK, nblk);
+  b2_groupby_dense_kernel<<<grid, B2_BLOCK, 0, (cudaStream_t)stream>>>(*scan, key_col, kmin, nslots, aa, *st);
+  B2_CHECK_LAUNCH("b2_groupby_dense_kernel");
+  return B2_OK;
+}
+
+int32_t b2_groupby_hash1(const b2_scan_t* scan, int32_t key_col, int64_t* table_keys, int64_t cap,
+                         const b2_agg_t* aggs, int32_t naggs, const b2_aggstate_t* st, int32_t* d_flags,
+                         void* stream) {
+  int32_t rc = b2_check_scan(scan);
+  if (rc) return rc;
+  b2_aggs_arg aa;
+  if ((rc = b2_check_aggs(scan, aggs, naggs, &aa))) return rc;
+  if ((rc = b2_check_state(aa, st))) return rc;
+  B2_REQUIRE(key_col >= 0 && key_col < scan->ncols, "key column out of range");
+  B2_REQUIRE(scan->cols[key_col].dtype != B2_U8, "hash1 keys must be 64-bit");
+  B2_REQUIRE(table_keys && d_flags, "null argument");
+  B2_REQUIRE(b2_pow2(cap), "cap must be a power of two");
+  if (scan->n == 0) return B2_OK;
+  int64_t nblk = (scan->n + B2_GB_ROWS_PER_BLOCK - 1) / B2_GB_ROWS_PER_BLOCK;
+  int grid = b2_wave_grid(b2_groupby_hash1_kernel, B2_BLOCK, nblk);
+  b2_groupby_hash1_kernel<<<grid, B2_BLOCK, 0, (cudaStream_t)stream>>>(*scan, key_col, table_keys, cap, aa, *st, d_flags);
+  B2_CHECK_LAUNCH("b2_groupby_hash1_kernel");
+  return B2_OK;
+}
+
+int32_t b2_groupby_hashk(const b2_scan_t* scan, const int32_t* key_cols, int32_t nkeys, int64_t* table_keys,
+                         uint8_t* table_nulls, int32_t* table_state, int64_t cap, const b2_agg_t* aggs,
+                         int32_t naggs, const b2_aggstate_t* st, int32_t* d_flags, void* stream) {
+  int32_t rc = b2_check_scan(scan);
+  if (rc) return rc;
+  b2_aggs_arg aa;
+  if ((rc = b2_check_aggs(scan, aggs, naggs, &aa))) return rc;
+  if ((rc = b2_check_state(aa, st))) return rc;
+  B2_REQUIRE(nkeys >= 1 && nkeys <= B2_MAX_KEYS && key_cols, "bad key list");
+  B2_REQUIRE(table_keys && table_nulls && table_state && d_flags, "null argument");
+  B2_REQUIRE(b2_pow2(cap), "cap must be a power of two");
+  b2_keys_arg ka;
+  memset(&ka, 0, sizeof(ka));
+  ka.n = nkeys;
+  for (int k = 0; k < nkeys; ++k) {
+    B2_REQUIRE(key_cols[k] >= 0 && key_cols[k] < scan->ncols, "key column out of range");
+    ka.cols[k] = key_cols[k];
+  }
+  if (scan->n == 0) return B2_OK;
+  int64_t nblk = (scan->n + B2_GB_ROWS_PER_BLOCK - 1) / B2_GB_ROWS_PER_BLOCK;
+  int grid = b2_wave_grid(b2_groupby_hashk_kernel, B2_BLOCK, nblk);
+  b2_groupby_hashk_kernel<<<grid, B2_BLOCK, 0, (cudaStream_t)stream>>>(*scan, ka, table_keys, table_nulls,
+                                                                        table_state, cap, aa, *st, d_flags);
+  B2_CHECK_LAUNCH("b2_groupby_hashk_kernel");
+  return B2_OK;
+}
+
+int32_t b2_dense_slots(const b2_col_t* key, int64_t n, int64_t kmin, int32_t null_slot, int32_t* out_slot,
+                       void* stream) {
+  B2_REQUIRE(key && out_slot, "null argument");
+  if (n <= 0) return B2_OK;
+  int grid = b2_wave_grid(b2_dense_slots_kernel, B2_BLOCK, (n + B2_BLOCK - 1) / B2_BLOCK);
+  b2_dense_slots_kernel<<<grid, B2_BLOCK, 0, (cudaStream_t)stream>>>(*key, n, kmin, null_slot, out_slot);
+  B2_CHECK_LAUNCH("b2_dense_slots_kernel");
+  return B2_OK;
+}
+
+int32_t b2_star_build_dense(const b2_col_t* pk, const int32_t* sel, int64_t n_sel, const int32_t* slot_of_row,
+                            int64_t kmin, int64_t range, int32_t* lookup, int32_t* d_flags, void* stream) {
+  B2_REQUIRE(pk && slot_of_row && lookup && d_flags, "null argument");
+  B2_REQUIRE(pk->dtype == B2_I64, "dense lookup needs an int64 key");
+  if (n_sel <= 0) return B2_OK;
+  int grid = b2_wave_grid(b2_star_build_dense_kernel, B2_BLOCK, (n_sel + B2_BLOCK - 1) / B2_BLOCK);
+  b2_star_build_dense_kernel<<<grid, B2_BLOCK, 0, (cudaStream_t)stream>>>(*pk, sel, n_sel, slot_of_row, kmin,
+                                                                           range, lookup, d_flags);
+  B2_CHECK_LAUNCH("b2_star_build_dense_kernel");
+  return B2_OK;
+}
+
+int32_t b2_star_build_hash(const b2_col_t* pk, const int32_t* sel, int64_t n_sel, const int32_t* slot_of_row,
+                           int64_t* table_keys, int32_t* table_slots, int64_t cap, int32_t* d_flags,
+                           void* stream) {
+  B2_REQUIRE(pk && slot_of_row && table_keys && table_slots && d_flags, "null argument");
+  B2_REQUIRE(pk->dtype == B2_I64, "star lookup needs an int64 key");
+  B2_REQUIRE(b2_pow2(cap), "cap must be a power of two");
+  if (n_sel <= 0) return B2_OK;
+  int grid = b2_wave_grid(b2_star_build_hash_kernel, B2_BLOCK, (n_sel + B2_BLOCK - 1) / B2_BLOCK);
+  b2_star_build_hash_kernel<<<grid, B2_BLOCK, 0, (cudaStream_t)stream>>>(*pk, sel, n_sel, slot_of_row, table_keys,
+                                                                          table_slots, cap, d_flags);
+  B2_CHECK_LAUNCH("b2_star_build_hash_kernel");
+  return B2_OK;
+}
+
+int32_t b2_star_agg(const b2_scan_t* scan, int32_t fk_col, const b2_starlookup_t* lk, const b2_agg_t* aggs,
+                    int32_t naggs, const b2_aggstate_t* st, void* stream) {
+  int32_t rc = b2_check_scan(scan);
+  if (rc) return rc;
+  b2_aggs_arg aa;
+  if ((rc = b2_check_aggs(scan, aggs, naggs, &aa))) return rc;
+  if ((rc = b2_check_state(aa, st))) return rc;
+  B2_REQUIRE(lk, "null lookup");
+  B2_REQUIRE(fk_col >= 0 && fk_col < scan->ncols, "fk column out of range");
+  B2_REQUIRE(scan->cols[fk_col].dtype == B2_I64, "fk must be int64");
+  if (lk->dense) B2_REQUIRE(lk->lookup && lk->range > 0, "bad dense lookup");
+  else B2_REQUIRE(lk->table_keys && lk->table_slots && b2_pow2(lk->cap), "bad hash lookup");
+  if (scan->n == 0) return B2_OK;
+  int64_t nblk = (scan->n + B2_GB_ROWS_PER_BLOCK - 1) / B2_GB_ROWS_PER_BLOCK;
+  int grid = b2_wave_grid(b2_star_agg_kernel, B2_BLOCK, nblk);
+  b2_star_agg_kernel<<<grid, B2_BLOCK, 0, (cudaStream_t)stream>>>(*scan, fk_col, *lk, aa, *st);
+  B2_CHECK_LAUNCH("b2_star_agg_kernel");
+  return B2_OK;
+}
+
+}  // extern "C"

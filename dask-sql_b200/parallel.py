@@ -1,0 +1,91 @@
+"""Multi-GPU plumbing: one process per GPU, torch.distributed (NCCL over NVLink/NVSwitch on
+GPUs, gloo in the CPU tests).  Only the two exchange steps of the path use it:
+
+  * join build side   : broadcast of the dimension table's columns from its owner rank
+                        (replaces dask's merge(broadcast=True), join.py:228-246)
+  * group-by partials : all-reduce of dense accumulator arrays, or a tree of pairwise
+                        send/recv + merge for hash tables, fan-in = sql.aggregate.split_every
+                        (replaces dask's tree reduction, aggregate.py:321,581)
+"""
+from typing import List, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def world() -> Tuple[int, int]:
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def shard_bounds(n: int, rank: int, size: int, align: int = 32) -> Tuple[int, int]:
+    """Contiguous row range of `rank` when n rows are sharded over `size` ranks; boundaries are
+    multiples of `align` rows so validity bitmaps split on word boundaries."""
+    per = -(-n // size)
+    per = (per + align - 1) // align * align
+    lo = min(n, rank * per)
+    hi = min(n, lo + per)
+    return lo, hi
+
+
+def allreduce_(t: torch.Tensor, op: str = "sum") -> torch.Tensor:
+    if world()[1] == 1:
+        return t
+    rop = {"sum": dist.ReduceOp.SUM, "min": dist.ReduceOp.MIN, "max": dist.ReduceOp.MAX}[op]
+    dist.all_reduce(t, op=rop)
+    return t
+
+
+def broadcast_(t: torch.Tensor, src: int = 0) -> torch.Tensor:
+    if world()[1] > 1:
+        dist.broadcast(t, src=src)
+    return t
+
+
+def broadcast_object(obj, src: int = 0):
+    if world()[1] == 1:
+        return obj
+    box = [obj]
+    dist.broadcast_object_list(box, src=src)
+    return box[0]
+
+
+def tree_rounds(size: int, fan_in: int = 2) -> List[List[Tuple[int, int]]]:
+    """Merge schedule of a fan-in-`fan_in` reduction tree onto rank 0.
+    Returns rounds; each round is a list of (receiver, sender) pairs that can run concurrently.
+    With fan_in = split_every this mirrors dask's tree of partial-aggregate concatenations."""
+    fan_in = max(2, int(fan_in))
+    rounds = []
+    stride = 1
+    while stride < size:
+        pairs = []
+        group = stride * fan_in
+        for base in range(0, size, group):
+            for k in range(1, fan_in):
+                s = base + k * stride
+                if s < size:
+                    pairs.append((base, s))
+        # senders within one group target the same receiver: serialise them into sub-rounds
+        sub = {}
+        for r, s in pairs:
+            sub.setdefault(r, []).append(s)
+        depth = max(len(v) for v in sub.values())
+        for d in range(depth):
+            rounds.append([(r, v[d]) for r, v in sub.items() if d < len(v)])
+        stride = group
+    return rounds
+
+
+def send_tensors(tensors: Sequence[torch.Tensor], dst: int):
+    for t in tensors:
+        dist.send(t.contiguous(), dst=dst)
+
+
+def recv_tensors(shapes_dtypes, src: int, device) -> List[torch.Tensor]:
+    out = []
+    for shape, dtype in shapes_dtypes:
+        t = torch.empty(shape, dtype=dtype, device=device)
+        dist.recv(t, src=src)
+        out.append(t)
+    return out

@@ -1,0 +1,329 @@
+/*
+ * b200sql.h — C-ABI of libb200sql.so: the B200-native (sm_100a) execution kernels
+ * behind dask-sql's filter -> hash-join -> hash-groupby-aggregate hot path.
+ *
+ * The reference (dask-contrib/dask-sql @ f186de3) has no FFI of its own for this
+ * path: its plugins call pandas / dask.dataframe methods.  Each entry point below
+ * therefore names the reference call site(s) whose per-partition arithmetic it
+ * replaces (paths relative to /root/reference).  The Python plugins in
+ * dask-sql_b200/physical/ reach these functions through ctypes (dask-sql_b200/_lib.py);
+ * INTEGRATION.md shows the binding a dask-sql maintainer would add.
+ *
+ * Conventions
+ *  - every function returns int32 status: 0 = OK, <0 = error; text via b2_last_error().
+ *  - no C++ exceptions, no torch types; plain pointers and sizes only.
+ *  - all data pointers are DEVICE pointers owned by the caller, 16-byte aligned
+ *    (value buffers) unless stated otherwise.  The library never allocates device memory.
+ *  - validity bitmaps are Arrow layout (LSB bit order, 1 = valid); NULL pointer = all valid.
+ *    For B2_F64 columns NaN additionally counts as NULL wherever pandas treats it so
+ *    (isna, join keys, group keys, aggregate inputs) but NOT in comparisons (IEEE).
+ *  - `stream` is a cudaStream_t passed as void*; every call is asynchronous with respect to
+ *    the host and writes results to device memory.  b2_d2h()/b2_sync() are the sync points.
+ *  - row indices are int32 (a partition holds < 2^31 rows); -1 means "no row" (NULL fill).
+ *  - thread-safe across distinct streams.
+ */
+#ifndef B200SQL_H
+#define B200SQL_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2_OK            0
+#define B2_ERR_CUDA     -1
+#define B2_ERR_ARG      -2
+
+/* physical column types */
+#define B2_I64 0   /* int64  (BIGINT and narrower ints, widened at ingest) */
+#define B2_F64 1   /* float64 (DOUBLE) */
+#define B2_U8  2   /* boolean, one byte per row (0/1) */
+
+#define B2_MAX_COLS   16
+#define B2_MAX_TERMS   8
+#define B2_MAX_AGGS    8
+#define B2_MAX_KEYS    4
+#define B2_MAX_GATHER  8
+#define B2_MAX_PROG   64
+#define B2_TILE     4096   /* rows per selection tile (b2_select_*, b2_join_*) */
+
+/* predicate term operators (b2_term_t.op) */
+#define B2_EQ 0
+#define B2_NE 1
+#define B2_LT 2
+#define B2_LE 3
+#define B2_GT 4
+#define B2_GE 5
+#define B2_IS_NULL     6
+#define B2_IS_NOT_NULL 7
+#define B2_IS_TRUE     8   /* column is a B2_U8 mask: pass iff valid and != 0 */
+
+/* aggregate operators (b2_agg_t.op) */
+#define B2_AGG_SUM    0   /* native type: int64 wraps (two's complement) / float64 */
+#define B2_AGG_SUMF   1   /* value converted to float64 before adding (AVG over ints) */
+#define B2_AGG_MIN    2
+#define B2_AGG_MAX    3
+#define B2_AGG_COUNT  4   /* only the non-null count is kept (acc may be NULL) */
+
+/* join flags */
+#define B2_JOIN_INNER        0
+#define B2_JOIN_LEFT         1   /* also emit unmatched probe rows with build index -1 */
+#define B2_JOIN_SEMI         2   /* emit each probe row once if it has >= 1 match (build index = -1) */
+#define B2_JOIN_ANTI         3   /* emit each probe row once if it has no match */
+
+/* empty-slot sentinel of int64 hash tables (b2_groupby_hash1, b2_star_build_hash) */
+#define B2_EMPTY_KEY ((int64_t)0x8000000000000000LL)
+
+typedef struct b2_col {
+  const void*    data;    /* int64_t* / double* / uint8_t* */
+  const uint8_t* valid;   /* Arrow validity bitmap or NULL */
+  int32_t        dtype;   /* B2_I64 / B2_F64 / B2_U8 */
+  int32_t        pad_;
+} b2_col_t;
+
+/* one conjunct of a pushed-down predicate:  cols[col] <op> literal */
+typedef struct b2_term {
+  int32_t col;
+  int32_t op;
+  int32_t as_f64;   /* compare as float64 (int column value is converted) */
+  int32_t pad_;
+  int64_t lit_i;
+  double  lit_f;
+} b2_term_t;
+
+/* a filtered scan of one partition: rows [0,n) of `cols` that satisfy ALL terms.
+ * Replaces DaskTableScanPlugin._apply_filters (physical/rel/logical/table_scan.py:80-119)
+ * and filter_or_scalar (physical/rel/logical/filter.py:20-45): a NULL predicate is False. */
+typedef struct b2_scan {
+  b2_col_t  cols[B2_MAX_COLS];
+  b2_term_t terms[B2_MAX_TERMS];
+  int32_t   ncols;
+  int32_t   nterms;
+  int64_t   n;
+} b2_scan_t;
+
+typedef struct b2_agg {
+  int32_t col;   /* input column in scan.cols; -1 = COUNT(*) */
+  int32_t op;
+} b2_agg_t;
+
+/* per-slot accumulators of a group table (caller-allocated, caller-initialised:
+ * SUM/COUNT arrays 0, MIN arrays INT64_MAX, MAX arrays INT64_MIN).
+ * float64 MIN/MAX accumulators hold the order-preserving int64 image of the double
+ * (see b2_f64_to_ordered in DESIGN.md); b2_ordered_to_f64() converts back. */
+typedef struct b2_aggstate {
+  void*     acc[B2_MAX_AGGS];   /* int64_t* or double*, [nslots]; NULL = not kept */
+  int64_t*  cnt[B2_MAX_AGGS];   /* non-null input count per slot; NULL = not kept */
+  int64_t*  rows;               /* rows per slot (COUNT(*)); NULL = not kept */
+  uint32_t* present;            /* presence bitmap over slots; NULL = not kept */
+  int32_t*  out_slot;           /* int32[n]: slot each input row landed in (-1 = filtered); NULL = not kept.
+                                   Turns the group-by kernels into a factorize (pandas groupby's first half). */
+} b2_aggstate_t;
+
+/* expression program (postfix) evaluated per row by b2_expr_eval.
+ * Replaces the per-operator pandas passes of RexCallPlugin.convert
+ * (physical/rex/core/call.py:1158-1216, OPERATION_MAPPING :1047-1062). */
+typedef struct b2_instr {
+  int32_t op;
+  int32_t a;       /* column index for LOAD */
+  int64_t imm_i;
+  double  imm_f;
+} b2_instr_t;
+
+typedef struct b2_prog {
+  b2_instr_t code[B2_MAX_PROG];
+  int32_t    n;
+  int32_t    out_dtype;   /* B2_I64 / B2_F64 / B2_U8 */
+} b2_prog_t;
+
+/* b2_instr_t.op */
+#define B2_OP_LOAD      0   /* push cols[a] (U8 pushed as int 0/1) */
+#define B2_OP_CONST_I   1
+#define B2_OP_CONST_F   2
+#define B2_OP_CONST_NULL 3
+#define B2_OP_I2F       4
+#define B2_OP_F2I       5   /* truncate toward zero */
+#define B2_OP_ADD_I    10
+#define B2_OP_SUB_I    11
+#define B2_OP_MUL_I    12
+#define B2_OP_DIV_I    13   /* SQL truncated division (call.py:165-189); x/0 -> NULL */
+#define B2_OP_NEG_I    14
+#define B2_OP_ABS_I    15
+#define B2_OP_MOD_I    16
+#define B2_OP_ADD_F    20
+#define B2_OP_SUB_F    21
+#define B2_OP_MUL_F    22
+#define B2_OP_DIV_F    23
+#define B2_OP_NEG_F    24
+#define B2_OP_ABS_F    25
+#define B2_OP_EQ_I     30   /* 30..35 = EQ NE LT LE GT GE on ints   */
+#define B2_OP_EQ_F     40   /* 40..45 = EQ NE LT LE GT GE on doubles (IEEE: NaN != x is true) */
+#define B2_OP_AND      50   /* Kleene */
+#define B2_OP_OR       51   /* Kleene */
+#define B2_OP_NOT      52
+#define B2_OP_ISNULL_I 53   /* -> never-null bool */
+#define B2_OP_ISNULL_F 54   /* NaN counts as NULL */
+#define B2_OP_CASE     55   /* pops else, then, cond: cond true -> then, else (or NULL cond) -> else */
+#define B2_OP_FILLNA   56   /* pops fill, x: x if valid else fill */
+#define B2_OP_ORD2F    57   /* order-preserving int64 image -> float64 (float MIN/MAX accumulators) */
+
+/* ---- runtime --------------------------------------------------------------------- */
+const char* b2_last_error(void);
+int32_t b2_version(void);
+/* sm count, L2 bytes, compute capability, total HBM bytes of `device` */
+int32_t b2_device_info(int32_t device, int32_t* sm_count, int64_t* l2_bytes,
+                       int32_t* cc_major, int32_t* cc_minor, int64_t* hbm_bytes);
+int32_t b2_d2h(void* host_dst, const void* dev_src, int64_t bytes, void* stream); /* copies then syncs stream */
+int32_t b2_sync(void* stream);
+/* number of B2_TILE tiles covering n rows */
+int64_t b2_num_tiles(int64_t n);
+
+/* ---- ingest ---------------------------------------------------------------------- */
+/* Column statistics computed once at Context.create_table (context.py:168-293 keeps only
+ * Statistics(row_count)); d_out = int64[4]: {min, max, null_count, n_nan}; min/max are the
+ * raw 64-bit pattern of the column type and cover non-null (non-NaN) values only.
+ * ws: device scratch of >= b2_stats_ws_bytes() bytes. */
+int64_t b2_stats_ws_bytes(void);
+int32_t b2_col_stats(const b2_col_t* col, int64_t n, int64_t* d_out, void* ws, void* stream);
+
+/* ---- expressions ----------------------------------------------------------------- */
+/* Evaluate `prog` for rows [0,n) of cols; writes out_data (type prog->out_dtype) and, when
+ * out_valid != NULL, the Arrow validity bitmap of the result ((n+31)/32 uint32 words). */
+int32_t b2_expr_eval(const b2_prog_t* prog, const b2_col_t* cols, int32_t ncols, int64_t n,
+                     void* out_data, uint32_t* out_valid, void* stream);
+
+/* ---- filter ---------------------------------------------------------------------- */
+/* Global (no GROUP BY) aggregates over a filtered scan, no survivor materialisation.
+ * Replaces df[cond] + groupby(<const col>).agg(...) of DaskAggregatePlugin._do_aggregations
+ * (physical/rel/logical/aggregate.py:288-375, constant-key trick :305-306,:576).
+ * d_out_acc: int64[naggs] raw 64-bit accumulators (int64, or double bits, or ordered-int64
+ * for float MIN/MAX); d_out_cnt: int64[naggs] non-null counts.  If `accumulate` != 0 the
+ * call combines into the existing outputs (next partition of the same table), otherwise it
+ * initialises them.  ws >= b2_scan_agg_ws_bytes(). */
+int64_t b2_scan_agg_ws_bytes(void);
+int32_t b2_scan_agg(const b2_scan_t* scan, const b2_agg_t* aggs, int32_t naggs,
+                    int64_t* d_out_acc, int64_t* d_out_cnt, int32_t accumulate,
+                    void* ws, void* stream);
+
+/* Order-preserving selection (df[cond], filter.py:39-40), two passes.
+ * b2_select_count: d_tile_off = int64[b2_num_tiles(n)+1]; on return d_tile_off[t] is the
+ * number of passing rows before tile t and d_tile_off[ntiles] the total.
+ * b2_select_write: writes the passing row ids to out_idx (may be NULL) and, for each of the
+ * ngather columns scan.cols[gather_cols[g]], the surviving values to out_data[g] and validity
+ * words to out_valid[g] (NULL = not needed; must be zero-initialised by the caller because
+ * bits are OR-ed in). */
+int32_t b2_select_count(const b2_scan_t* scan, int64_t* d_tile_off, void* stream);
+int32_t b2_select_write(const b2_scan_t* scan, const int64_t* d_tile_off, int32_t* out_idx,
+                        int32_t ngather, const int32_t* gather_cols, void* const* out_data,
+                        uint32_t* const* out_valid, void* stream);
+
+/* out[i] = col[idx[i]] (idx[i] == -1 -> NULL).  The take() at the end of pandas
+ * boolean indexing / merge (join.py:241-246).  out_valid: (n_idx+31)/32 words or NULL. */
+int32_t b2_gather(const b2_col_t* col, const int32_t* idx, int64_t n_idx,
+                  void* out_data, uint32_t* out_valid, void* stream);
+
+/* ---- group-by -------------------------------------------------------------------- */
+/* Dense (direct-address) group table: slot = key - kmin for kmin <= key <= kmax, NULL key
+ * -> slot nslots-1 (nslots = kmax-kmin+2).  Fused with the scan's predicate.
+ * Replaces groupby(by, dropna=False).agg(...) per partition (aggregate.py:575-581). */
+int32_t b2_groupby_dense(const b2_scan_t* scan, int32_t key_col, int64_t kmin, int64_t nslots,
+                         const b2_agg_t* aggs, int32_t naggs, const b2_aggstate_t* st,
+                         void* stream);
+
+/* Hash group table on ONE 64-bit key (int64, or float64 bits normalised -0.0 -> 0.0).
+ * table_keys = int64[cap+2] pre-filled with B2_EMPTY_KEY, cap a power of two; slot cap holds
+ * the NULL(/NaN) key group and slot cap+1 the group whose key equals B2_EMPTY_KEY.
+ * Accumulator arrays have cap+2 slots.  d_flags = int32[4]: [0] set to 1 if the table
+ * overflowed (caller retries with larger cap), [1] NULL-key group present, [2] sentinel-key
+ * group present. */
+int32_t b2_groupby_hash1(const b2_scan_t* scan, int32_t key_col, int64_t* table_keys,
+                         int64_t cap, const b2_agg_t* aggs, int32_t naggs,
+                         const b2_aggstate_t* st, int32_t* d_flags, void* stream);
+
+/* Hash group table on 1..B2_MAX_KEYS key columns of any type (NULL keys group together).
+ * table_keys = int64[nkeys*cap] key bit patterns, key k of slot h at [k*cap+h], table_nulls = uint8[cap] per-slot key-null
+ * mask, table_state = int32[cap] zero-initialised (0 empty, 1 being written, 2 ready). */
+int32_t b2_groupby_hashk(const b2_scan_t* scan, const int32_t* key_cols, int32_t nkeys,
+                         int64_t* table_keys, uint8_t* table_nulls, int32_t* table_state,
+                         int64_t cap, const b2_agg_t* aggs, int32_t naggs,
+                         const b2_aggstate_t* st, int32_t* d_flags, void* stream);
+
+/* bit-exact order-preserving double<->int64 images used by float MIN/MAX accumulators */
+int64_t b2_f64_to_ordered(double x);
+double  b2_ordered_to_f64(int64_t k);
+
+/* ---- hash join ------------------------------------------------------------------- */
+/* Chained hash table over the build side's key columns: head = int32[cap] pre-filled with
+ * -1 (cap a power of two), next = int32[n].  Rows with a NULL/NaN key are skipped
+ * (join.py:202-213).  Replaces the factorize half of pandas.merge (join.py:241-246). */
+int32_t b2_join_build(const b2_col_t* keys, int32_t nkeys, int64_t n,
+                      int32_t* head, int32_t* next, int64_t cap, void* stream);
+
+/* Direct-address table for a single int64 key: lookup = int32[range] pre-filled with -1,
+ * lookup[key-kmin] = row.  d_flags[0] is set to 1 if two rows share a key (caller falls
+ * back to b2_join_build). */
+int32_t b2_join_build_dense(const b2_col_t* key, int64_t n, int64_t kmin, int64_t range,
+                            int32_t* lookup, int32_t* d_flags, void* stream);
+
+typedef struct b2_jointable {
+  b2_col_t  keys[B2_MAX_KEYS];  /* build-side key columns */
+  int32_t   nkeys;
+  int32_t   dense;              /* 0 = chained (head/next/cap), 1 = direct (lookup/kmin/range) */
+  const int32_t* head;
+  const int32_t* next;
+  int64_t   cap;
+  const int32_t* lookup;
+  int64_t   kmin;
+  int64_t   range;
+} b2_jointable_t;
+
+/* Probe with the rows of `scan` that pass its terms; probe_keys index scan.cols.
+ * Same two-pass protocol as b2_select_*: count fills d_tile_off (int64[ntiles+1], exclusive
+ * scan, total last), write emits (probe row, build row) pairs in probe-row order.
+ * mode = B2_JOIN_*.  build_matched (uint8[n_build], may be NULL) is set to 1 for every build
+ * row that found a partner (RIGHT / FULL joins, join.py:41-48). */
+int32_t b2_join_count(const b2_scan_t* scan, const int32_t* probe_keys, const b2_jointable_t* jt,
+                      int32_t mode, int64_t* d_tile_off, void* stream);
+int32_t b2_join_write(const b2_scan_t* scan, const int32_t* probe_keys, const b2_jointable_t* jt,
+                      int32_t mode, const int64_t* d_tile_off, int32_t* out_probe_idx,
+                      int32_t* out_build_idx, uint8_t* build_matched, void* stream);
+
+/* ---- fused filter -> join -> group-by (star pipeline) ----------------------------- */
+/* out_slot[i] = key[i]-kmin (NULL key -> null_slot) as int32: turns a dense group-key column of
+ * the build side into group-table slot numbers. */
+int32_t b2_dense_slots(const b2_col_t* key, int64_t n, int64_t kmin, int32_t null_slot,
+                       int32_t* out_slot, void* stream);
+
+/* Build the join->group lookup of the fused pipeline from the (already filtered) build side:
+ * for build row r = sel ? sel[i] : i, lookup[pk[r]-kmin] = slot_of_row[i].  Dense variant;
+ * d_flags[0] = 1 on duplicate pk. */
+int32_t b2_star_build_dense(const b2_col_t* pk, const int32_t* sel, int64_t n_sel,
+                            const int32_t* slot_of_row, int64_t kmin, int64_t range,
+                            int32_t* lookup, int32_t* d_flags, void* stream);
+/* Hash variant: table_keys = int64[cap] pre-filled with B2_EMPTY_KEY, table_slots = int32[cap].
+ * d_flags[0] = 1 on duplicate pk, d_flags[1] = 1 on overflow. */
+int32_t b2_star_build_hash(const b2_col_t* pk, const int32_t* sel, int64_t n_sel,
+                           const int32_t* slot_of_row, int64_t* table_keys, int32_t* table_slots,
+                           int64_t cap, int32_t* d_flags, void* stream);
+
+typedef struct b2_starlookup {
+  int32_t dense;
+  int32_t pad_;
+  const int32_t* lookup;   /* dense: int32[range], -1 = no partner */
+  int64_t kmin;
+  int64_t range;
+  const int64_t* table_keys;  /* hash */
+  const int32_t* table_slots;
+  int64_t cap;
+} b2_starlookup_t;
+
+/* One pass over the probe (fact) partition: predicate -> key lookup -> aggregate into the
+ * group slot of the matching build row.  Replaces, fused, table_scan.py:80-119 +
+ * join.py:189-248 + aggregate.py:522-589 for plans of the shape
+ *   Aggregate(group by build cols; aggs over probe cols) <- Inner Join(fk = unique pk). */
+int32_t b2_star_agg(const b2_scan_t* scan, int32_t fk_col, const b2_starlookup_t* lk,
+                    const b2_agg_t* aggs, int32_t naggs, const b2_aggstate_t* st, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200SQL_H */
