@@ -1,5 +1,11 @@
 // common.cuh — shared device helpers for libb200sql (sm_100a).
 // Everything here is hand-written CUDA; no CUB/Thrust/cuDF.
+//
+// Design rule learnt from the first ncu capture (profiles/r01_first_capture.md): these kernels
+// are HBM-bound only if the per-row instruction count stays small.  All run-time dispatch
+// (operator, column type, nullable or not) therefore happens ONCE PER BATCH of R rows per lane
+// (`switch` outside), and the unrolled per-row loops inside are template instances with
+// compile-time operator/type and immediate-offset addressing.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -69,7 +75,7 @@ __device__ __forceinline__ bool b2_bit(const uint8_t* __restrict__ bm, int64_t i
   return (bm[i >> 3] >> (i & 7)) & 1;
 }
 
-// L2 eviction policies (sm_80+ createpolicy; plain ld only takes .L2::evict_* on 256-bit vectors).
+// L2 eviction policies (createpolicy; plain ld only takes .L2::evict_* on 256-bit vectors).
 // Non-volatile asm without inputs: the compiler hoists/CSEs it, one instruction per kernel.
 __device__ __forceinline__ uint64_t b2_policy_stream() {
   uint64_t p;
@@ -81,11 +87,12 @@ __device__ __forceinline__ uint64_t b2_policy_keep() {
   asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
   return p;
 }
-// streaming 8-byte load: read-only path, do not pollute L1, first-out of L2 so that the
-// L2-resident lookup / group tables survive the scan.
+// streaming 8-byte load: read-only path, first-out of L2 so that the L2-resident lookup / group
+// tables survive the scan.  (L1 allocation is left on: a column that is both a predicate and an
+// aggregate input is re-read a few instructions later and should hit L1.)
 __device__ __forceinline__ int64_t b2_ld_stream(const int64_t* p) {
   int64_t v;
-  asm("ld.global.nc.L1::no_allocate.L2::cache_hint.b64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(b2_policy_stream()));
+  asm("ld.global.nc.L2::cache_hint.b64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(b2_policy_stream()));
   return v;
 }
 // table load that should stay in L2
@@ -102,6 +109,7 @@ __host__ __device__ __forceinline__ int64_t b2_ordered_from_bits(int64_t b) {
   return b ^ ((b >> 63) & 0x7fffffffffffffffLL);
 }
 
+// run-time comparators: used only by the per-row interpreter (expr.cuh), never in scan loops
 __device__ __forceinline__ bool b2_cmp_i(int op, int64_t a, int64_t b) {
   switch (op) {
     case B2_EQ: return a == b;
@@ -122,8 +130,18 @@ __device__ __forceinline__ bool b2_cmp_f(int op, double a, double b) {
     default: return a >= b;
   }
 }
+// compile-time comparators for the scan loops
+template <int OP, class T>
+__device__ __forceinline__ bool b2_cmp_t(T a, T b) {
+  if (OP == B2_EQ) return a == b;
+  if (OP == B2_NE) return a != b;
+  if (OP == B2_LT) return a < b;
+  if (OP == B2_LE) return a <= b;
+  if (OP == B2_GT) return a > b;
+  return a >= b;
+}
 
-// raw 64-bit load of any column type (U8 widened to 0/1)
+// raw 64-bit load of any column type (U8 widened to 0/1); per-row helper for non-hot paths
 __device__ __forceinline__ int64_t b2_load_raw(const b2_col_t& c, int64_t row) {
   if (c.dtype == B2_U8) return (int64_t) reinterpret_cast<const uint8_t*>(c.data)[row];
   return b2_ld_stream(reinterpret_cast<const int64_t*>(c.data) + row);
@@ -135,95 +153,201 @@ __device__ __forceinline__ bool b2_is_null(const b2_col_t& c, int64_t row, int64
   return false;
 }
 
-// Evaluate all predicate terms for R rows of one lane: rows row0 + j*32, j < R.
-// Returns a bitmask (bit j = row j passes).  Loads of one term are issued back-to-back
-// (R independent 8-byte loads in flight per lane) before they are consumed.
+// ---------------------------------------------------------------------------------------
+// batch helpers.  A "batch" is R rows of one lane: rows row0 + 32*j, j < R.  `bits` has bit j
+// set for the rows that are (still) live.  When the whole warp batch is in bounds (`full`),
+// loads are unconditional with immediate offsets.
+// ---------------------------------------------------------------------------------------
 template <int R>
-__device__ __forceinline__ uint32_t b2_eval_terms(const b2_scan_t& s, int64_t row0) {
+__device__ __forceinline__ uint32_t b2_bounds_bits(int64_t row0, int64_t n, bool& full) {
+  full = row0 + (int64_t)(R - 1) * 32 < n;   // lane-local; callers use it only for load predication
+  if (full) return (R == 32) ? 0xffffffffu : ((1u << R) - 1u);
   uint32_t bits = 0;
 #pragma unroll
   for (int j = 0; j < R; ++j)
-    if (row0 + (int64_t)j * 32 < s.n) bits |= 1u << j;
+    if (row0 + (int64_t)j * 32 < n) bits |= 1u << j;
+  return bits;
+}
+
+// load R raw 64-bit values of a 64-bit column
+template <int R>
+__device__ __forceinline__ void b2_load_batch64(const void* data, int64_t row0, uint32_t bits, bool full,
+                                                int64_t (&raw)[R]) {
+  const int64_t* p = reinterpret_cast<const int64_t*>(data) + row0;
+  if (full) {
+#pragma unroll
+    for (int j = 0; j < R; ++j) raw[j] = b2_ld_stream(p + j * 32);
+  } else {
+#pragma unroll
+    for (int j = 0; j < R; ++j) raw[j] = (bits >> j) & 1 ? b2_ld_stream(p + j * 32) : 0;
+  }
+}
+template <int R>
+__device__ __forceinline__ void b2_load_batch8(const void* data, int64_t row0, uint32_t bits, bool full,
+                                               int64_t (&raw)[R]) {
+  const uint8_t* p = reinterpret_cast<const uint8_t*>(data) + row0;
+#pragma unroll
+  for (int j = 0; j < R; ++j) raw[j] = (full || ((bits >> j) & 1)) ? (int64_t)p[j * 32] : 0;
+}
+template <int R>
+__device__ __forceinline__ void b2_load_batch(const b2_col_t& c, int64_t row0, uint32_t bits, bool full,
+                                              int64_t (&raw)[R]) {
+  if (c.dtype == B2_U8) b2_load_batch8<R>(c.data, row0, bits, full, raw);
+  else b2_load_batch64<R>(c.data, row0, bits, full, raw);
+}
+
+// validity bits of the batch (bit j = row j valid).  Bitmap bytes: row0+32j -> byte (row0>>3)+4j
+template <int R>
+__device__ __forceinline__ uint32_t b2_valid_bits(const uint8_t* __restrict__ valid, int64_t row0, uint32_t bits) {
+  const uint8_t* p = valid + (row0 >> 3);
+  const int sh = (int)(row0 & 7);
+  uint32_t v = 0;
+#pragma unroll
+  for (int j = 0; j < R; ++j)
+    if ((bits >> j) & 1) v |= (uint32_t)((p[j * 4] >> sh) & 1) << j;
+  return v;
+}
+// NULL bits of a batch in the pandas sense (bitmap, plus NaN for float columns)
+template <int R>
+__device__ __forceinline__ uint32_t b2_null_bits(const b2_col_t& c, int64_t row0, uint32_t bits,
+                                                 const int64_t (&raw)[R]) {
+  uint32_t nul = 0;
+  if (c.valid) nul = bits & ~b2_valid_bits<R>(c.valid, row0, bits);
+  if (c.dtype == B2_F64) {
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      const double d = __longlong_as_double(raw[j]);
+      nul |= (uint32_t)(d != d) << j;
+    }
+    nul &= bits;
+  }
+  return nul;
+}
+
+template <int R, int OP, int KIND>  // KIND 0: int64 compare, 1: float64 column, 2: int column compared as float64
+__device__ __forceinline__ uint32_t b2_cmp_batch(const int64_t (&raw)[R], int64_t lit_i, double lit_f) {
+  uint32_t ok = 0;
+#pragma unroll
+  for (int j = 0; j < R; ++j) {
+    bool r;
+    if (KIND == 0) r = b2_cmp_t<OP, int64_t>(raw[j], lit_i);
+    else if (KIND == 1) r = b2_cmp_t<OP, double>(__longlong_as_double(raw[j]), lit_f);
+    else r = b2_cmp_t<OP, double>((double)raw[j], lit_f);
+    ok |= (uint32_t)r << j;
+  }
+  return ok;
+}
+template <int R, int KIND>
+__device__ __forceinline__ uint32_t b2_cmp_dispatch(int op, const int64_t (&raw)[R], int64_t lit_i, double lit_f) {
+  switch (op) {
+    case B2_EQ: return b2_cmp_batch<R, B2_EQ, KIND>(raw, lit_i, lit_f);
+    case B2_NE: return b2_cmp_batch<R, B2_NE, KIND>(raw, lit_i, lit_f);
+    case B2_LT: return b2_cmp_batch<R, B2_LT, KIND>(raw, lit_i, lit_f);
+    case B2_LE: return b2_cmp_batch<R, B2_LE, KIND>(raw, lit_i, lit_f);
+    case B2_GT: return b2_cmp_batch<R, B2_GT, KIND>(raw, lit_i, lit_f);
+    default: return b2_cmp_batch<R, B2_GE, KIND>(raw, lit_i, lit_f);
+  }
+}
+
+// Evaluate all predicate terms for the batch at row0.  Returns the surviving row bits and
+// whether the batch is fully in bounds.
+template <int R>
+__device__ __forceinline__ uint32_t b2_eval_terms(const b2_scan_t& s, int64_t row0, bool& full) {
+  uint32_t bits = b2_bounds_bits<R>(row0, s.n, full);
   for (int t = 0; t < s.nterms; ++t) {
     const b2_term_t& tm = s.terms[t];
     const b2_col_t& c = s.cols[tm.col];
-    int64_t raw[R];
-    if (c.dtype == B2_U8) {
-      const uint8_t* p = reinterpret_cast<const uint8_t*>(c.data);
-#pragma unroll
-      for (int j = 0; j < R; ++j) raw[j] = (bits >> j) & 1 ? (int64_t)p[row0 + (int64_t)j * 32] : 0;
-    } else {
-      const int64_t* p = reinterpret_cast<const int64_t*>(c.data);
-#pragma unroll
-      for (int j = 0; j < R; ++j) raw[j] = (bits >> j) & 1 ? b2_ld_stream(p + row0 + (int64_t)j * 32) : 0;
-    }
-    uint32_t ok = 0;
     const int op = tm.op;
+    int64_t raw[R];
+    b2_load_batch<R>(c, row0, bits, full, raw);
+    uint32_t ok;
     if (op == B2_IS_NULL || op == B2_IS_NOT_NULL) {
-#pragma unroll
-      for (int j = 0; j < R; ++j) {
-        if ((bits >> j) & 1) {
-          bool isn = b2_is_null(c, row0 + (int64_t)j * 32, raw[j]);
-          ok |= (uint32_t)(isn == (op == B2_IS_NULL)) << j;
-        }
-      }
+      const uint32_t nul = b2_null_bits<R>(c, row0, bits, raw);
+      ok = op == B2_IS_NULL ? nul : ~nul;
     } else {
-      uint32_t vbits = bits;
-      if (c.valid) {
-#pragma unroll
-        for (int j = 0; j < R; ++j)
-          if (((bits >> j) & 1) && !b2_bit(c.valid, row0 + (int64_t)j * 32)) vbits &= ~(1u << j);
-      }
       if (op == B2_IS_TRUE) {
+        ok = 0;
 #pragma unroll
         for (int j = 0; j < R; ++j) ok |= (uint32_t)(raw[j] != 0) << j;
       } else if (c.dtype == B2_F64) {
-        const double lit = tm.lit_f;
-#pragma unroll
-        for (int j = 0; j < R; ++j) ok |= (uint32_t)b2_cmp_f(op, __longlong_as_double(raw[j]), lit) << j;
+        ok = b2_cmp_dispatch<R, 1>(op, raw, tm.lit_i, tm.lit_f);
       } else if (tm.as_f64) {
-        const double lit = tm.lit_f;
-#pragma unroll
-        for (int j = 0; j < R; ++j) ok |= (uint32_t)b2_cmp_f(op, (double)raw[j], lit) << j;
+        ok = b2_cmp_dispatch<R, 2>(op, raw, tm.lit_i, tm.lit_f);
       } else {
-        const int64_t lit = tm.lit_i;
-#pragma unroll
-        for (int j = 0; j < R; ++j) ok |= (uint32_t)b2_cmp_i(op, raw[j], lit) << j;
+        ok = b2_cmp_dispatch<R, 0>(op, raw, tm.lit_i, tm.lit_f);
       }
-      ok &= vbits;
+      if (c.valid) ok &= b2_valid_bits<R>(c.valid, row0, bits);
     }
     bits &= ok;
   }
   return bits;
 }
+template <int R>
+__device__ __forceinline__ uint32_t b2_eval_terms(const b2_scan_t& s, int64_t row0) {
+  bool full;
+  return b2_eval_terms<R>(s, row0, full);
+}
 
 // ---------------------------------------------------------------------------------------
-// aggregate updates
+// aggregate updates into group tables (global-memory atomics)
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ void b2_atomic_update(int op, int dtype, void* acc, int64_t slot, int64_t raw) {
-  if (op == B2_AGG_SUM) {
-    if (dtype == B2_F64)
-      atomicAdd(reinterpret_cast<double*>(acc) + slot, __longlong_as_double(raw));
-    else
-      atomicAdd(reinterpret_cast<unsigned long long*>(acc) + slot, (unsigned long long)raw);
-  } else if (op == B2_AGG_SUMF) {
-    double d = dtype == B2_F64 ? __longlong_as_double(raw) : (double)raw;
-    atomicAdd(reinterpret_cast<double*>(acc) + slot, d);
-  } else if (op == B2_AGG_MIN) {
-    long long v = dtype == B2_F64 ? b2_ordered_from_bits(raw) : raw;
-    atomicMin(reinterpret_cast<long long*>(acc) + slot, v);
-  } else if (op == B2_AGG_MAX) {
-    long long v = dtype == B2_F64 ? b2_ordered_from_bits(raw) : raw;
-    atomicMax(reinterpret_cast<long long*>(acc) + slot, v);
+// accumulator kinds: op x input type, resolved once per batch
+#define B2_K_SUM_I   0
+#define B2_K_SUM_F   1   // SUM of float64, and SUMF of float64
+#define B2_K_SUMF_I  2   // int converted to float64, then added
+#define B2_K_MIN_I   3
+#define B2_K_MAX_I   4
+#define B2_K_MIN_F   5   // ordered-int64 image
+#define B2_K_MAX_F   6
+#define B2_K_NONE    7   // COUNT only
+
+__device__ __forceinline__ int b2_agg_kind(int op, int dtype) {
+  const bool f = dtype == B2_F64;
+  switch (op) {
+    case B2_AGG_SUM: return f ? B2_K_SUM_F : B2_K_SUM_I;
+    case B2_AGG_SUMF: return f ? B2_K_SUM_F : B2_K_SUMF_I;
+    case B2_AGG_MIN: return f ? B2_K_MIN_F : B2_K_MIN_I;
+    case B2_AGG_MAX: return f ? B2_K_MAX_F : B2_K_MAX_I;
+    default: return B2_K_NONE;
   }
 }
 
-// For R rows of one lane with resolved slots (slot < 0 = row does not contribute):
-// load each aggregate's input column (batched), skip NULLs, apply atomics.
+template <int KIND>
+__device__ __forceinline__ void b2_atomic_k(void* acc, int64_t slot, int64_t raw) {
+  if (KIND == B2_K_SUM_I) atomicAdd(reinterpret_cast<unsigned long long*>(acc) + slot, (unsigned long long)raw);
+  else if (KIND == B2_K_SUM_F) atomicAdd(reinterpret_cast<double*>(acc) + slot, __longlong_as_double(raw));
+  else if (KIND == B2_K_SUMF_I) atomicAdd(reinterpret_cast<double*>(acc) + slot, (double)raw);
+  else if (KIND == B2_K_MIN_I) atomicMin(reinterpret_cast<long long*>(acc) + slot, (long long)raw);
+  else if (KIND == B2_K_MAX_I) atomicMax(reinterpret_cast<long long*>(acc) + slot, (long long)raw);
+  else if (KIND == B2_K_MIN_F) atomicMin(reinterpret_cast<long long*>(acc) + slot, (long long)b2_ordered_from_bits(raw));
+  else if (KIND == B2_K_MAX_F) atomicMax(reinterpret_cast<long long*>(acc) + slot, (long long)b2_ordered_from_bits(raw));
+}
+
+template <int R, int KIND>
+__device__ __forceinline__ void b2_atomic_batch(void* acc, int64_t* cnt, const int64_t (&slot)[R],
+                                                const int64_t (&raw)[R], uint32_t live) {
+#pragma unroll
+  for (int j = 0; j < R; ++j) {
+    if (!((live >> j) & 1)) continue;
+    if (KIND != B2_K_NONE) b2_atomic_k<KIND>(acc, slot[j], raw[j]);
+    if (cnt) atomicAdd(reinterpret_cast<unsigned long long*>(cnt) + slot[j], 1ULL);
+  }
+}
+
+struct b2_aggs_arg {  // aggs passed by value in kernel params
+  b2_agg_t a[B2_MAX_AGGS];
+  int32_t n;
+};
+
+// For the batch at row0 with resolved slots (slot < 0 = row does not contribute): per aggregate,
+// load its input column for the contributing rows, drop NULLs, apply the atomics.
 template <int R>
 __device__ __forceinline__ void b2_apply_aggs(const b2_scan_t& s, const b2_agg_t* __restrict__ aggs,
                                               int naggs, const b2_aggstate_t& st, int64_t row0,
                                               const int64_t (&slot)[R]) {
+  uint32_t live = 0;
+#pragma unroll
+  for (int j = 0; j < R; ++j) live |= (uint32_t)(slot[j] >= 0) << j;
   if (st.out_slot) {
 #pragma unroll
     for (int j = 0; j < R; ++j)
@@ -232,13 +356,13 @@ __device__ __forceinline__ void b2_apply_aggs(const b2_scan_t& s, const b2_agg_t
   if (st.rows) {
 #pragma unroll
     for (int j = 0; j < R; ++j)
-      if (slot[j] >= 0) atomicAdd(reinterpret_cast<unsigned long long*>(st.rows) + slot[j], 1ULL);
+      if ((live >> j) & 1) atomicAdd(reinterpret_cast<unsigned long long*>(st.rows) + slot[j], 1ULL);
   }
   if (st.present) {
 #pragma unroll
     for (int j = 0; j < R; ++j)
-      if (slot[j] >= 0) {
-        uint32_t w = (uint32_t)(slot[j] >> 5), b = 1u << (slot[j] & 31);
+      if ((live >> j) & 1) {
+        const uint32_t w = (uint32_t)(slot[j] >> 5), b = 1u << (slot[j] & 31);
         // read first: after warm-up almost every group is already marked, so the atomic is rare
         if (!(__ldcg(st.present + w) & b)) atomicOr(st.present + w, b);
       }
@@ -248,21 +372,21 @@ __device__ __forceinline__ void b2_apply_aggs(const b2_scan_t& s, const b2_agg_t
     if (ag.col < 0) continue;  // COUNT(*) is st.rows
     const b2_col_t& c = s.cols[ag.col];
     int64_t raw[R];
-#pragma unroll
-    for (int j = 0; j < R; ++j) raw[j] = slot[j] >= 0 ? b2_load_raw(c, row0 + (int64_t)j * 32) : 0;
+    b2_load_batch<R>(c, row0, live, false, raw);
+    uint32_t ok = live;
+    if (c.valid || c.dtype == B2_F64) ok &= ~b2_null_bits<R>(c, row0, live, raw);
     void* acc = st.acc[a];
     int64_t* cnt = st.cnt[a];
-#pragma unroll
-    for (int j = 0; j < R; ++j) {
-      if (slot[j] < 0) continue;
-      if (b2_is_null(c, row0 + (int64_t)j * 32, raw[j])) continue;
-      if (acc) b2_atomic_update(ag.op, c.dtype, acc, slot[j], raw[j]);
-      if (cnt) atomicAdd(reinterpret_cast<unsigned long long*>(cnt) + slot[j], 1ULL);
+    const int kind = acc ? b2_agg_kind(ag.op, c.dtype) : B2_K_NONE;
+    switch (kind) {
+      case B2_K_SUM_I: b2_atomic_batch<R, B2_K_SUM_I>(acc, cnt, slot, raw, ok); break;
+      case B2_K_SUM_F: b2_atomic_batch<R, B2_K_SUM_F>(acc, cnt, slot, raw, ok); break;
+      case B2_K_SUMF_I: b2_atomic_batch<R, B2_K_SUMF_I>(acc, cnt, slot, raw, ok); break;
+      case B2_K_MIN_I: b2_atomic_batch<R, B2_K_MIN_I>(acc, cnt, slot, raw, ok); break;
+      case B2_K_MAX_I: b2_atomic_batch<R, B2_K_MAX_I>(acc, cnt, slot, raw, ok); break;
+      case B2_K_MIN_F: b2_atomic_batch<R, B2_K_MIN_F>(acc, cnt, slot, raw, ok); break;
+      case B2_K_MAX_F: b2_atomic_batch<R, B2_K_MAX_F>(acc, cnt, slot, raw, ok); break;
+      default: b2_atomic_batch<R, B2_K_NONE>(acc, cnt, slot, raw, ok); break;
     }
   }
 }
-
-struct b2_aggs_arg {  // aggs passed by value in kernel params
-  b2_agg_t a[B2_MAX_AGGS];
-  int32_t n;
-};

@@ -34,68 +34,80 @@ __device__ __forceinline__ int64_t b2_identity(int op) {
   return 0;  // +0.0 has the same bit pattern
 }
 
+// per-lane combine of one batch into a running accumulator, compile-time kind
+template <int R, int KIND>
+__device__ __forceinline__ int64_t b2_fold_batch(int64_t acc, const int64_t (&raw)[R], uint32_t ok) {
+#pragma unroll
+  for (int j = 0; j < R; ++j) {
+    if (!((ok >> j) & 1)) continue;
+    if (KIND == B2_K_SUM_I) acc = (int64_t)((uint64_t)acc + (uint64_t)raw[j]);
+    else if (KIND == B2_K_SUM_F) acc = __double_as_longlong(__longlong_as_double(acc) + __longlong_as_double(raw[j]));
+    else if (KIND == B2_K_SUMF_I) acc = __double_as_longlong(__longlong_as_double(acc) + (double)raw[j]);
+    else if (KIND == B2_K_MIN_I) acc = raw[j] < acc ? raw[j] : acc;
+    else if (KIND == B2_K_MAX_I) acc = raw[j] > acc ? raw[j] : acc;
+    else if (KIND == B2_K_MIN_F) { const int64_t v = b2_ordered_from_bits(raw[j]); acc = v < acc ? v : acc; }
+    else if (KIND == B2_K_MAX_F) { const int64_t v = b2_ordered_from_bits(raw[j]); acc = v > acc ? v : acc; }
+  }
+  return acc;
+}
+
+// Accumulators live in shared memory, one slot per (aggregate, thread): the aggregate loop is a
+// run-time loop (no 8-way unrolled register file), the kind switch sits outside the row loop.
 __global__ void __launch_bounds__(B2_BLOCK)
 b2_scan_agg_kernel(const __grid_constant__ b2_scan_t s, const __grid_constant__ b2_aggs_arg aggs,
                    b2_partial* __restrict__ partials) {
-  int64_t acc[B2_MAX_AGGS];
-  int64_t cnt[B2_MAX_AGGS];
-#pragma unroll
-  for (int a = 0; a < B2_MAX_AGGS; ++a) {
-    acc[a] = a < aggs.n ? b2_identity(aggs.a[a].op) : 0;
-    cnt[a] = 0;
+  __shared__ int64_t sh_acc[B2_MAX_AGGS][B2_BLOCK];
+  __shared__ int32_t sh_cnt[B2_MAX_AGGS][B2_BLOCK];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int a = 0; a < aggs.n; ++a) {
+    sh_acc[a][tid] = b2_identity(aggs.a[a].op);
+    sh_cnt[a][tid] = 0;
   }
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int64_t cnt64[1] = {0};
+  (void)cnt64;
   for (int64_t base = (int64_t)blockIdx.x * B2_AGG_ROWS_PER_BLOCK; base < s.n;
        base += (int64_t)gridDim.x * B2_AGG_ROWS_PER_BLOCK) {
     const int64_t row0 = base + (int64_t)warp * (32 * B2_AGG_R) + lane;
-    const uint32_t bits = b2_eval_terms<B2_AGG_R>(s, row0);
-#pragma unroll
-    for (int a = 0; a < B2_MAX_AGGS; ++a) {
-      if (a >= aggs.n) break;
+    bool full;
+    const uint32_t bits = b2_eval_terms<B2_AGG_R>(s, row0, full);
+    for (int a = 0; a < aggs.n; ++a) {
       const b2_agg_t ag = aggs.a[a];
       if (ag.col < 0) {  // COUNT(*)
-        cnt[a] += __popc(bits);
+        sh_cnt[a][tid] += __popc(bits);
         continue;
       }
       const b2_col_t& c = s.cols[ag.col];
       int64_t raw[B2_AGG_R];
-#pragma unroll
-      for (int j = 0; j < B2_AGG_R; ++j)
-        raw[j] = (bits >> j) & 1 ? b2_load_raw(c, row0 + (int64_t)j * 32) : 0;
-#pragma unroll
-      for (int j = 0; j < B2_AGG_R; ++j) {
-        if (!((bits >> j) & 1)) continue;
-        if (b2_is_null(c, row0 + (int64_t)j * 32, raw[j])) continue;
-        ++cnt[a];
-        int64_t v = raw[j];
-        if (ag.op == B2_AGG_SUMF && c.dtype != B2_F64) v = __double_as_longlong((double)v);
-        if ((ag.op == B2_AGG_MIN || ag.op == B2_AGG_MAX) && c.dtype == B2_F64) v = b2_ordered_from_bits(v);
-        if (ag.op != B2_AGG_COUNT) acc[a] = b2_combine(ag.op, c.dtype, acc[a], v);
+      b2_load_batch<B2_AGG_R>(c, row0, bits, full, raw);
+      uint32_t ok = bits;
+      if (c.valid || c.dtype == B2_F64) ok &= ~b2_null_bits<B2_AGG_R>(c, row0, bits, raw);
+      sh_cnt[a][tid] += __popc(ok);
+      int64_t acc = sh_acc[a][tid];
+      switch (b2_agg_kind(ag.op, c.dtype)) {
+        case B2_K_SUM_I: acc = b2_fold_batch<B2_AGG_R, B2_K_SUM_I>(acc, raw, ok); break;
+        case B2_K_SUM_F: acc = b2_fold_batch<B2_AGG_R, B2_K_SUM_F>(acc, raw, ok); break;
+        case B2_K_SUMF_I: acc = b2_fold_batch<B2_AGG_R, B2_K_SUMF_I>(acc, raw, ok); break;
+        case B2_K_MIN_I: acc = b2_fold_batch<B2_AGG_R, B2_K_MIN_I>(acc, raw, ok); break;
+        case B2_K_MAX_I: acc = b2_fold_batch<B2_AGG_R, B2_K_MAX_I>(acc, raw, ok); break;
+        case B2_K_MIN_F: acc = b2_fold_batch<B2_AGG_R, B2_K_MIN_F>(acc, raw, ok); break;
+        case B2_K_MAX_F: acc = b2_fold_batch<B2_AGG_R, B2_K_MAX_F>(acc, raw, ok); break;
+        default: break;
       }
+      sh_acc[a][tid] = acc;
     }
-  }
-  // block reduction: shuffle within warps, then warp leaders through shared memory
-  __shared__ int64_t sh_acc[B2_WARPS][B2_MAX_AGGS];
-  __shared__ int64_t sh_cnt[B2_WARPS][B2_MAX_AGGS];
-#pragma unroll
-  for (int a = 0; a < B2_MAX_AGGS; ++a) {
-    if (a >= aggs.n) break;
-    const int op = aggs.a[a].op;
-    const int dt = aggs.a[a].col >= 0 ? s.cols[aggs.a[a].col].dtype : B2_I64;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      acc[a] = b2_combine(op, dt, acc[a], __shfl_xor_sync(FULL_MASK, acc[a], o));
-      cnt[a] += __shfl_xor_sync(FULL_MASK, cnt[a], o);
-    }
-    if (lane == 0) { sh_acc[warp][a] = acc[a]; sh_cnt[warp][a] = cnt[a]; }
   }
   __syncthreads();
-  if (threadIdx.x < aggs.n) {
-    const int a = threadIdx.x;
+  // block reduction in a fixed order: thread a folds the 256 per-thread slots of aggregate a.
+  // (int32 per-thread counts cannot overflow: a thread sees < 2^31 rows of a < 2^31-row partition)
+  if (tid < aggs.n) {
+    const int a = tid;
     const int op = aggs.a[a].op;
     const int dt = aggs.a[a].col >= 0 ? s.cols[aggs.a[a].col].dtype : B2_I64;
-    int64_t r = sh_acc[0][a], c = sh_cnt[0][a];
-    for (int w = 1; w < B2_WARPS; ++w) { r = b2_combine(op, dt, r, sh_acc[w][a]); c += sh_cnt[w][a]; }
+    int64_t r = b2_identity(op), c = 0;
+    for (int t = 0; t < B2_BLOCK; ++t) {
+      r = b2_combine(op, dt, r, sh_acc[a][t]);
+      c += sh_cnt[a][t];
+    }
     partials[blockIdx.x].acc[a] = r;
     partials[blockIdx.x].cnt[a] = c;
   }

@@ -19,11 +19,10 @@ b2_groupby_dense_kernel(const __grid_constant__ b2_scan_t s, int key_col, int64_
   for (int64_t base = (int64_t)blockIdx.x * B2_GB_ROWS_PER_BLOCK; base < s.n;
        base += (int64_t)gridDim.x * B2_GB_ROWS_PER_BLOCK) {
     const int64_t row0 = base + (int64_t)warp * (32 * B2_GB_R) + lane;
-    const uint32_t bits = b2_eval_terms<B2_GB_R>(s, row0);
+    bool full;
+    const uint32_t bits = b2_eval_terms<B2_GB_R>(s, row0, full);
     int64_t key[B2_GB_R];
-#pragma unroll
-    for (int j = 0; j < B2_GB_R; ++j)
-      key[j] = (bits >> j) & 1 ? b2_load_raw(kc, row0 + (int64_t)j * 32) : 0;
+    b2_load_batch<B2_GB_R>(kc, row0, bits, full, key);
     int64_t slot[B2_GB_R];
 #pragma unroll
     for (int j = 0; j < B2_GB_R; ++j) {
@@ -67,11 +66,10 @@ b2_groupby_hash1_kernel(const __grid_constant__ b2_scan_t s, int key_col, int64_
   for (int64_t base = (int64_t)blockIdx.x * B2_GB_ROWS_PER_BLOCK; base < s.n;
        base += (int64_t)gridDim.x * B2_GB_ROWS_PER_BLOCK) {
     const int64_t row0 = base + (int64_t)warp * (32 * B2_GB_R) + lane;
-    const uint32_t bits = b2_eval_terms<B2_GB_R>(s, row0);
+    bool full;
+    const uint32_t bits = b2_eval_terms<B2_GB_R>(s, row0, full);
     int64_t key[B2_GB_R];
-#pragma unroll
-    for (int j = 0; j < B2_GB_R; ++j)
-      key[j] = (bits >> j) & 1 ? b2_load_raw(kc, row0 + (int64_t)j * 32) : 0;
+    b2_load_batch<B2_GB_R>(kc, row0, bits, full, key);
     int64_t slot[B2_GB_R];
 #pragma unroll
     for (int j = 0; j < B2_GB_R; ++j) {
@@ -231,11 +229,10 @@ b2_star_agg_kernel(const __grid_constant__ b2_scan_t s, int fk_col, const __grid
   for (int64_t base = (int64_t)blockIdx.x * B2_GB_ROWS_PER_BLOCK; base < s.n;
        base += (int64_t)gridDim.x * B2_GB_ROWS_PER_BLOCK) {
     const int64_t row0 = base + (int64_t)warp * (32 * B2_GB_R) + lane;
-    const uint32_t bits = b2_eval_terms<B2_GB_R>(s, row0);
+    bool full;
+    const uint32_t bits = b2_eval_terms<B2_GB_R>(s, row0, full);
     int64_t key[B2_GB_R];
-#pragma unroll
-    for (int j = 0; j < B2_GB_R; ++j)
-      key[j] = (bits >> j) & 1 ? b2_load_raw(kc, row0 + (int64_t)j * 32) : 0;
+    b2_load_batch<B2_GB_R>(kc, row0, bits, full, key);
     int32_t found[B2_GB_R];
 #pragma unroll
     for (int j = 0; j < B2_GB_R; ++j) {

@@ -36,6 +36,26 @@ stats = {"launches": 0, "star_fused": 0, "dense_groupby": 0, "hash_groupby": 0, 
          "chain_join": 0, "h2d_bytes": 0, "d2h_bytes": 0}
 
 
+# Optional per-launch timing of the dominant kernels (bench.py sets this to a list): each entry
+# is [kernel name, rows, start event, end event], recorded on the launching stream.
+kernel_events = None
+
+
+def _kernel_event_begin(name, rows):
+    if kernel_events is None:
+        return None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    rec = [name, rows, e0, e1]
+    kernel_events.append(rec)
+    return rec
+
+
+def _kernel_event_end(rec):
+    if rec is not None:
+        rec[3].record()
+
+
 def _dev():
     D.require_cuda()
     return torch.device("cuda", torch.cuda.current_device())
@@ -963,8 +983,10 @@ def try_star(src: AggSource, child: LazyFrame, gexprs, aggs, pred, sharded) -> O
         fk_slot = ctx.slot(fk_e)
         gs.bind(ctx)
         stats["launches"] += 1
+        ev = _kernel_event_begin("b2_star_agg_kernel", part.n)
         L.star_agg(C.byref(ctx.scan()), fk_slot, C.byref(lk), gs.table.aggs, len(gs.table.specs),
                    C.byref(gs.table.state), D.stream_ptr())
+        _kernel_event_end(ev)
     stats["star_fused"] += 1
     if sharded:
         _allreduce_table(gs.table, plan)

@@ -151,7 +151,7 @@ class DeviceTable:
                     part[nm] = DeviceColumn(v[lo:hi], None, dt)
                     continue
                 piece = v.iloc[lo:hi] if hasattr(v, "iloc") else v[lo:hi]
-                hc = _host_column(piece, pin=not persist or True)
+                hc = _host_column(piece, pin=not persist)
                 part[nm] = hc.to_device(device) if persist else hc
             parts.append(part)
         return cls(parts, distribution, name)

@@ -1,0 +1,215 @@
+"""CPU tests of the drop-in boundary: plugin registry, containers, planner shapes, C-ABI symbols,
+expression compilation.  No kernel is launched (there is no GPU here and no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pandas as pd
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ---- C-ABI -----------------------------------------------------------------------------------
+def test_library_loads_and_exports_every_declared_symbol():
+    from dask_sql_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "b200sql.h")).read()
+    declared = sorted(set(re.findall(r"\b(b2_[a-z0-9_]+)\s*\(", header)))
+    declared = [d for d in declared if not d.endswith("_t")]
+    assert len(declared) >= 25
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    missing = [d for d in declared if not hasattr(lib, d)]
+    assert not missing, f"declared in include/b200sql.h but not exported: {missing}"
+    assert set(_lib.EXPORTS) <= set(declared)
+    assert _lib.version() == 100
+    assert _lib.num_tiles(4097) == 2
+    # pure host helpers of the ABI
+    for x in (0.0, -0.0, 1.5, -2.25, 1e300, -1e-300):
+        assert _lib.ordered_to_f64(_lib.f64_to_ordered(x)) == x
+    xs = [-3.0, -1.0, -0.0, 0.0, 2.0, 7.5]
+    ks = [_lib.f64_to_ordered(x) for x in xs]
+    assert ks == sorted(ks)
+
+
+def test_struct_layouts_match_header_sizes():
+    from dask_sql_b200 import _lib as L
+    assert ctypes.sizeof(L.Scan) == 16 * 24 + 8 * 32 + 16
+    assert ctypes.sizeof(L.Prog) == 64 * 24 + 8
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "dask-sql_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in re.sub(r'""".*?"""', "", src, flags=re.S).replace("# oracle", ""), f
+
+
+# ---- plugin registry (reference: tests/unit/test_utils.py:33-58) ------------------------------
+def test_pluggable_replace_semantics():
+    from dask_sql_b200.utils import Pluggable
+
+    class PluginTest1(Pluggable):
+        pass
+
+    class PluginTest2(Pluggable):
+        pass
+
+    PluginTest1.add_plugin("some_key", "value")
+    assert PluginTest1.get_plugin("some_key") == "value"
+    assert PluginTest1.get_plugins() == ["value"]
+    with pytest.raises(KeyError):
+        PluginTest2.get_plugin("some_key")
+    PluginTest1.add_plugin("some_key", "value_2")
+    assert PluginTest1.get_plugin("some_key") == "value_2"
+    PluginTest1.add_plugin("some_key", "value_3", replace=False)
+    assert PluginTest1.get_plugin("some_key") == "value_2"
+    PluginTest1.add_plugin(["a", "b"], "multi")
+    assert PluginTest1.get_plugin("a") == PluginTest1.get_plugin("b") == "multi"
+
+
+def test_custom_rel_plugin_drops_in():
+    from dask_sql_b200 import BaseRelPlugin, Context, RelConverter
+    from dask_sql_b200.physical.rel.logical import DaskFilterPlugin
+
+    calls = []
+
+    class MyFilter(DaskFilterPlugin):
+        class_name = "Filter"
+
+        def convert(self, rel, context):
+            calls.append(rel.get_current_node_type())
+            return super().convert(rel, context)
+
+    c = Context()
+    RelConverter.add_plugin_class(MyFilter, replace=True)
+    try:
+        c.create_table("t", pd.DataFrame({"x": [1, 2, 3]}))
+        c.sql("SELECT x FROM t WHERE x > 1", config_options={"sql.optimize": False})
+        assert calls == ["Filter"]
+        assert issubclass(MyFilter, BaseRelPlugin)
+    finally:
+        RelConverter.add_plugin_class(DaskFilterPlugin, replace=True)
+
+
+# ---- containers (reference: tests/unit/test_datacontainer.py:4-67) ----------------------------
+def test_column_container():
+    from dask_sql_b200.datacontainer import ColumnContainer
+    c = ColumnContainer(["a", "b", "c"])
+    assert c.columns == ["a", "b", "c"]
+    assert c.mapping() == [("a", "a"), ("b", "b"), ("c", "c")]
+    c2 = c.limit_to(["c", "a"])
+    assert c2.columns == ["c", "a"] and c.columns == ["a", "b", "c"]
+    c3 = c.rename({"a": "A", "b": "a"})
+    assert c3.columns == ["A", "a", "c"]
+    assert c3.get_backend_by_frontend_name("A") == "a" and c3.get_backend_by_frontend_name("a") == "b"
+    assert c3.get_backend_by_frontend_index(1) == "b"
+    c4 = c.add("d").add("e", "a")
+    assert c4.columns == ["a", "b", "c", "d", "e"] and c4.get_backend_by_frontend_name("e") == "a"
+    c5 = c.make_unique("x")
+    assert c5.columns == ["x_0", "x_1", "x_2"] and c5.get_backend_by_frontend_name("x_2") == "c"
+    c6 = c.rename_handle_duplicates(["a", "a"], ["p", "q"])
+    assert c6.get_backend_by_frontend_name("p") == "a" and c6.get_backend_by_frontend_name("q") == "a"
+
+
+# ---- planner shapes ---------------------------------------------------------------------------
+def _ctx():
+    from dask_sql_b200 import Context
+    c = Context()
+    rng = np.random.default_rng(0)
+    c.create_table("fact", pd.DataFrame({"fk": rng.integers(0, 10, 64), "x": rng.integers(-5, 5, 64),
+                                         "val": rng.random(64)}), npartitions=3)
+    c.create_table("dim", pd.DataFrame({"pk": np.arange(10), "flag": rng.integers(0, 10, 10),
+                                        "grp": rng.integers(0, 3, 10)}))
+    return c
+
+
+def test_c1_plan_pushes_filter_into_scan():
+    c = _ctx()
+    plan = c.explain("SELECT SUM(x) FROM fact WHERE x > 0")
+    # SURVEY 3.2 / tests/integration/test_join.py:482-492 plan text style
+    assert plan.splitlines()[-1].strip() == "TableScan: fact projection=[x], full_filters=[fact.x > Int64(0)]"
+    assert "Aggregate: groupBy=[[]], aggr=[[SUM(fact.x)]]" in plan
+    assert "Filter:" not in plan
+
+
+def test_q3_plan_shape_and_lazy_graph():
+    from dask_sql_b200.frame import AggSource, JoinSource, TableSource
+    c = _ctx()
+    q = """SELECT d.grp, SUM(f.val) AS rev FROM fact f JOIN dim d ON f.fk = d.pk
+           WHERE f.x > 0 AND d.flag < 5 GROUP BY d.grp"""
+    plan = c.explain(q)
+    assert "Inner Join: f.fk = d.pk" in plan
+    assert "full_filters=[fact.x > Int64(0), fact.fk IS NOT NULL]" in plan
+    assert "full_filters=[dim.flag < Int64(5), dim.pk IS NOT NULL]" in plan
+    lazy = c.sql(q)
+    assert lazy.columns == ["grp", "rev"]
+    agg = lazy.source
+    assert isinstance(agg, AggSource) and [a[2] for a in agg.aggs] == ["sum"]
+    join = agg.child.source
+    assert isinstance(join, JoinSource) and join.how == "inner"
+    assert isinstance(join.left.source, TableSource) and len(join.left.pred) == 2
+    assert isinstance(join.right.source, TableSource) and len(join.right.pred) == 2
+
+
+def test_unoptimized_plan_keeps_filter_node():
+    c = _ctx()
+    lazy = c.sql("SELECT x FROM fact WHERE x > 0", config_options={"sql.optimize": False})
+    assert len(lazy.pred) == 1
+
+
+def test_parse_errors_are_parsing_exceptions():
+    from dask_sql_b200.utils import ParsingException
+    c = _ctx()
+    for bad in ["SELEC x FROM fact", "SELECT nope FROM fact", "SELECT x FROM missing_table",
+                "SELECT x, SUM(val) FROM fact", "SELECT x FROM fact WHERE"]:
+        with pytest.raises(ParsingException):
+            c.sql(bad)
+
+
+def test_out_of_scope_features_fail_loudly():
+    c = _ctx()
+    with pytest.raises(NotImplementedError):
+        c.sql("SELECT * FROM fact, dim")
+    with pytest.raises(Exception):
+        c.sql("SELECT UPPER(x) FROM fact")
+
+
+# ---- expression IR ----------------------------------------------------------------------------
+def test_term_extraction_and_program_compilation():
+    from dask_sql_b200 import _lib as L
+    from dask_sql_b200 import expr as E
+    x, y = E.ColRef("x", E.I64), E.ColRef("y", E.F64)
+    assert E.as_term(E.binop("gt", x, 0)) == ("x", L.GT, 0)
+    assert E.as_term(E.binop("lt", 3, x)) == ("x", L.GT, 3)            # flipped
+    assert E.as_term(E.binop("le", y, 2)) == ("y", L.LE, 2.0)
+    assert E.as_term(E.binop("gt", x, 0.5)) == ("x", L.GT, 0.5)        # int column, float literal
+    assert E.as_term(E.unop("not", E.unop("isnull", x))) == ("x", L.IS_NOT_NULL, 0)
+    assert E.as_term(E.binop("gt", E.binop("add", x, 1), 0)) is None   # needs the interpreter
+    e = E.fillna(E.binop("and", E.binop("gt", x, 0), E.binop("lt", y, 1.5)), False)
+    assert len(E.conjuncts(e)) == 2
+    prog = E.compile_expr(E.binop("mul", E.binop("add", x, 1), y), ["x", "y"])
+    ops = [prog.code[i].op for i in range(prog.n)]
+    assert ops == [L.OP_LOAD, L.OP_CONST_I, L.OP_ADD_I, L.OP_I2F, L.OP_LOAD, L.OP_MUL_F]
+    assert prog.out_dtype == L.F64
+    assert E.binop("divt", x, 2).dtype == E.I64 and E.binop("truediv", x, 2).dtype == E.F64
+
+
+def test_host_column_roundtrip_keeps_logical_dtypes():
+    import torch
+    from dask_sql_b200.device import DeviceColumn, column_to_host
+    from dask_sql_b200.table import _host_column
+    s = pd.Series(pd.array([1, None, 3, None, 5] * 13, dtype="Int64"))
+    hc = _host_column(s, pin=False)
+    assert hc.dtype == 0 and hc.valid is not None and hc.logical == "Int64"
+    back = column_to_host(DeviceColumn(hc.data, hc.valid, hc.dtype, hc.logical))
+    assert pd.Series(back).isna().tolist() == s.isna().tolist()
+    assert pd.Series(back).dropna().astype(int).tolist() == s.dropna().astype(int).tolist()
+    f = _host_column(pd.Series([1.5, np.nan, 2.5]), pin=False)
+    assert f.dtype == 1 and f.valid is None
+    b = _host_column(pd.Series([True, False, True]), pin=False)
+    assert b.dtype == 2 and b.data.dtype == torch.uint8
+    with pytest.raises(NotImplementedError):
+        _host_column(pd.Series(["a", "b"]), pin=False)

@@ -1,0 +1,128 @@
+"""Multi-rank plumbing on CPU (gloo, world_size 2 and 3): sharding, the merge-tree schedule, the
+build-side broadcast / all-gather, and the partial-aggregate tree merge protocol.  The merge
+arithmetic itself is a CUDA kernel (no CPU fallback), so here the receiver-side combine is the
+oracle's (tests may use the oracle); what is under test is who-sends-what-to-whom."""
+import os
+import socket
+
+import numpy as np
+import pandas as pd
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def test_shard_bounds_cover_rows_without_overlap():
+    from dask_sql_b200.parallel import shard_bounds
+    for n in (0, 1, 31, 32, 1000, 10**9 + 7):
+        for size in (1, 2, 3, 8):
+            spans = [shard_bounds(n, r, size) for r in range(size)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            for (a, b), (c, d) in zip(spans, spans[1:]):
+                assert b == c and a <= b
+            for lo, hi in spans:
+                assert lo % 32 == 0 or lo == hi      # non-empty shards start on a bitmap word
+
+
+@pytest.mark.parametrize("size", [1, 2, 3, 4, 8, 13])
+@pytest.mark.parametrize("fan_in", [2, 3, 8])
+def test_tree_rounds_reduce_everything_onto_rank0(size, fan_in):
+    from dask_sql_b200.parallel import tree_rounds
+    holds = {r: {r} for r in range(size)}
+    alive = set(range(size))
+    for rnd in tree_rounds(size, fan_in):
+        receivers = [r for r, _ in rnd]
+        senders = [s for _, s in rnd]
+        assert len(set(senders)) == len(senders) and not set(senders) & set(receivers)
+        assert len(set(receivers)) == len(receivers)      # one message per receiver per round
+        for r, s in rnd:
+            assert r in alive and s in alive
+            holds[r] |= holds.pop(s)
+            alive.discard(s)
+    assert alive == {0} and holds[0] == set(range(size))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, size, port, fan_in, out_q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=size)
+    try:
+        from dask_sql_b200 import merge
+        from dask_sql_b200.device import DeviceColumn, I64, F64
+        from dask_sql_b200.executor import Part, RawGroups
+        dev = torch.device("cpu")
+
+        # --- broadcast of a build side that only rank 0 holds
+        if rank == 0:
+            part = Part({"pk": DeviceColumn(torch.arange(10, dtype=torch.int64), None, I64),
+                         "w": DeviceColumn(torch.arange(10, dtype=torch.float64) * 0.5, None, F64)}, 10)
+        else:
+            part = Part({}, 0)
+        got = merge.broadcast_part(part, dev, src=0)
+        assert got.n == 10 and got["pk"].data.tolist() == list(range(10))
+        assert got["w"].data.tolist() == [i * 0.5 for i in range(10)]
+
+        # --- all-gather of a pre-sharded build side
+        mine = Part({"k": DeviceColumn(torch.arange(rank * 4, rank * 4 + 4, dtype=torch.int64), None, I64)}, 4)
+        allp = merge.allgather_part(mine, dev)
+        assert allp["k"].data.tolist() == list(range(4 * size))
+
+        # --- tree merge of partial group tables (receiver combine = oracle)
+        rng = np.random.default_rng(100 + rank)
+        keys = rng.choice(50, size=20, replace=False).astype(np.int64)
+        sums = rng.random(20)
+        cnts = rng.integers(1, 9, 20).astype(np.int64)
+
+        class KA:
+            def __init__(self, op):
+                self.op = op
+
+        class Plan:
+            kaggs = [KA(0)]
+
+        def oracle_merge(parts, plan, nkeys):
+            df = pd.concat([pd.DataFrame({n: p[n].data.numpy() for n in p}) for p in parts])
+            m = df.groupby("k0", as_index=False).sum()
+            return Part({"k0": DeviceColumn(torch.from_numpy(m["k0"].to_numpy()), None, I64),
+                         "a0": DeviceColumn(torch.from_numpy(m["a0"].to_numpy()), None, F64),
+                         "c0": DeviceColumn(torch.from_numpy(m["c0"].to_numpy()), None, I64)}, len(m))
+
+        merge.merge_partials = oracle_merge
+        raw = RawGroups({"key": DeviceColumn(torch.from_numpy(keys), None, I64)},
+                        [DeviceColumn(torch.from_numpy(sums), None, F64)],
+                        [DeviceColumn(torch.from_numpy(cnts), None, I64)], None, 20)
+        merged = merge.tree_merge_raw(raw, Plan(), {"split_every": fan_in}, dev)
+        res = pd.DataFrame({"k": merged.keys["key"].data.numpy(), "s": merged.acc[0].data.numpy(),
+                            "c": merged.cnt[0].data.numpy()}).sort_values("k").reset_index(drop=True)
+        out_q.put((rank, keys, sums, cnts, res))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("size,fan_in", [(2, 2), (3, 2), (3, 8)])
+def test_gloo_broadcast_allgather_and_tree_merge(size, fan_in):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, size, port, fan_in, q)) for r in range(size)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in range(size)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    everything = pd.concat([pd.DataFrame({"k": k, "s": s, "c": c}) for _, k, s, c, _ in results])
+    exp = everything.groupby("k", as_index=False).sum().sort_values("k").reset_index(drop=True)
+    for _, _, _, _, res in results:           # every rank ends with the full merged table
+        assert res["k"].tolist() == exp["k"].tolist()
+        assert res["c"].tolist() == exp["c"].tolist()
+        np.testing.assert_allclose(res["s"].to_numpy(), exp["s"].to_numpy(), rtol=1e-12)

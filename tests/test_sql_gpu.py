@@ -1,0 +1,192 @@
+"""SQL-level GPU parity: the reference's known-answer tests (tests/golden/reference_vectors.py)
+and a sqlite3 differential on seeded random data (the reference's own differential oracle,
+tests/integration/test_compatibility.py:25-83), both through Context.sql() -> plugins ->
+libb200sql.so.  Row order is not part of the contract (frames are compared as multisets)."""
+import sqlite3
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from tests.golden import reference_vectors as G
+
+pytestmark = pytest.mark.gpu
+
+
+def _norm(df):
+    out = pd.DataFrame({str(c): df[c].to_numpy(dtype=float, na_value=np.nan) for c in df.columns})
+    if len(out):
+        out = out.sort_values(list(out.columns), na_position="last").reset_index(drop=True)
+    return out
+
+
+def assert_same(got, exp, float_cols=(), rtol=1e-9, check_names=True):
+    assert len(got.columns) == len(exp.columns), f"{list(got.columns)} vs {list(exp.columns)}"
+    if check_names:
+        assert [str(c) for c in got.columns] == [str(c) for c in exp.columns]
+    g, e = _norm(got), _norm(exp)
+    e.columns = g.columns
+    assert len(g) == len(e), f"{len(g)} rows vs {len(e)}"
+    for c, ce in zip(g.columns, exp.columns):
+        if str(ce) in float_cols:
+            np.testing.assert_allclose(g[c].to_numpy(), e[c].to_numpy(), rtol=rtol, equal_nan=True)
+        else:
+            np.testing.assert_array_equal(g[c].to_numpy(), e[c].to_numpy())
+
+
+@pytest.fixture()
+def c():
+    from dask_sql_b200 import Context
+    return Context()
+
+
+@pytest.mark.parametrize("case", G.CASES, ids=[c["name"] for c in G.CASES])
+@pytest.mark.parametrize("npartitions", [1, 3])
+def test_reference_known_answers(c, case, npartitions):
+    tables = G.tables_of(case)
+    for name, df in tables.items():
+        c.create_table(name, df, npartitions=npartitions)   # the reference registers with npartitions=3
+    got = c.sql(case["sql"]).compute()
+    exp = G.expected_of(case, tables)
+    assert_same(got, exp, case.get("float_cols", ()))
+
+
+def make_rand_df(size, seed=0, **kwargs):
+    """Same generator shape as the reference's make_rand_df (test_compatibility.py:50-83):
+    kwargs: column -> (type, null_ct)."""
+    np.random.seed(seed)
+    data = {}
+    for k, v in kwargs.items():
+        dt, null_ct = v if isinstance(v, tuple) else (v, 0)
+        if dt is int:
+            s = np.random.randint(10, size=size).astype(float if null_ct else int)
+        elif dt is float:
+            s = np.random.rand(size)
+        elif dt is bool:
+            s = np.where(np.random.randint(2, size=size), True, False).astype(object if null_ct else bool)
+        else:
+            raise NotImplementedError
+        s = pd.Series(s)
+        if null_ct:
+            idx = np.random.choice(size, null_ct, replace=False).tolist()
+            s[idx] = np.nan
+        data[k] = s
+    return pd.DataFrame(data)
+
+
+def eq_sqlite(c, sql, float_cols=(), **dfs):
+    con = sqlite3.connect(":memory:")
+    for name, df in dfs.items():
+        c.create_table(name, df, npartitions=2)
+        df.to_sql(name, con, index=False)
+    got = c.sql(sql).compute()
+    exp = pd.read_sql(sql, con)
+    assert_same(got, exp, float_cols or [str(x) for x in exp.columns if exp[x].dtype.kind == "f"], check_names=False)
+
+
+def test_where(c):
+    # tests/integration/test_compatibility.py:177-196 (int columns; float columns carry NaN whose
+    # comparison semantics differ between numpy and sqlite)
+    df = make_rand_df(100, a=(int, 30), b=(int, 30), c=(float, 0))
+    eq_sqlite(c, "SELECT * FROM a WHERE a<2 OR c>0.8", a=df)
+    eq_sqlite(c, "SELECT * FROM a WHERE a<2 AND c>0.3", a=df)
+    eq_sqlite(c, "SELECT * FROM a WHERE a IS NULL OR (b>=5 AND c<0.5)", a=df)
+    eq_sqlite(c, "SELECT * FROM a WHERE a IS NOT NULL AND NOT (b<5)", a=df)
+    eq_sqlite(c, "SELECT a + b AS s, a * 2 - b AS t, c / 2 AS h FROM a WHERE a = b OR a <> 3", a=df)
+
+
+def test_in_between(c):
+    # test_compatibility.py:198-207
+    df = make_rand_df(100, a=(int, 30), b=(int, 0))
+    eq_sqlite(c, "SELECT * FROM a WHERE a IN (2,4,6)", a=df)
+    eq_sqlite(c, "SELECT * FROM a WHERE a BETWEEN 2 AND 4+1", a=df)
+    eq_sqlite(c, "SELECT * FROM a WHERE a NOT IN (2,4,6) AND a IS NOT NULL", a=df)
+    eq_sqlite(c, "SELECT * FROM a WHERE a NOT BETWEEN 2 AND 4+1 AND a IS NOT NULL", a=df)
+
+
+def test_join_inner_and_left(c):
+    # test_compatibility.py:210-238
+    a = make_rand_df(100, a=(int, 40), b=(int, 0), c=int)
+    b = make_rand_df(80, seed=1, d=(float, 10), a=(int, 10), b=(int, 0))
+    eq_sqlite(c, "SELECT a.*, d, d*c AS x FROM a INNER JOIN b ON a.a=b.a AND a.b=b.b", a=a, b=b)
+    eq_sqlite(c, "SELECT a.*, d, d*c AS x FROM a LEFT JOIN b ON a.a=b.a AND a.b=b.b", a=a, b=b)
+    eq_sqlite(c, "SELECT a.a, a.c, b.d FROM a JOIN b ON a.a = b.a WHERE a.c > 3 AND b.d < 0.7", a=a, b=b)
+
+
+def test_agg_count_sum_avg_min_max(c):
+    # test_compatibility.py:379-451, 490-522
+    a = make_rand_df(100, a=(int, 50), b=(int, 50), c=(int, 30), d=(float, 30), e=(float, 40))
+    eq_sqlite(c, """SELECT a, b, COUNT(c) AS c_c, COUNT(d) AS c_d, COUNT(*) AS n, SUM(c) AS s_c, AVG(c) AS a_c,
+                    SUM(d) AS s_d, AVG(e) AS a_e, MIN(c) AS mn, MAX(d) AS mx
+                    FROM a GROUP BY a, b""", a=a)
+    eq_sqlite(c, "SELECT SUM(c) AS s, AVG(d) AS av, COUNT(*) AS n, MIN(e) AS mn, MAX(c) AS mx FROM a", a=a)
+    eq_sqlite(c, "SELECT a, SUM(c+d) AS s, AVG(c*2) AS av FROM a WHERE b IS NOT NULL GROUP BY a", a=a)
+    eq_sqlite(c, "SELECT a, COUNT(DISTINCT b) AS cd FROM a GROUP BY a", a=a)
+    eq_sqlite(c, "SELECT DISTINCT a, b FROM a", a=a)
+    eq_sqlite(c, "SELECT a, SUM(c) AS s FROM a GROUP BY a HAVING SUM(c) > 20", a=a)
+
+
+def test_integration_filter_join_groupby(c):
+    # shape of test_compatibility.py:1015-1036 (CTEs: filter + agg + inner + left join)
+    a = make_rand_df(200, a=int, b=(int, 20), c=(float, 0))
+    b = make_rand_df(60, seed=2, a=int, d=(float, 0))
+    eq_sqlite(c, """
+        WITH t1 AS (SELECT a, SUM(c) AS sc FROM a WHERE b > 2 GROUP BY a),
+             t2 AS (SELECT a, AVG(d) AS ad FROM b GROUP BY a)
+        SELECT t1.a, t1.sc, t2.ad FROM t1 INNER JOIN t2 ON t1.a = t2.a
+        """, a=a, b=b)
+    eq_sqlite(c, """
+        SELECT x.a, x.sc, b.d FROM (SELECT a, SUM(c) AS sc FROM a GROUP BY a) AS x
+        LEFT JOIN b ON x.a = b.a WHERE x.sc > 5
+        """, a=a, b=b)
+
+
+def test_q3_shape_uses_fused_pipeline(c):
+    from dask_sql_b200 import executor
+    from oracle import pandas_oracle as O
+    rng = np.random.default_rng(4)
+    nd, nf = 20_000, 500_000
+    dim = pd.DataFrame({"pk": rng.permutation(nd), "flag": rng.integers(0, 10, nd), "grp": rng.integers(0, 500, nd)})
+    fact = pd.DataFrame({"fk": rng.integers(0, nd, nf), "x": rng.integers(-2**31, 2**31, nf), "val": rng.random(nf)})
+    c.create_table("fact", fact, npartitions=8, persist=True)
+    c.create_table("dim", dim, persist=True)
+    before = executor.stats["star_fused"]
+    got = c.sql("""SELECT d.grp, SUM(f.val) AS rev FROM fact f JOIN dim d ON f.fk = d.pk
+                   WHERE f.x > 0 AND d.flag < 5 GROUP BY d.grp""", return_futures=False)
+    assert executor.stats["star_fused"] == before + 1
+    assert_same(got, O.c4_q3(O.split(fact, 8), dim), ["rev"])
+    # C1 / C2 / C3 shapes
+    got = c.sql("SELECT SUM(x) FROM fact WHERE x > 0", return_futures=False)
+    assert int(got.iloc[0, 0]) == int(fact.x[fact.x > 0].sum())
+    assert list(got.columns) == ["SUM(fact.x)"]
+    got = c.sql("SELECT fk, SUM(val) AS s, AVG(val) AS a FROM fact GROUP BY fk", return_futures=False)
+    exp = O.c5_groupby_sum_avg(O.split(fact.rename(columns={"fk": "key"})[["key", "val"]], 8))
+    assert_same(got, exp, ["s", "a"], check_names=False)
+    got = c.sql("SELECT f.fk, f.val, d.grp FROM fact f JOIN dim d ON f.fk = d.pk", return_futures=False)
+    exp = fact.merge(dim, left_on="fk", right_on="pk")[["fk", "val", "grp"]]
+    assert_same(got, exp, ["val"])
+
+
+def test_plumbing(c):
+    # tests/unit/test_context.py:51-69: lazy vs computed, dataframes= kwarg, explain
+    df = pd.DataFrame({"a": [1, 2, 3], "b": [1.1, 2.2, 3.3]})
+    c.create_table("df", df)
+    lazy = c.sql("SELECT a FROM df")
+    assert not isinstance(lazy, pd.DataFrame) and lazy.columns == ["a"]
+    assert lazy.compute()["a"].tolist() == [1, 2, 3]
+    res = c.sql("SELECT a FROM other", return_futures=False, dataframes={"other": df})
+    assert isinstance(res, pd.DataFrame) and res["a"].tolist() == [1, 2, 3]
+    assert "TableScan: df projection=[a]" in c.explain("SELECT a FROM df")
+    c.drop_table("df")
+    with pytest.raises(Exception):
+        c.sql("SELECT a FROM df")
+    # per-query config (context.py:519) and split_out/split_every keys are accepted
+    res = c.sql("SELECT a, SUM(b) AS s FROM other GROUP BY a", return_futures=False,
+                config_options={"sql.aggregate.split_out": 2, "sql.aggregate.split_every": 3})
+    assert len(res) == 3
+
+
+def test_no_cpu_fallback_errors_are_loud(c):
+    df = pd.DataFrame({"a": [1, 2, 3], "s": ["x", "y", "z"]})
+    with pytest.raises(NotImplementedError):
+        c.create_table("t", df)          # strings are outside the int64/float64 hot path
