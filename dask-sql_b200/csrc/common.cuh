@@ -224,42 +224,86 @@ __device__ __forceinline__ uint32_t b2_null_bits(const b2_col_t& c, int64_t row0
   return nul;
 }
 
-template <int R, int OP, int KIND>  // KIND 0: int64 compare, 1: float64 column, 2: int column compared as float64
-__device__ __forceinline__ uint32_t b2_cmp_batch(const int64_t (&raw)[R], int64_t lit_i, double lit_f) {
+// Branch-free comparison against a literal: every SQL comparison is a choice among the three
+// outcomes (less, equal, greater) plus "unordered" for NaN, so the operator becomes four masks
+// computed once per batch and the per-row work is two compares and two selects, with no jump
+// table and one code path for all six operators.
+struct b2_cmpmask {
+  uint32_t lt, eq, gt, un;  // 0 or 0xffffffff
+};
+__device__ __forceinline__ b2_cmpmask b2_make_cmpmask(int op) {
+  b2_cmpmask m;
+  m.lt = (op == B2_LT || op == B2_LE || op == B2_NE) ? 0xffffffffu : 0u;
+  m.eq = (op == B2_EQ || op == B2_LE || op == B2_GE) ? 0xffffffffu : 0u;
+  m.gt = (op == B2_GT || op == B2_GE || op == B2_NE) ? 0xffffffffu : 0u;
+  m.un = (op == B2_NE) ? 0xffffffffu : 0u;  // IEEE: NaN != x is true, everything else false
+  return m;
+}
+template <int R>
+__device__ __forceinline__ uint32_t b2_cmp_batch_i(const int64_t (&raw)[R], int64_t lit, const b2_cmpmask m) {
   uint32_t ok = 0;
 #pragma unroll
   for (int j = 0; j < R; ++j) {
-    bool r;
-    if (KIND == 0) r = b2_cmp_t<OP, int64_t>(raw[j], lit_i);
-    else if (KIND == 1) r = b2_cmp_t<OP, double>(__longlong_as_double(raw[j]), lit_f);
-    else r = b2_cmp_t<OP, double>((double)raw[j], lit_f);
-    ok |= (uint32_t)r << j;
+    const uint32_t r = raw[j] < lit ? m.lt : (raw[j] == lit ? m.eq : m.gt);
+    ok |= r & (1u << j);
   }
   return ok;
 }
-template <int R, int KIND>
-__device__ __forceinline__ uint32_t b2_cmp_dispatch(int op, const int64_t (&raw)[R], int64_t lit_i, double lit_f) {
-  switch (op) {
-    case B2_EQ: return b2_cmp_batch<R, B2_EQ, KIND>(raw, lit_i, lit_f);
-    case B2_NE: return b2_cmp_batch<R, B2_NE, KIND>(raw, lit_i, lit_f);
-    case B2_LT: return b2_cmp_batch<R, B2_LT, KIND>(raw, lit_i, lit_f);
-    case B2_LE: return b2_cmp_batch<R, B2_LE, KIND>(raw, lit_i, lit_f);
-    case B2_GT: return b2_cmp_batch<R, B2_GT, KIND>(raw, lit_i, lit_f);
-    default: return b2_cmp_batch<R, B2_GE, KIND>(raw, lit_i, lit_f);
+template <int R, bool CVT>  // CVT: the column holds int64 and is compared as float64
+__device__ __forceinline__ uint32_t b2_cmp_batch_f(const int64_t (&raw)[R], double lit, const b2_cmpmask m) {
+  uint32_t ok = 0;
+#pragma unroll
+  for (int j = 0; j < R; ++j) {
+    const double a = CVT ? (double)raw[j] : __longlong_as_double(raw[j]);
+    const uint32_t r = a < lit ? m.lt : (a == lit ? m.eq : (a > lit ? m.gt : m.un));
+    ok |= r & (1u << j);
   }
+  return ok;
 }
 
-// Evaluate all predicate terms for the batch at row0.  Returns the surviving row bits and
-// whether the batch is fully in bounds.
-template <int R>
-__device__ __forceinline__ uint32_t b2_eval_terms(const b2_scan_t& s, int64_t row0, bool& full) {
+// ---------------------------------------------------------------------------------------
+// column loaders: where a batch's values come from
+// ---------------------------------------------------------------------------------------
+struct b2_gld {  // straight from global memory
+  const b2_scan_t* s;
+  int64_t row0;
+  template <int R>
+  __device__ __forceinline__ void load(int col, uint32_t bits, bool full, int64_t (&raw)[R]) const {
+    b2_load_batch<R>(s->cols[col], row0, bits, full, raw);
+  }
+};
+struct b2_sld {  // from the shared-memory tile staged by the TMA producer warp (pipeline.cuh)
+  const b2_scan_t* s;
+  int64_t row0;            // global row of this lane's first row (bitmaps, out_slot)
+  const uint8_t* stage;    // base of the current stage in shared memory
+  const int32_t* col_off;  // byte offset of each column's tile within a stage
+  int tile_off;            // this lane's first row within the tile
+  template <int R>
+  __device__ __forceinline__ void load(int col, uint32_t bits, bool full, int64_t (&raw)[R]) const {
+    if (s->cols[col].dtype == B2_U8) {
+      const uint8_t* p = stage + col_off[col] + tile_off;
+#pragma unroll
+      for (int j = 0; j < R; ++j) raw[j] = (int64_t)p[j * 32];
+    } else {
+      const int64_t* p = reinterpret_cast<const int64_t*>(stage + col_off[col]) + tile_off;
+#pragma unroll
+      for (int j = 0; j < R; ++j) raw[j] = p[j * 32];
+    }
+  }
+};
+
+// Evaluate all predicate terms for the batch.  Returns the surviving row bits and whether the
+// batch is fully in bounds.
+template <int R, class LD>
+__device__ __forceinline__ uint32_t b2_eval_terms(const b2_scan_t& s, const LD& ld, bool& full) {
+  const int64_t row0 = ld.row0;
   uint32_t bits = b2_bounds_bits<R>(row0, s.n, full);
   for (int t = 0; t < s.nterms; ++t) {
     const b2_term_t& tm = s.terms[t];
     const b2_col_t& c = s.cols[tm.col];
     const int op = tm.op;
     int64_t raw[R];
-    b2_load_batch<R>(c, row0, bits, full, raw);
+    ld.template load<R>(tm.col, bits, full, raw);
     uint32_t ok;
     if (op == B2_IS_NULL || op == B2_IS_NOT_NULL) {
       const uint32_t nul = b2_null_bits<R>(c, row0, bits, raw);
@@ -269,18 +313,22 @@ __device__ __forceinline__ uint32_t b2_eval_terms(const b2_scan_t& s, int64_t ro
         ok = 0;
 #pragma unroll
         for (int j = 0; j < R; ++j) ok |= (uint32_t)(raw[j] != 0) << j;
-      } else if (c.dtype == B2_F64) {
-        ok = b2_cmp_dispatch<R, 1>(op, raw, tm.lit_i, tm.lit_f);
-      } else if (tm.as_f64) {
-        ok = b2_cmp_dispatch<R, 2>(op, raw, tm.lit_i, tm.lit_f);
       } else {
-        ok = b2_cmp_dispatch<R, 0>(op, raw, tm.lit_i, tm.lit_f);
+        const b2_cmpmask m = b2_make_cmpmask(op);
+        if (c.dtype == B2_F64) ok = b2_cmp_batch_f<R, false>(raw, tm.lit_f, m);
+        else if (tm.as_f64) ok = b2_cmp_batch_f<R, true>(raw, tm.lit_f, m);
+        else ok = b2_cmp_batch_i<R>(raw, tm.lit_i, m);
       }
       if (c.valid) ok &= b2_valid_bits<R>(c.valid, row0, bits);
     }
     bits &= ok;
   }
   return bits;
+}
+template <int R>
+__device__ __forceinline__ uint32_t b2_eval_terms(const b2_scan_t& s, int64_t row0, bool& full) {
+  const b2_gld ld{&s, row0};
+  return b2_eval_terms<R>(s, ld, full);
 }
 template <int R>
 __device__ __forceinline__ uint32_t b2_eval_terms(const b2_scan_t& s, int64_t row0) {
@@ -323,15 +371,22 @@ __device__ __forceinline__ void b2_atomic_k(void* acc, int64_t slot, int64_t raw
   else if (KIND == B2_K_MAX_F) atomicMax(reinterpret_cast<long long*>(acc) + slot, (long long)b2_ordered_from_bits(raw));
 }
 
+template <int R, int KIND, bool CNT>
+__device__ __forceinline__ void b2_atomic_batch2(void* acc, int64_t* cnt, const int64_t (&slot)[R],
+                                                 const int64_t (&raw)[R], uint32_t live) {
+#pragma unroll
+  for (int j = 0; j < R; ++j) {
+    if ((live >> j) & 1) {
+      if (KIND != B2_K_NONE) b2_atomic_k<KIND>(acc, slot[j], raw[j]);
+      if (CNT) atomicAdd(reinterpret_cast<unsigned long long*>(cnt) + slot[j], 1ULL);
+    }
+  }
+}
 template <int R, int KIND>
 __device__ __forceinline__ void b2_atomic_batch(void* acc, int64_t* cnt, const int64_t (&slot)[R],
                                                 const int64_t (&raw)[R], uint32_t live) {
-#pragma unroll
-  for (int j = 0; j < R; ++j) {
-    if (!((live >> j) & 1)) continue;
-    if (KIND != B2_K_NONE) b2_atomic_k<KIND>(acc, slot[j], raw[j]);
-    if (cnt) atomicAdd(reinterpret_cast<unsigned long long*>(cnt) + slot[j], 1ULL);
-  }
+  if (cnt) b2_atomic_batch2<R, KIND, true>(acc, cnt, slot, raw, live);
+  else b2_atomic_batch2<R, KIND, false>(acc, cnt, slot, raw, live);
 }
 
 struct b2_aggs_arg {  // aggs passed by value in kernel params
@@ -341,10 +396,11 @@ struct b2_aggs_arg {  // aggs passed by value in kernel params
 
 // For the batch at row0 with resolved slots (slot < 0 = row does not contribute): per aggregate,
 // load its input column for the contributing rows, drop NULLs, apply the atomics.
-template <int R>
-__device__ __forceinline__ void b2_apply_aggs(const b2_scan_t& s, const b2_agg_t* __restrict__ aggs,
-                                              int naggs, const b2_aggstate_t& st, int64_t row0,
+template <int R, class LD>
+__device__ __forceinline__ void b2_apply_aggs(const b2_scan_t& s, const LD& ld, const b2_agg_t* __restrict__ aggs,
+                                              int naggs, const b2_aggstate_t& st,
                                               const int64_t (&slot)[R]) {
+  const int64_t row0 = ld.row0;
   uint32_t live = 0;
 #pragma unroll
   for (int j = 0; j < R; ++j) live |= (uint32_t)(slot[j] >= 0) << j;
@@ -359,20 +415,23 @@ __device__ __forceinline__ void b2_apply_aggs(const b2_scan_t& s, const b2_agg_t
       if ((live >> j) & 1) atomicAdd(reinterpret_cast<unsigned long long*>(st.rows) + slot[j], 1ULL);
   }
   if (st.present) {
+    // read first (L1-cached: a stale miss only costs a redundant atomicOr): after warm-up almost
+    // every group is already marked, so the atomic is rare
+    uint32_t word[R];
 #pragma unroll
-    for (int j = 0; j < R; ++j)
-      if ((live >> j) & 1) {
-        const uint32_t w = (uint32_t)(slot[j] >> 5), b = 1u << (slot[j] & 31);
-        // read first: after warm-up almost every group is already marked, so the atomic is rare
-        if (!(__ldcg(st.present + w) & b)) atomicOr(st.present + w, b);
-      }
+    for (int j = 0; j < R; ++j) word[j] = (live >> j) & 1 ? __ldca(st.present + (slot[j] >> 5)) : 0xffffffffu;
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      const uint32_t b = 1u << (slot[j] & 31);
+      if (((live >> j) & 1) && !(word[j] & b)) atomicOr(st.present + (slot[j] >> 5), b);
+    }
   }
   for (int a = 0; a < naggs; ++a) {
     const b2_agg_t ag = aggs[a];
     if (ag.col < 0) continue;  // COUNT(*) is st.rows
     const b2_col_t& c = s.cols[ag.col];
     int64_t raw[R];
-    b2_load_batch<R>(c, row0, live, false, raw);
+    ld.template load<R>(ag.col, live, false, raw);
     uint32_t ok = live;
     if (c.valid || c.dtype == B2_F64) ok &= ~b2_null_bits<R>(c, row0, live, raw);
     void* acc = st.acc[a];

@@ -2,13 +2,14 @@
 // selection (count / scan / write+gather), gather.
 #pragma once
 #include "common.cuh"
+#include "pipeline.cuh"
 
 // =======================================================================================
 // fused filter + global aggregate   (SELECT SUM(x) FROM t WHERE x > 0)
 // each warp owns 32*R consecutive rows per step; lanes read 8-byte words 256 B apart per row
 // group so every warp-load is one fully coalesced 256-byte request.
 // =======================================================================================
-#define B2_AGG_R 8
+#define B2_AGG_R 16   // rows per lane per batch on the direct path (the staged path uses B2_PIPE_R)
 #define B2_AGG_ROWS_PER_BLOCK (B2_BLOCK * B2_AGG_R)
 
 struct b2_partial {
@@ -53,49 +54,53 @@ __device__ __forceinline__ int64_t b2_fold_batch(int64_t acc, const int64_t (&ra
 
 // Accumulators live in shared memory, one slot per (aggregate, thread): the aggregate loop is a
 // run-time loop (no 8-way unrolled register file), the kind switch sits outside the row loop.
-__global__ void __launch_bounds__(B2_BLOCK)
-b2_scan_agg_kernel(const __grid_constant__ b2_scan_t s, const __grid_constant__ b2_aggs_arg aggs,
-                   b2_partial* __restrict__ partials) {
+template <int R, class LD>
+__device__ __forceinline__ void b2_scan_agg_body(const b2_scan_t& s, const LD& ld, const b2_aggs_arg& aggs,
+                                                 int64_t (*sh_acc)[B2_BLOCK], int32_t (*sh_cnt)[B2_BLOCK], int tid) {
+  bool full;
+  const uint32_t bits = b2_eval_terms<R>(s, ld, full);
+  for (int a = 0; a < aggs.n; ++a) {
+    const b2_agg_t ag = aggs.a[a];
+    if (ag.col < 0) {  // COUNT(*)
+      sh_cnt[a][tid] += __popc(bits);
+      continue;
+    }
+    const b2_col_t& c = s.cols[ag.col];
+    int64_t raw[R];
+    ld.template load<R>(ag.col, bits, full, raw);
+    uint32_t ok = bits;
+    if (c.valid || c.dtype == B2_F64) ok &= ~b2_null_bits<R>(c, ld.row0, bits, raw);
+    sh_cnt[a][tid] += __popc(ok);
+    int64_t acc = sh_acc[a][tid];
+    switch (b2_agg_kind(ag.op, c.dtype)) {
+      case B2_K_SUM_I: acc = b2_fold_batch<R, B2_K_SUM_I>(acc, raw, ok); break;
+      case B2_K_SUM_F: acc = b2_fold_batch<R, B2_K_SUM_F>(acc, raw, ok); break;
+      case B2_K_SUMF_I: acc = b2_fold_batch<R, B2_K_SUMF_I>(acc, raw, ok); break;
+      case B2_K_MIN_I: acc = b2_fold_batch<R, B2_K_MIN_I>(acc, raw, ok); break;
+      case B2_K_MAX_I: acc = b2_fold_batch<R, B2_K_MAX_I>(acc, raw, ok); break;
+      case B2_K_MIN_F: acc = b2_fold_batch<R, B2_K_MIN_F>(acc, raw, ok); break;
+      case B2_K_MAX_F: acc = b2_fold_batch<R, B2_K_MAX_F>(acc, raw, ok); break;
+      default: break;
+    }
+    sh_acc[a][tid] = acc;
+  }
+}
+
+template <bool PIPE>
+__global__ void __launch_bounds__(PIPE ? B2_PIPE_THREADS : B2_BLOCK)
+b2_scan_agg_kernel(const __grid_constant__ b2_scan_t s, const __grid_constant__ b2_pipe_t pp,
+                   const __grid_constant__ b2_aggs_arg aggs, b2_partial* __restrict__ partials) {
   __shared__ int64_t sh_acc[B2_MAX_AGGS][B2_BLOCK];
   __shared__ int32_t sh_cnt[B2_MAX_AGGS][B2_BLOCK];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int a = 0; a < aggs.n; ++a) {
-    sh_acc[a][tid] = b2_identity(aggs.a[a].op);
-    sh_cnt[a][tid] = 0;
-  }
-  int64_t cnt64[1] = {0};
-  (void)cnt64;
-  for (int64_t base = (int64_t)blockIdx.x * B2_AGG_ROWS_PER_BLOCK; base < s.n;
-       base += (int64_t)gridDim.x * B2_AGG_ROWS_PER_BLOCK) {
-    const int64_t row0 = base + (int64_t)warp * (32 * B2_AGG_R) + lane;
-    bool full;
-    const uint32_t bits = b2_eval_terms<B2_AGG_R>(s, row0, full);
+  const int tid = threadIdx.x;
+  if (tid < B2_BLOCK) {
     for (int a = 0; a < aggs.n; ++a) {
-      const b2_agg_t ag = aggs.a[a];
-      if (ag.col < 0) {  // COUNT(*)
-        sh_cnt[a][tid] += __popc(bits);
-        continue;
-      }
-      const b2_col_t& c = s.cols[ag.col];
-      int64_t raw[B2_AGG_R];
-      b2_load_batch<B2_AGG_R>(c, row0, bits, full, raw);
-      uint32_t ok = bits;
-      if (c.valid || c.dtype == B2_F64) ok &= ~b2_null_bits<B2_AGG_R>(c, row0, bits, raw);
-      sh_cnt[a][tid] += __popc(ok);
-      int64_t acc = sh_acc[a][tid];
-      switch (b2_agg_kind(ag.op, c.dtype)) {
-        case B2_K_SUM_I: acc = b2_fold_batch<B2_AGG_R, B2_K_SUM_I>(acc, raw, ok); break;
-        case B2_K_SUM_F: acc = b2_fold_batch<B2_AGG_R, B2_K_SUM_F>(acc, raw, ok); break;
-        case B2_K_SUMF_I: acc = b2_fold_batch<B2_AGG_R, B2_K_SUMF_I>(acc, raw, ok); break;
-        case B2_K_MIN_I: acc = b2_fold_batch<B2_AGG_R, B2_K_MIN_I>(acc, raw, ok); break;
-        case B2_K_MAX_I: acc = b2_fold_batch<B2_AGG_R, B2_K_MAX_I>(acc, raw, ok); break;
-        case B2_K_MIN_F: acc = b2_fold_batch<B2_AGG_R, B2_K_MIN_F>(acc, raw, ok); break;
-        case B2_K_MAX_F: acc = b2_fold_batch<B2_AGG_R, B2_K_MAX_F>(acc, raw, ok); break;
-        default: break;
-      }
-      sh_acc[a][tid] = acc;
+      sh_acc[a][tid] = b2_identity(aggs.a[a].op);
+      sh_cnt[a][tid] = 0;
     }
   }
+  if (PIPE) b2_tile_pipeline(s, pp, [&](const auto& ld) { b2_scan_agg_body<B2_PIPE_R>(s, ld, aggs, sh_acc, sh_cnt, tid); });
+  else b2_tile_direct<B2_AGG_R>(s, [&](const auto& ld) { b2_scan_agg_body<B2_AGG_R>(s, ld, aggs, sh_acc, sh_cnt, tid); });
   __syncthreads();
   // block reduction in a fixed order: thread a folds the 256 per-thread slots of aggregate a.
   // (int32 per-thread counts cannot overflow: a thread sees < 2^31 rows of a < 2^31-row partition)
@@ -119,18 +124,32 @@ __global__ void b2_scan_agg_final_kernel(const __grid_constant__ b2_scan_t s,
                                          const b2_partial* __restrict__ partials, int nblocks,
                                          int64_t* __restrict__ out_acc, int64_t* __restrict__ out_cnt,
                                          int accumulate) {
-  const int a = threadIdx.x;
-  if (a >= aggs.n) return;
+  // one block per aggregate; thread t folds partials t, t+256, ... then a fixed-order tree in
+  // shared memory: the result does not depend on scheduling (bit-reproducible float sums).
+  __shared__ int64_t sh_r[B2_BLOCK];
+  __shared__ int64_t sh_c[B2_BLOCK];
+  const int a = blockIdx.x, t = threadIdx.x;
   const int op = aggs.a[a].op;
   const int dt = aggs.a[a].col >= 0 ? s.cols[aggs.a[a].col].dtype : B2_I64;
-  int64_t r = accumulate ? out_acc[a] : b2_identity(op);
-  int64_t c = accumulate ? out_cnt[a] : 0;
-  for (int b = 0; b < nblocks; ++b) {
+  int64_t r = b2_identity(op), c = 0;
+  for (int b = t; b < nblocks; b += B2_BLOCK) {
     r = b2_combine(op, dt, r, partials[b].acc[a]);
     c += partials[b].cnt[a];
   }
-  out_acc[a] = r;
-  out_cnt[a] = c;
+  sh_r[t] = r;
+  sh_c[t] = c;
+  __syncthreads();
+  for (int w = B2_BLOCK / 2; w > 0; w >>= 1) {
+    if (t < w) {
+      sh_r[t] = b2_combine(op, dt, sh_r[t], sh_r[t + w]);
+      sh_c[t] += sh_c[t + w];
+    }
+    __syncthreads();
+  }
+  if (t == 0) {
+    out_acc[a] = accumulate ? b2_combine(op, dt, out_acc[a], sh_r[0]) : sh_r[0];
+    out_cnt[a] = accumulate ? out_cnt[a] + sh_c[0] : sh_c[0];
+  }
 }
 
 // =======================================================================================
@@ -346,13 +365,23 @@ int32_t b2_scan_agg(const b2_scan_t* scan, const b2_agg_t* aggs, int32_t naggs, 
   if (rc) return rc;
   B2_REQUIRE(d_out_acc && d_out_cnt && ws, "null argument");
   cudaStream_t st = (cudaStream_t)stream;
-  int64_t nblk = (scan->n + B2_AGG_ROWS_PER_BLOCK - 1) / B2_AGG_ROWS_PER_BLOCK;
-  int grid = b2_wave_grid(b2_scan_agg_kernel, B2_BLOCK, nblk);
-  if (grid > 148 * 16) grid = 148 * 16;
+  b2_pipe_t pp;
+  b2_make_pipe(*scan, &pp);
   b2_partial* partials = reinterpret_cast<b2_partial*>(ws);
-  b2_scan_agg_kernel<<<grid, B2_BLOCK, 0, st>>>(*scan, aa, partials);
+  int grid;
+  if (pp.enabled) {
+    grid = b2_pipe_grid(b2_scan_agg_kernel<true>, pp, scan->n);
+    if (grid > 148 * 16) grid = 148 * 16;
+    b2_scan_agg_kernel<true><<<grid, B2_PIPE_THREADS, pp.smem_bytes, st>>>(*scan, pp, aa, partials);
+  } else {
+    int64_t nblk = (scan->n + B2_AGG_ROWS_PER_BLOCK - 1) / B2_AGG_ROWS_PER_BLOCK;
+    grid = b2_wave_grid(b2_scan_agg_kernel<false>, B2_BLOCK, nblk);
+    if (grid > 148 * 16) grid = 148 * 16;
+    b2_scan_agg_kernel<false><<<grid, B2_BLOCK, 0, st>>>(*scan, pp, aa, partials);
+  }
   B2_CHECK_LAUNCH("b2_scan_agg_kernel");
-  b2_scan_agg_final_kernel<<<1, 32, 0, st>>>(*scan, aa, partials, grid, d_out_acc, d_out_cnt, accumulate);
+  if (naggs > 0)
+    b2_scan_agg_final_kernel<<<naggs, B2_BLOCK, 0, st>>>(*scan, aa, partials, grid, d_out_acc, d_out_cnt, accumulate);
   B2_CHECK_LAUNCH("b2_scan_agg_final_kernel");
   return B2_OK;
 }

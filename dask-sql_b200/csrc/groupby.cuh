@@ -5,38 +5,46 @@
 // plus the fused star pipeline (filter -> key lookup -> aggregate).
 #pragma once
 #include "common.cuh"
+#include "pipeline.cuh"
 
 #define B2_GB_R 8
 #define B2_GB_ROWS_PER_BLOCK (B2_BLOCK * B2_GB_R)
 #define B2_MAX_PROBE 1024
 
 // ---- dense ------------------------------------------------------------------------------
-__global__ void __launch_bounds__(B2_BLOCK)
-b2_groupby_dense_kernel(const __grid_constant__ b2_scan_t s, int key_col, int64_t kmin, int64_t nslots,
-                        const __grid_constant__ b2_aggs_arg aggs, const __grid_constant__ b2_aggstate_t st) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+template <class LD>
+__device__ __forceinline__ void b2_dense_body(const b2_scan_t& s, const LD& ld, int key_col, int64_t kmin,
+                                              int64_t nslots, const b2_aggs_arg& aggs, const b2_aggstate_t& st) {
   const b2_col_t& kc = s.cols[key_col];
-  for (int64_t base = (int64_t)blockIdx.x * B2_GB_ROWS_PER_BLOCK; base < s.n;
-       base += (int64_t)gridDim.x * B2_GB_ROWS_PER_BLOCK) {
-    const int64_t row0 = base + (int64_t)warp * (32 * B2_GB_R) + lane;
-    bool full;
-    const uint32_t bits = b2_eval_terms<B2_GB_R>(s, row0, full);
-    int64_t key[B2_GB_R];
-    b2_load_batch<B2_GB_R>(kc, row0, bits, full, key);
-    int64_t slot[B2_GB_R];
+  bool full;
+  const uint32_t bits = b2_eval_terms<B2_GB_R>(s, ld, full);
+  int64_t key[B2_GB_R];
+  ld.template load<B2_GB_R>(key_col, bits, full, key);
+  uint32_t kvalid = bits;
+  if (kc.valid) kvalid = b2_valid_bits<B2_GB_R>(kc.valid, ld.row0, bits);
+  int64_t slot[B2_GB_R];
 #pragma unroll
-    for (int j = 0; j < B2_GB_R; ++j) {
-      slot[j] = -1;
-      if ((bits >> j) & 1) {
-        if (kc.valid && !b2_bit(kc.valid, row0 + (int64_t)j * 32)) slot[j] = nslots - 1;
-        else {
-          const uint64_t d = (uint64_t)key[j] - (uint64_t)kmin;
-          slot[j] = d < (uint64_t)(nslots - 1) ? (int64_t)d : -1;  // out of range cannot happen if stats are right
-        }
+  for (int j = 0; j < B2_GB_R; ++j) {
+    slot[j] = -1;
+    if ((bits >> j) & 1) {
+      if (!((kvalid >> j) & 1)) slot[j] = nslots - 1;
+      else {
+        const uint64_t d = (uint64_t)key[j] - (uint64_t)kmin;
+        slot[j] = d < (uint64_t)(nslots - 1) ? (int64_t)d : -1;  // out of range cannot happen if stats are right
       }
     }
-    b2_apply_aggs<B2_GB_R>(s, aggs.a, aggs.n, st, row0, slot);
   }
+  b2_apply_aggs<B2_GB_R>(s, ld, aggs.a, aggs.n, st, slot);
+}
+
+template <bool PIPE>
+__global__ void __launch_bounds__(PIPE ? B2_PIPE_THREADS : B2_BLOCK)
+b2_groupby_dense_kernel(const __grid_constant__ b2_scan_t s, const __grid_constant__ b2_pipe_t pp, int key_col,
+                        int64_t kmin, int64_t nslots, const __grid_constant__ b2_aggs_arg aggs,
+                        const __grid_constant__ b2_aggstate_t st) {
+  auto body = [&](const auto& ld) { b2_dense_body(s, ld, key_col, kmin, nslots, aggs, st); };
+  if (PIPE) b2_tile_pipeline(s, pp, body);
+  else b2_tile_direct<B2_GB_R>(s, body);
 }
 
 // ---- hash, single 64-bit key ----------------------------------------------------------------
@@ -57,32 +65,38 @@ __device__ __forceinline__ int64_t b2_hash1_slot(int64_t* __restrict__ tk, int64
   return -1;
 }
 
-__global__ void __launch_bounds__(B2_BLOCK)
-b2_groupby_hash1_kernel(const __grid_constant__ b2_scan_t s, int key_col, int64_t* __restrict__ tk,
-                        int64_t cap, const __grid_constant__ b2_aggs_arg aggs,
-                        const __grid_constant__ b2_aggstate_t st, int32_t* __restrict__ flags) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+template <class LD>
+__device__ __forceinline__ void b2_hash1_body(const b2_scan_t& s, const LD& ld, int key_col, int64_t* __restrict__ tk,
+                                              int64_t cap, const b2_aggs_arg& aggs, const b2_aggstate_t& st,
+                                              int32_t* __restrict__ flags) {
   const b2_col_t& kc = s.cols[key_col];
-  for (int64_t base = (int64_t)blockIdx.x * B2_GB_ROWS_PER_BLOCK; base < s.n;
-       base += (int64_t)gridDim.x * B2_GB_ROWS_PER_BLOCK) {
-    const int64_t row0 = base + (int64_t)warp * (32 * B2_GB_R) + lane;
-    bool full;
-    const uint32_t bits = b2_eval_terms<B2_GB_R>(s, row0, full);
-    int64_t key[B2_GB_R];
-    b2_load_batch<B2_GB_R>(kc, row0, bits, full, key);
-    int64_t slot[B2_GB_R];
+  bool full;
+  const uint32_t bits = b2_eval_terms<B2_GB_R>(s, ld, full);
+  int64_t key[B2_GB_R];
+  ld.template load<B2_GB_R>(key_col, bits, full, key);
+  const uint32_t knull = b2_null_bits<B2_GB_R>(kc, ld.row0, bits, key);
+  int64_t slot[B2_GB_R];
 #pragma unroll
-    for (int j = 0; j < B2_GB_R; ++j) {
-      slot[j] = -1;
-      if (!((bits >> j) & 1)) continue;
-      int64_t k = key[j];
-      if (b2_is_null(kc, row0 + (int64_t)j * 32, k)) { slot[j] = cap; flags[1] = 1; continue; }
-      if (kc.dtype == B2_F64 && k == (int64_t)0x8000000000000000LL) k = 0;  // -0.0 groups with 0.0
-      else if (k == B2_EMPTY_KEY) { slot[j] = cap + 1; flags[2] = 1; continue; }
-      slot[j] = b2_hash1_slot(tk, cap, k, flags);
-    }
-    b2_apply_aggs<B2_GB_R>(s, aggs.a, aggs.n, st, row0, slot);
+  for (int j = 0; j < B2_GB_R; ++j) {
+    slot[j] = -1;
+    if (!((bits >> j) & 1)) continue;
+    int64_t k = key[j];
+    if ((knull >> j) & 1) { slot[j] = cap; flags[1] = 1; continue; }
+    if (kc.dtype == B2_F64 && k == (int64_t)0x8000000000000000LL) k = 0;  // -0.0 groups with 0.0
+    else if (k == B2_EMPTY_KEY) { slot[j] = cap + 1; flags[2] = 1; continue; }
+    slot[j] = b2_hash1_slot(tk, cap, k, flags);
   }
+  b2_apply_aggs<B2_GB_R>(s, ld, aggs.a, aggs.n, st, slot);
+}
+
+template <bool PIPE>
+__global__ void __launch_bounds__(PIPE ? B2_PIPE_THREADS : B2_BLOCK)
+b2_groupby_hash1_kernel(const __grid_constant__ b2_scan_t s, const __grid_constant__ b2_pipe_t pp, int key_col,
+                        int64_t* __restrict__ tk, int64_t cap, const __grid_constant__ b2_aggs_arg aggs,
+                        const __grid_constant__ b2_aggstate_t st, int32_t* __restrict__ flags) {
+  auto body = [&](const auto& ld) { b2_hash1_body(s, ld, key_col, tk, cap, aggs, st, flags); };
+  if (PIPE) b2_tile_pipeline(s, pp, body);
+  else b2_tile_direct<B2_GB_R>(s, body);
 }
 
 // ---- hash, composite keys -------------------------------------------------------------------
@@ -124,39 +138,55 @@ __device__ __forceinline__ int64_t b2_hashk_slot(int64_t* __restrict__ tk, uint8
   return -1;
 }
 
-__global__ void __launch_bounds__(B2_BLOCK)
-b2_groupby_hashk_kernel(const __grid_constant__ b2_scan_t s, const __grid_constant__ b2_keys_arg keys,
-                        int64_t* __restrict__ tk, uint8_t* __restrict__ tnull, int32_t* __restrict__ tstate,
-                        int64_t cap, const __grid_constant__ b2_aggs_arg aggs,
-                        const __grid_constant__ b2_aggstate_t st, int32_t* __restrict__ flags) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int64_t base = (int64_t)blockIdx.x * B2_GB_ROWS_PER_BLOCK; base < s.n;
-       base += (int64_t)gridDim.x * B2_GB_ROWS_PER_BLOCK) {
-    const int64_t row0 = base + (int64_t)warp * (32 * B2_GB_R) + lane;
-    const uint32_t bits = b2_eval_terms<B2_GB_R>(s, row0);
-    int64_t slot[B2_GB_R];
+template <class LD>
+__device__ __forceinline__ void b2_hashk_body(const b2_scan_t& s, const LD& ld, const b2_keys_arg& keys,
+                                              int64_t* __restrict__ tk, uint8_t* __restrict__ tnull,
+                                              int32_t* __restrict__ tstate, int64_t cap, const b2_aggs_arg& aggs,
+                                              const b2_aggstate_t& st, int32_t* __restrict__ flags) {
+  bool full;
+  const uint32_t bits = b2_eval_terms<B2_GB_R>(s, ld, full);
+  int64_t kv[B2_MAX_KEYS][B2_GB_R];
+  uint32_t knull[B2_MAX_KEYS];
 #pragma unroll
-    for (int j = 0; j < B2_GB_R; ++j) {
-      slot[j] = -1;
-      if (!((bits >> j) & 1)) continue;
-      const int64_t row = row0 + (int64_t)j * 32;
-      int64_t key[B2_MAX_KEYS];
-      uint32_t nullmask = 0;
-#pragma unroll
-      for (int k = 0; k < B2_MAX_KEYS; ++k) {
-        key[k] = 0;
-        if (k < keys.n) {
-          const b2_col_t& kc = s.cols[keys.cols[k]];
-          int64_t v = b2_load_raw(kc, row);
-          if (b2_is_null(kc, row, v)) { nullmask |= 1u << k; v = 0; }
-          else if (kc.dtype == B2_F64 && v == (int64_t)0x8000000000000000LL) v = 0;
-          key[k] = v;
-        }
-      }
-      slot[j] = b2_hashk_slot(tk, tnull, tstate, cap, keys.n, key, nullmask, flags);
+  for (int k = 0; k < B2_MAX_KEYS; ++k) {
+    knull[k] = 0;
+    if (k < keys.n) {
+      ld.template load<B2_GB_R>(keys.cols[k], bits, full, kv[k]);
+      knull[k] = b2_null_bits<B2_GB_R>(s.cols[keys.cols[k]], ld.row0, bits, kv[k]);
     }
-    b2_apply_aggs<B2_GB_R>(s, aggs.a, aggs.n, st, row0, slot);
   }
+  int64_t slot[B2_GB_R];
+#pragma unroll
+  for (int j = 0; j < B2_GB_R; ++j) {
+    slot[j] = -1;
+    if (!((bits >> j) & 1)) continue;
+    int64_t key[B2_MAX_KEYS];
+    uint32_t nullmask = 0;
+#pragma unroll
+    for (int k = 0; k < B2_MAX_KEYS; ++k) {
+      key[k] = 0;
+      if (k < keys.n) {
+        int64_t v = kv[k][j];
+        if ((knull[k] >> j) & 1) { nullmask |= 1u << k; v = 0; }
+        else if (s.cols[keys.cols[k]].dtype == B2_F64 && v == (int64_t)0x8000000000000000LL) v = 0;
+        key[k] = v;
+      }
+    }
+    slot[j] = b2_hashk_slot(tk, tnull, tstate, cap, keys.n, key, nullmask, flags);
+  }
+  b2_apply_aggs<B2_GB_R>(s, ld, aggs.a, aggs.n, st, slot);
+}
+
+template <bool PIPE>
+__global__ void __launch_bounds__(PIPE ? B2_PIPE_THREADS : B2_BLOCK)
+b2_groupby_hashk_kernel(const __grid_constant__ b2_scan_t s, const __grid_constant__ b2_pipe_t pp,
+                        const __grid_constant__ b2_keys_arg keys, int64_t* __restrict__ tk,
+                        uint8_t* __restrict__ tnull, int32_t* __restrict__ tstate, int64_t cap,
+                        const __grid_constant__ b2_aggs_arg aggs, const __grid_constant__ b2_aggstate_t st,
+                        int32_t* __restrict__ flags) {
+  auto body = [&](const auto& ld) { b2_hashk_body(s, ld, keys, tk, tnull, tstate, cap, aggs, st, flags); };
+  if (PIPE) b2_tile_pipeline(s, pp, body);
+  else b2_tile_direct<B2_GB_R>(s, body);
 }
 
 // ---- fused star pipeline ----------------------------------------------------------------------
@@ -221,31 +251,37 @@ __device__ __forceinline__ int32_t b2_star_lookup(const b2_starlookup_t& lk, int
   return -1;
 }
 
-__global__ void __launch_bounds__(B2_BLOCK)
-b2_star_agg_kernel(const __grid_constant__ b2_scan_t s, int fk_col, const __grid_constant__ b2_starlookup_t lk,
-                   const __grid_constant__ b2_aggs_arg aggs, const __grid_constant__ b2_aggstate_t st) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+template <class LD>
+__device__ __forceinline__ void b2_star_body(const b2_scan_t& s, const LD& ld, int fk_col, const b2_starlookup_t& lk,
+                                             const b2_aggs_arg& aggs, const b2_aggstate_t& st) {
   const b2_col_t& kc = s.cols[fk_col];
-  for (int64_t base = (int64_t)blockIdx.x * B2_GB_ROWS_PER_BLOCK; base < s.n;
-       base += (int64_t)gridDim.x * B2_GB_ROWS_PER_BLOCK) {
-    const int64_t row0 = base + (int64_t)warp * (32 * B2_GB_R) + lane;
-    bool full;
-    const uint32_t bits = b2_eval_terms<B2_GB_R>(s, row0, full);
-    int64_t key[B2_GB_R];
-    b2_load_batch<B2_GB_R>(kc, row0, bits, full, key);
-    int32_t found[B2_GB_R];
+  bool full;
+  const uint32_t bits = b2_eval_terms<B2_GB_R>(s, ld, full);
+  int64_t key[B2_GB_R];
+  ld.template load<B2_GB_R>(fk_col, bits, full, key);
+  uint32_t live = bits;
+  if (kc.valid) live &= b2_valid_bits<B2_GB_R>(kc.valid, ld.row0, bits);
+  // all lookups of the batch are issued before the first one is consumed
+  int32_t found[B2_GB_R];
 #pragma unroll
-    for (int j = 0; j < B2_GB_R; ++j) {
-      found[j] = -1;
-      if (((bits >> j) & 1) && !b2_is_null(kc, row0 + (int64_t)j * 32, key[j]) &&
-          !(lk.dense == 0 && key[j] == B2_EMPTY_KEY))
-        found[j] = b2_star_lookup(lk, key[j]);
-    }
-    int64_t slot[B2_GB_R];
-#pragma unroll
-    for (int j = 0; j < B2_GB_R; ++j) slot[j] = found[j];
-    b2_apply_aggs<B2_GB_R>(s, aggs.a, aggs.n, st, row0, slot);
+  for (int j = 0; j < B2_GB_R; ++j) {
+    found[j] = -1;
+    if (((live >> j) & 1) && !(lk.dense == 0 && key[j] == B2_EMPTY_KEY)) found[j] = b2_star_lookup(lk, key[j]);
   }
+  int64_t slot[B2_GB_R];
+#pragma unroll
+  for (int j = 0; j < B2_GB_R; ++j) slot[j] = found[j];
+  b2_apply_aggs<B2_GB_R>(s, ld, aggs.a, aggs.n, st, slot);
+}
+
+template <bool PIPE>
+__global__ void __launch_bounds__(PIPE ? B2_PIPE_THREADS : B2_BLOCK)
+b2_star_agg_kernel(const __grid_constant__ b2_scan_t s, const __grid_constant__ b2_pipe_t pp, int fk_col,
+                   const __grid_constant__ b2_starlookup_t lk, const __grid_constant__ b2_aggs_arg aggs,
+                   const __grid_constant__ b2_aggstate_t st) {
+  auto body = [&](const auto& ld) { b2_star_body(s, ld, fk_col, lk, aggs, st); };
+  if (PIPE) b2_tile_pipeline(s, pp, body);
+  else b2_tile_direct<B2_GB_R>(s, body);
 }
 
 extern "C" {
@@ -272,9 +308,16 @@ int32_t b2_groupby_dense(const b2_scan_t* scan, int32_t key_col, int64_t kmin, i
   B2_REQUIRE(scan->cols[key_col].dtype == B2_I64 || scan->cols[key_col].dtype == B2_U8, "dense keys must be integers");
   B2_REQUIRE(nslots >= 2, "nslots must cover the key range plus the NULL slot");
   if (scan->n == 0) return B2_OK;
-  int64_t nblk = (scan->n + B2_GB_ROWS_PER_BLOCK - 1) / B2_GB_ROWS_PER_BLOCK;
-  int grid = b2_wave_grid(b2_groupby_dense_kernel, B2_BLOCK, nblk);
-  b2_groupby_dense_kernel<<<grid, B2_BLOCK, 0, (cudaStream_t)stream>>>(*scan, key_col, kmin, nslots, aa, *st);
+  b2_pipe_t pp;
+  b2_make_pipe(*scan, &pp);
+  if (pp.enabled) {
+    int grid = b2_pipe_grid(b2_groupby_dense_kernel<true>, pp, scan->n);
+    b2_groupby_dense_kernel<true><<<grid, B2_PIPE_THREADS, pp.smem_bytes, (cudaStream_t)stream>>>(*scan, pp, key_col, kmin, nslots, aa, *st);
+  } else {
+    int64_t nblk = (scan->n + B2_GB_ROWS_PER_BLOCK - 1) / B2_GB_ROWS_PER_BLOCK;
+    int grid = b2_wave_grid(b2_groupby_dense_kernel<false>, B2_BLOCK, nblk);
+    b2_groupby_dense_kernel<false><<<grid, B2_BLOCK, 0, (cudaStream_t)stream>>>(*scan, pp, key_col, kmin, nslots, aa, *st);
+  }
   B2_CHECK_LAUNCH("b2_groupby_dense_kernel");
   return B2_OK;
 }
@@ -292,9 +335,16 @@ int32_t b2_groupby_hash1(const b2_scan_t* scan, int32_t key_col, int64_t* table_
   B2_REQUIRE(table_keys && d_flags, "null argument");
   B2_REQUIRE(b2_pow2(cap), "cap must be a power of two");
   if (scan->n == 0) return B2_OK;
-  int64_t nblk = (scan->n + B2_GB_ROWS_PER_BLOCK - 1) / B2_GB_ROWS_PER_BLOCK;
-  int grid = b2_wave_grid(b2_groupby_hash1_kernel, B2_BLOCK, nblk);
-  b2_groupby_hash1_kernel<<<grid, B2_BLOCK, 0, (cudaStream_t)stream>>>(*scan, key_col, table_keys, cap, aa, *st, d_flags);
+  b2_pipe_t pp;
+  b2_make_pipe(*scan, &pp);
+  if (pp.enabled) {
+    int grid = b2_pipe_grid(b2_groupby_hash1_kernel<true>, pp, scan->n);
+    b2_groupby_hash1_kernel<true><<<grid, B2_PIPE_THREADS, pp.smem_bytes, (cudaStream_t)stream>>>(*scan, pp, key_col, table_keys, cap, aa, *st, d_flags);
+  } else {
+    int64_t nblk = (scan->n + B2_GB_ROWS_PER_BLOCK - 1) / B2_GB_ROWS_PER_BLOCK;
+    int grid = b2_wave_grid(b2_groupby_hash1_kernel<false>, B2_BLOCK, nblk);
+    b2_groupby_hash1_kernel<false><<<grid, B2_BLOCK, 0, (cudaStream_t)stream>>>(*scan, pp, key_col, table_keys, cap, aa, *st, d_flags);
+  }
   B2_CHECK_LAUNCH("b2_groupby_hash1_kernel");
   return B2_OK;
 }
@@ -318,10 +368,18 @@ int32_t b2_groupby_hashk(const b2_scan_t* scan, const int32_t* key_cols, int32_t
     ka.cols[k] = key_cols[k];
   }
   if (scan->n == 0) return B2_OK;
-  int64_t nblk = (scan->n + B2_GB_ROWS_PER_BLOCK - 1) / B2_GB_ROWS_PER_BLOCK;
-  int grid = b2_wave_grid(b2_groupby_hashk_kernel, B2_BLOCK, nblk);
-  b2_groupby_hashk_kernel<<<grid, B2_BLOCK, 0, (cudaStream_t)stream>>>(*scan, ka, table_keys, table_nulls,
+  b2_pipe_t pp;
+  b2_make_pipe(*scan, &pp);
+  if (pp.enabled) {
+    int grid = b2_pipe_grid(b2_groupby_hashk_kernel<true>, pp, scan->n);
+    b2_groupby_hashk_kernel<true><<<grid, B2_PIPE_THREADS, pp.smem_bytes, (cudaStream_t)stream>>>(*scan, pp, ka, table_keys, table_nulls,
                                                                         table_state, cap, aa, *st, d_flags);
+  } else {
+    int64_t nblk = (scan->n + B2_GB_ROWS_PER_BLOCK - 1) / B2_GB_ROWS_PER_BLOCK;
+    int grid = b2_wave_grid(b2_groupby_hashk_kernel<false>, B2_BLOCK, nblk);
+    b2_groupby_hashk_kernel<false><<<grid, B2_BLOCK, 0, (cudaStream_t)stream>>>(*scan, pp, ka, table_keys, table_nulls,
+                                                                        table_state, cap, aa, *st, d_flags);
+  }
   B2_CHECK_LAUNCH("b2_groupby_hashk_kernel");
   return B2_OK;
 }
@@ -375,9 +433,16 @@ int32_t b2_star_agg(const b2_scan_t* scan, int32_t fk_col, const b2_starlookup_t
   if (lk->dense) B2_REQUIRE(lk->lookup && lk->range > 0, "bad dense lookup");
   else B2_REQUIRE(lk->table_keys && lk->table_slots && b2_pow2(lk->cap), "bad hash lookup");
   if (scan->n == 0) return B2_OK;
-  int64_t nblk = (scan->n + B2_GB_ROWS_PER_BLOCK - 1) / B2_GB_ROWS_PER_BLOCK;
-  int grid = b2_wave_grid(b2_star_agg_kernel, B2_BLOCK, nblk);
-  b2_star_agg_kernel<<<grid, B2_BLOCK, 0, (cudaStream_t)stream>>>(*scan, fk_col, *lk, aa, *st);
+  b2_pipe_t pp;
+  b2_make_pipe(*scan, &pp);
+  if (pp.enabled) {
+    int grid = b2_pipe_grid(b2_star_agg_kernel<true>, pp, scan->n);
+    b2_star_agg_kernel<true><<<grid, B2_PIPE_THREADS, pp.smem_bytes, (cudaStream_t)stream>>>(*scan, pp, fk_col, *lk, aa, *st);
+  } else {
+    int64_t nblk = (scan->n + B2_GB_ROWS_PER_BLOCK - 1) / B2_GB_ROWS_PER_BLOCK;
+    int grid = b2_wave_grid(b2_star_agg_kernel<false>, B2_BLOCK, nblk);
+    b2_star_agg_kernel<false><<<grid, B2_BLOCK, 0, (cudaStream_t)stream>>>(*scan, pp, fk_col, *lk, aa, *st);
+  }
   B2_CHECK_LAUNCH("b2_star_agg_kernel");
   return B2_OK;
 }

@@ -160,6 +160,9 @@ class ScanCtx:
             t = E.as_term(c)
             if t is not None and len(self.terms) < L.MAX_TERMS - 1:
                 name, op, lit = t
+                col = part[name]
+                if op == L.IS_NOT_NULL and col.valid is None and col.dtype != F64:
+                    continue  # statically true (e.g. the planner's IS NOT NULL on join keys): no load, no term
                 self.terms.append(TermSpec(self._slot_for_name(name), op, lit))
             else:
                 complex_.append(c)

@@ -143,6 +143,18 @@ class DaskAggregatePlugin(BaseRelPlugin):
             if expr.isDistinctAgg() and backend_name is None:
                 raise NotImplementedError("COUNT(DISTINCT *)")
             output_col = expr.toString()
+            if filter_backend_col is not None and not expr.isDistinctAgg():
+                # agg(x) FILTER (WHERE f)  ==  agg(CASE WHEN f THEN x END): NULLs are skipped by every
+                # aggregate, so the filtered aggregate shares the single fused pass of the unfiltered
+                # ones instead of the reference's extra groupby per filter bucket (aggregate.py:352-373)
+                cond = df[filter_backend_col]
+                if backend_name is None:
+                    masked, aggregation_function = cond.where(cond), "count"
+                else:
+                    masked = df[backend_name].where(cond)
+                input_col = new_temporary_column(df)
+                df = df.assign(**{input_col: masked})
+                filter_backend_col = None
             collected_aggregations[(filter_backend_col, backend_name if expr.isDistinctAgg() else None)].append(
                 (input_col, output_col, aggregation_function))
             output_column_order.append(output_col)

@@ -88,11 +88,24 @@ def test_where(c):
     # tests/integration/test_compatibility.py:177-196 (int columns; float columns carry NaN whose
     # comparison semantics differ between numpy and sqlite)
     df = make_rand_df(100, a=(int, 30), b=(int, 30), c=(float, 0))
+    eq_sqlite(c, "SELECT * FROM a WHERE TRUE OR TRUE", a=df)
+    eq_sqlite(c, "SELECT * FROM a WHERE FALSE AND FALSE", a=df)
     eq_sqlite(c, "SELECT * FROM a WHERE a<2 OR c>0.8", a=df)
     eq_sqlite(c, "SELECT * FROM a WHERE a<2 AND c>0.3", a=df)
     eq_sqlite(c, "SELECT * FROM a WHERE a IS NULL OR (b>=5 AND c<0.5)", a=df)
-    eq_sqlite(c, "SELECT * FROM a WHERE a IS NOT NULL AND NOT (b<5)", a=df)
-    eq_sqlite(c, "SELECT a + b AS s, a * 2 - b AS t, c / 2 AS h FROM a WHERE a = b OR a <> 3", a=df)
+    eq_sqlite(c, "SELECT * FROM a WHERE c IS NOT NULL OR (a<5 AND b IS NOT NULL)", a=df)
+    eq_sqlite(c, "SELECT a + b AS s, a * 2 - b AS t, c / 2 AS h FROM a WHERE a = b OR a > 3", a=df)
+    # the reference's float block (test_compatibility.py:191-196), NaN as NULL in all three columns
+    df = make_rand_df(100, a=(float, 30), b=(float, 30), c=(float, 30))
+    eq_sqlite(c, "SELECT * FROM a WHERE a<0.5 AND b<0.5 AND c<0.5", a=df)
+    eq_sqlite(c, "SELECT * FROM a WHERE a<0.5 OR b<0.5 AND c<0.5", a=df)
+    eq_sqlite(c, "SELECT * FROM a WHERE a IS NULL OR (b<0.5 AND c<0.5)", a=df)
+    eq_sqlite(c, "SELECT * FROM a WHERE a*b IS NULL OR (b*c<0.5 AND c*a<0.5)", a=df)
+    # NOT / <> over a nullable INTEGER column follow SQL three-valued logic (validity bitmap)
+    df = pd.DataFrame({"a": pd.array(np.where(np.arange(100) % 7 == 0, None, np.arange(100) % 10), dtype="Int64"),
+                       "b": np.arange(100) % 4})
+    eq_sqlite(c, "SELECT * FROM a WHERE NOT (a<5) AND b <> 1", a=df)
+    eq_sqlite(c, "SELECT * FROM a WHERE a <> 3 OR b = 0", a=df)
 
 
 def test_in_between(c):
