@@ -109,6 +109,9 @@ def workload_config(args, n):
             "fact_rows_total": int(args.rows), "fact_rows_per_gpu": int(args.rows) // n, "dim_rows": DIM_ROWS,
             "groups": N_GROUPS, "partitions_per_gpu": PARTS_PER_GPU, "query": QUERY,
             "l2": "inputs (24 B/row x rows) >> 126 MB L2, no flush needed",
+            "planning": "Context.sql() is called every step; its plan (not its result) is served from the "
+                        "prepared-statement cache after the first call; build side, lookup and group table "
+                        "are rebuilt every step",
             "parallelism": f"fact sharded over {n} GPU(s); dim broadcast from rank 0 (NCCL); "
                            "dense partial aggregates all-reduced (NCCL)" if n > 1 else "single GPU"}
 

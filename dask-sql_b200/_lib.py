@@ -121,6 +121,9 @@ _SIGS = {
     "b2_join_count": [C.POINTER(Scan), C.POINTER(C.c_int32), C.POINTER(JoinTable), C.c_int32, _P, _P],
     "b2_join_write": [C.POINTER(Scan), C.POINTER(C.c_int32), C.POINTER(JoinTable), C.c_int32, _P, _P, _P,
                       _P, _P],
+    "b2_join_write_gather": [C.POINTER(Scan), C.POINTER(C.c_int32), C.POINTER(JoinTable), C.c_int32, _P, _P, _P,
+                             _P, C.c_int32, C.POINTER(C.c_int32), C.POINTER(_P), C.POINTER(_P), C.c_int32,
+                             C.POINTER(Col), C.POINTER(_P), C.POINTER(_P), _P],
     "b2_dense_slots": [C.POINTER(Col), C.c_int64, C.c_int64, C.c_int32, _P, _P],
     "b2_star_build_dense": [C.POINTER(Col), _P, C.c_int64, _P, C.c_int64, C.c_int64, _P, _P, _P],
     "b2_star_build_hash": [C.POINTER(Col), _P, C.c_int64, _P, _P, _P, C.c_int64, _P, _P],
@@ -165,6 +168,7 @@ join_build = _wrap("b2_join_build")
 join_build_dense = _wrap("b2_join_build_dense")
 join_count = _wrap("b2_join_count")
 join_write = _wrap("b2_join_write")
+join_write_gather = _wrap("b2_join_write_gather")
 dense_slots = _wrap("b2_dense_slots")
 star_build_dense = _wrap("b2_star_build_dense")
 star_build_hash = _wrap("b2_star_build_hash")

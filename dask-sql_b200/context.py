@@ -44,6 +44,8 @@ class Context:
         self.schema: Dict[str, SchemaContainer] = {self.schema_name: SchemaContainer(self.schema_name)}
         self.device = device
         self.sql_server = None
+        self._catalog_version = 0          # bumped by create_table / drop_table / schema changes
+        self._plan_cache = {}
         logger.setLevel(logging_level)
 
         RelConverter.add_plugin_class(logical.DaskAggregatePlugin, replace=False)
@@ -107,18 +109,22 @@ class Context:
         dc.statistics = statistics
         self.schema[schema_name].tables[table_name.lower()] = dc
         self.schema[schema_name].statistics[table_name.lower()] = statistics
+        self._catalog_version += 1
 
     def drop_table(self, table_name: str, schema_name: str = None):
         schema_name = schema_name or self.schema_name
         del self.schema[schema_name].tables[table_name.lower()]
+        self._catalog_version += 1
 
     def create_schema(self, schema_name: str):
         self.schema[schema_name] = SchemaContainer(schema_name)
+        self._catalog_version += 1
 
     def drop_schema(self, schema_name: str):
         if schema_name == self.DEFAULT_SCHEMA_NAME:
             raise RuntimeError(f"Default Schema `{schema_name}` cannot be deleted")
         del self.schema[schema_name]
+        self._catalog_version += 1
         if self.schema_name == schema_name:
             self.schema_name = self.DEFAULT_SCHEMA_NAME
 
@@ -139,7 +145,23 @@ class Context:
                 for df_name, df in dataframes.items():
                     self.create_table(df_name, df, gpu=gpu)
             if isinstance(sql, str):
-                rel, _ = self._get_ral(sql)
+                # prepared-statement cache: planning + plugin conversion are pure functions of
+                # (SQL text, catalog, config), and LazyFrames are immutable
+                from .utils import Pluggable
+                key = (sql, self._catalog_version, Pluggable.version, self.schema_name, dask_config.get("sql.optimize"),
+                       dask_config.get("sql.identifier.case_sensitive"), dask_config.get("sql.join.broadcast"),
+                       str(dask_config.get("sql.aggregate")))
+                df = self._plan_cache.get(key)
+                if df is None:
+                    rel, _ = self._get_ral(sql)
+                    df = self._compute_table_from_rel(rel, True)
+                    if isinstance(df, LazyFrame):
+                        if len(self._plan_cache) > 256:
+                            self._plan_cache.clear()
+                        self._plan_cache[key] = df
+                if return_futures or not isinstance(df, LazyFrame):
+                    return df
+                return df.compute()
             elif isinstance(sql, LogicalPlan):
                 rel = sql
             else:
@@ -174,19 +196,17 @@ class Context:
         """SQL -> (optimised plan, explain string) (context.py:819-872)."""
         logger.debug(f"Entering _get_ral('{sql}')")
         case_sensitive = dask_config.get("sql.identifier.case_sensitive")
-        try:
-            rel = plan_sql(sql, self._catalog, case_sensitive, optimize_plan=False)
-        except ParsingException:
-            raise
-        rel_string = rel.explain_original()
+        rel = None
         if dask_config.get("sql.optimize"):
             try:
                 rel = plan_sql(sql, self._catalog, case_sensitive, optimize_plan=True)
-                rel_string = rel.explain_original()
             except ParsingException:
                 raise
             except Exception as e:  # optimizer failure -> unoptimised plan (context.py:858-864)
                 warnings.warn(f"The optimizer failed ({OptimizationException(e)}); using the unoptimized plan")
+        if rel is None:
+            rel = plan_sql(sql, self._catalog, case_sensitive, optimize_plan=False)
+        rel_string = rel.explain_original()
         logger.debug(f"_get_ral -> LogicalPlan:\n{rel_string}")
         return rel, rel_string
 

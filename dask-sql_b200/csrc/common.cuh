@@ -295,15 +295,20 @@ struct b2_sld {  // from the shared-memory tile staged by the TMA producer warp 
 // Evaluate all predicate terms for the batch.  Returns the surviving row bits and whether the
 // batch is fully in bounds.
 template <int R, class LD>
-__device__ __forceinline__ uint32_t b2_eval_terms(const b2_scan_t& s, const LD& ld, bool& full) {
+__device__ __forceinline__ uint32_t b2_eval_terms(const b2_scan_t& s, const LD& ld, bool& full, int& last_col,
+                                                  int64_t (&raw)[R]) {
+  // On return `raw` still holds the values of column `last_col` (the last term's column, -1 if
+  // none) for the surviving rows: consumers that need the same column again (SUM(x) ... WHERE x > 0,
+  // a join key that is also filtered) reuse the registers instead of re-loading.
   const int64_t row0 = ld.row0;
   uint32_t bits = b2_bounds_bits<R>(row0, s.n, full);
+  last_col = -1;
   for (int t = 0; t < s.nterms; ++t) {
     const b2_term_t& tm = s.terms[t];
     const b2_col_t& c = s.cols[tm.col];
     const int op = tm.op;
-    int64_t raw[R];
     ld.template load<R>(tm.col, bits, full, raw);
+    last_col = tm.col;
     uint32_t ok;
     if (op == B2_IS_NULL || op == B2_IS_NOT_NULL) {
       const uint32_t nul = b2_null_bits<R>(c, row0, bits, raw);
@@ -324,6 +329,12 @@ __device__ __forceinline__ uint32_t b2_eval_terms(const b2_scan_t& s, const LD& 
     bits &= ok;
   }
   return bits;
+}
+template <int R, class LD>
+__device__ __forceinline__ uint32_t b2_eval_terms(const b2_scan_t& s, const LD& ld, bool& full) {
+  int last_col;
+  int64_t raw[R];
+  return b2_eval_terms<R>(s, ld, full, last_col, raw);
 }
 template <int R>
 __device__ __forceinline__ uint32_t b2_eval_terms(const b2_scan_t& s, int64_t row0, bool& full) {
@@ -396,10 +407,12 @@ struct b2_aggs_arg {  // aggs passed by value in kernel params
 
 // For the batch at row0 with resolved slots (slot < 0 = row does not contribute): per aggregate,
 // load its input column for the contributing rows, drop NULLs, apply the atomics.
+// `pre` (optional): values of aggregate 0's input column already loaded by the caller for the rows
+// in `pre_bits` (a superset of the contributing rows), so that this load overlapped the slot lookup.
 template <int R, class LD>
 __device__ __forceinline__ void b2_apply_aggs(const b2_scan_t& s, const LD& ld, const b2_agg_t* __restrict__ aggs,
                                               int naggs, const b2_aggstate_t& st,
-                                              const int64_t (&slot)[R]) {
+                                              const int64_t (&slot)[R], const int64_t* pre = nullptr) {
   const int64_t row0 = ld.row0;
   uint32_t live = 0;
 #pragma unroll
@@ -431,7 +444,12 @@ __device__ __forceinline__ void b2_apply_aggs(const b2_scan_t& s, const LD& ld, 
     if (ag.col < 0) continue;  // COUNT(*) is st.rows
     const b2_col_t& c = s.cols[ag.col];
     int64_t raw[R];
-    ld.template load<R>(ag.col, live, false, raw);
+    if (a == 0 && pre) {
+#pragma unroll
+      for (int j = 0; j < R; ++j) raw[j] = pre[j];
+    } else {
+      ld.template load<R>(ag.col, live, false, raw);
+    }
     uint32_t ok = live;
     if (c.valid || c.dtype == B2_F64) ok &= ~b2_null_bits<R>(c, row0, live, raw);
     void* acc = st.acc[a];

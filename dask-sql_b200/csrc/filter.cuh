@@ -58,7 +58,9 @@ template <int R, class LD>
 __device__ __forceinline__ void b2_scan_agg_body(const b2_scan_t& s, const LD& ld, const b2_aggs_arg& aggs,
                                                  int64_t (*sh_acc)[B2_BLOCK], int32_t (*sh_cnt)[B2_BLOCK], int tid) {
   bool full;
-  const uint32_t bits = b2_eval_terms<R>(s, ld, full);
+  int cached_col;
+  int64_t cached[R];
+  const uint32_t bits = b2_eval_terms<R>(s, ld, full, cached_col, cached);
   for (int a = 0; a < aggs.n; ++a) {
     const b2_agg_t ag = aggs.a[a];
     if (ag.col < 0) {  // COUNT(*)
@@ -67,7 +69,12 @@ __device__ __forceinline__ void b2_scan_agg_body(const b2_scan_t& s, const LD& l
     }
     const b2_col_t& c = s.cols[ag.col];
     int64_t raw[R];
-    ld.template load<R>(ag.col, bits, full, raw);
+    if (ag.col == cached_col) {  // the predicate already loaded this column: reuse the registers
+#pragma unroll
+      for (int j = 0; j < R; ++j) raw[j] = cached[j];
+    } else {
+      ld.template load<R>(ag.col, bits, full, raw);
+    }
     uint32_t ok = bits;
     if (c.valid || c.dtype == B2_F64) ok &= ~b2_null_bits<R>(c, ld.row0, bits, raw);
     sh_cnt[a][tid] += __popc(ok);

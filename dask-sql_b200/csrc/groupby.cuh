@@ -254,24 +254,44 @@ __device__ __forceinline__ int32_t b2_star_lookup(const b2_starlookup_t& lk, int
 template <class LD>
 __device__ __forceinline__ void b2_star_body(const b2_scan_t& s, const LD& ld, int fk_col, const b2_starlookup_t& lk,
                                              const b2_aggs_arg& aggs, const b2_aggstate_t& st) {
+  // Two memory round trips per batch instead of four:
+  //   1. the join-key column is requested together with the predicate columns (its sectors are
+  //      touched anyway unless the predicate is very selective);
+  //   2. the first aggregate's input is requested for the rows that passed the predicate WHILE the
+  //      pk -> slot lookups are in flight;
+  //   3. atomics are fire-and-forget.
   const b2_col_t& kc = s.cols[fk_col];
+  bool full0;
+  const uint32_t inb = b2_bounds_bits<B2_GB_R>(ld.row0, s.n, full0);
+  int64_t key[B2_GB_R];
+  ld.template load<B2_GB_R>(fk_col, inb, full0, key);
   bool full;
   const uint32_t bits = b2_eval_terms<B2_GB_R>(s, ld, full);
-  int64_t key[B2_GB_R];
-  ld.template load<B2_GB_R>(fk_col, bits, full, key);
   uint32_t live = bits;
   if (kc.valid) live &= b2_valid_bits<B2_GB_R>(kc.valid, ld.row0, bits);
   // all lookups of the batch are issued before the first one is consumed
   int32_t found[B2_GB_R];
+  if (lk.dense) {
+    const uint64_t range = (uint64_t)lk.range;
 #pragma unroll
-  for (int j = 0; j < B2_GB_R; ++j) {
-    found[j] = -1;
-    if (((live >> j) & 1) && !(lk.dense == 0 && key[j] == B2_EMPTY_KEY)) found[j] = b2_star_lookup(lk, key[j]);
+    for (int j = 0; j < B2_GB_R; ++j) {
+      const uint64_t d = (uint64_t)key[j] - (uint64_t)lk.kmin;
+      found[j] = (((live >> j) & 1) && d < range) ? b2_ld_keep_i32(lk.lookup + d) : -1;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < B2_GB_R; ++j) {
+      found[j] = -1;
+      if (((live >> j) & 1) && key[j] != B2_EMPTY_KEY) found[j] = b2_star_lookup(lk, key[j]);
+    }
   }
+  const bool prefetch = aggs.n > 0 && aggs.a[0].col >= 0;
+  int64_t pre[B2_GB_R];
+  if (prefetch) ld.template load<B2_GB_R>(aggs.a[0].col, live, false, pre);
   int64_t slot[B2_GB_R];
 #pragma unroll
   for (int j = 0; j < B2_GB_R; ++j) slot[j] = found[j];
-  b2_apply_aggs<B2_GB_R>(s, ld, aggs.a, aggs.n, st, slot);
+  b2_apply_aggs<B2_GB_R>(s, ld, aggs.a, aggs.n, st, slot, prefetch ? pre : nullptr);
 }
 
 template <bool PIPE>

@@ -1,5 +1,6 @@
 // join.cuh — hash join: chained build (duplicates allowed), direct-address build (unique dense
-// keys), two-pass probe that emits (probe row, build row) pairs in probe-row order.
+// keys), two-pass probe that emits matches in probe-row order and, in the same pass, gathers the
+// requested probe / build columns straight into the output (no index round trip).
 #pragma once
 #include "common.cuh"
 
@@ -12,6 +13,15 @@ struct b2_keycols_arg {
 };
 struct b2_probekeys_arg {
   int32_t cols[B2_MAX_KEYS];
+};
+struct b2_joingather_arg {
+  int32_t nprobe, nbuild;
+  int32_t probe_cols[B2_MAX_GATHER];
+  void* probe_out[B2_MAX_GATHER];
+  uint32_t* probe_valid[B2_MAX_GATHER];
+  b2_col_t build_cols[B2_MAX_GATHER];
+  void* build_out[B2_MAX_GATHER];
+  uint32_t* build_valid[B2_MAX_GATHER];
 };
 
 // normalised key image: -0.0 -> +0.0 so float keys compare like pandas; ints unchanged
@@ -58,18 +68,10 @@ b2_join_build_dense_kernel(const __grid_constant__ b2_col_t key, int64_t n, int6
   }
 }
 
-// Walk the matches of one probe row.  F(build_row) is called for every match.
+// Walk the chain of one probe row.  F(build_row) is called for every match.
 template <class F>
 __device__ __forceinline__ int b2_for_matches(const b2_jointable_t& jt, const int64_t* pkey, F f) {
   int cnt = 0;
-  if (jt.dense) {
-    const uint64_t d = (uint64_t)pkey[0] - (uint64_t)jt.kmin;
-    if (d < (uint64_t)jt.range) {
-      const int32_t r = __ldg(jt.lookup + d);
-      if (r >= 0) { f(r); cnt = 1; }
-    }
-    return cnt;
-  }
   const uint64_t h = b2_hash_keys(pkey, jt.nkeys) & (uint64_t)(jt.cap - 1);
   for (int32_t r = __ldg(jt.head + h); r >= 0; r = __ldg(jt.next + r)) {
     bool same = true;
@@ -108,6 +110,36 @@ __device__ __forceinline__ int b2_emit_count(int mode, int matches) {
   }
 }
 
+// ---- direct-address table: at most one match per probe row, everything is batched --------------
+// returns the bits of rows that emit; brow[j] = matching build row or -1
+template <int R>
+__device__ __forceinline__ uint32_t b2_dense_probe(const b2_scan_t& s, int key_col, const b2_jointable_t& jt,
+                                                   int mode, int64_t row0, int32_t (&brow)[R]) {
+  bool full;
+  const uint32_t bits = b2_eval_terms<R>(s, row0, full);
+  const b2_col_t& kc = s.cols[key_col];
+  int64_t key[R];
+  b2_load_batch<R>(kc, row0, bits, full, key);
+  uint32_t live = bits;
+  if (kc.valid) live &= b2_valid_bits<R>(kc.valid, row0, bits);
+  uint32_t matched = 0;
+  const uint64_t range = (uint64_t)jt.range;
+#pragma unroll
+  for (int j = 0; j < R; ++j) {
+    const uint64_t d = (uint64_t)key[j] - (uint64_t)jt.kmin;
+    brow[j] = (((live >> j) & 1) && d < range) ? __ldg(jt.lookup + d) : -1;
+  }
+#pragma unroll
+  for (int j = 0; j < R; ++j) matched |= (uint32_t)(brow[j] >= 0) << j;
+  switch (mode) {
+    case B2_JOIN_INNER:
+    case B2_JOIN_SEMI: return matched;
+    case B2_JOIN_LEFT: return bits;
+    default: return bits & ~matched;  // ANTI
+  }
+}
+
+template <bool DENSE>
 __global__ void __launch_bounds__(B2_BLOCK)
 b2_join_count_kernel(const __grid_constant__ b2_scan_t s, const __grid_constant__ b2_probekeys_arg pk,
                      const __grid_constant__ b2_jointable_t jt, int mode, int64_t ntiles,
@@ -116,16 +148,21 @@ b2_join_count_kernel(const __grid_constant__ b2_scan_t s, const __grid_constant_
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int64_t row0 = tile * B2_TILE + (int64_t)warp * (32 * B2_JOIN_R) + lane;
-    const uint32_t bits = b2_eval_terms<B2_JOIN_R>(s, row0);
     int64_t c = 0;
-#pragma unroll 4
-    for (int j = 0; j < B2_JOIN_R; ++j) {
-      if (!((bits >> j) & 1)) continue;
-      int64_t key[B2_MAX_KEYS];
-      int m = 0;
-      if (b2_probe_key(s, pk, jt.nkeys, row0 + (int64_t)j * 32, key))
-        m = b2_for_matches(jt, key, [](int32_t) {});
-      c += b2_emit_count(mode, m);
+    if (DENSE) {
+      int32_t brow[B2_JOIN_R];
+      c = __popc(b2_dense_probe<B2_JOIN_R>(s, pk.cols[0], jt, mode, row0, brow));
+    } else {
+      const uint32_t bits = b2_eval_terms<B2_JOIN_R>(s, row0);
+#pragma unroll 1
+      for (int j = 0; j < B2_JOIN_R; ++j) {
+        if (!((bits >> j) & 1)) continue;
+        int64_t key[B2_MAX_KEYS];
+        int m = 0;
+        if (b2_probe_key(s, pk, jt.nkeys, row0 + (int64_t)j * 32, key))
+          m = b2_for_matches(jt, key, [](int32_t) {});
+        c += b2_emit_count(mode, m);
+      }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(FULL_MASK, c, o);
@@ -140,74 +177,197 @@ b2_join_count_kernel(const __grid_constant__ b2_scan_t s, const __grid_constant_
   }
 }
 
-__global__ void __launch_bounds__(B2_BLOCK)
+// one output row: indices and gathered columns
+__device__ __forceinline__ void b2_join_emit(const b2_scan_t& s, const b2_joingather_arg& g, int64_t pos,
+                                             int64_t prow, int32_t brow, int32_t* __restrict__ out_probe,
+                                             int32_t* __restrict__ out_build) {
+  if (out_probe) out_probe[pos] = (int32_t)prow;
+  if (out_build) out_build[pos] = brow;
+  for (int k = 0; k < g.nprobe; ++k) {
+    const b2_col_t& c = s.cols[g.probe_cols[k]];
+    if (c.dtype == B2_U8) reinterpret_cast<uint8_t*>(g.probe_out[k])[pos] = reinterpret_cast<const uint8_t*>(c.data)[prow];
+    else reinterpret_cast<int64_t*>(g.probe_out[k])[pos] = b2_ld_stream(reinterpret_cast<const int64_t*>(c.data) + prow);
+    if (g.probe_valid[k] && (!c.valid || b2_bit(c.valid, prow)))
+      atomicOr(g.probe_valid[k] + (pos >> 5), 1u << (pos & 31));
+  }
+  for (int k = 0; k < g.nbuild; ++k) {
+    const b2_col_t& c = g.build_cols[k];
+    const bool has = brow >= 0;
+    if (c.dtype == B2_U8) {
+      reinterpret_cast<uint8_t*>(g.build_out[k])[pos] = has ? reinterpret_cast<const uint8_t*>(c.data)[brow] : 0;
+    } else {
+      int64_t v = has ? __ldg(reinterpret_cast<const long long*>(c.data) + brow) : 0;
+      if (!has && c.dtype == B2_F64) v = 0x7ff8000000000000LL;  // NaN fill, like pandas take(-1)
+      reinterpret_cast<int64_t*>(g.build_out[k])[pos] = v;
+    }
+    if (g.build_valid[k] && has && (!c.valid || b2_bit(c.valid, brow)))
+      atomicOr(g.build_valid[k] + (pos >> 5), 1u << (pos & 31));
+  }
+}
+
+template <bool DENSE>
+__global__ void __launch_bounds__(B2_BLOCK, 3)
 b2_join_write_kernel(const __grid_constant__ b2_scan_t s, const __grid_constant__ b2_probekeys_arg pk,
                      const __grid_constant__ b2_jointable_t jt, int mode, int64_t ntiles,
                      const int64_t* __restrict__ tile_off, int32_t* __restrict__ out_probe,
-                     int32_t* __restrict__ out_build, uint8_t* __restrict__ build_matched) {
+                     int32_t* __restrict__ out_build, uint8_t* __restrict__ build_matched,
+                     const __grid_constant__ b2_joingather_arg g) {
   __shared__ int64_t sh[B2_WARPS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t lt_mask = (1u << lane) - 1;
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int64_t row0 = tile * B2_TILE + (int64_t)warp * (32 * B2_JOIN_R) + lane;
-    const uint32_t bits = b2_eval_terms<B2_JOIN_R>(s, row0);
-    // pass 1 (registers): emit counts per row, remember the first match (the common unique case)
-    int cnt[B2_JOIN_R];
-    int32_t first[B2_JOIN_R];
-    int64_t wtotal = 0;
+    if (DENSE) {
+      // ---- at most one output per probe row: ballot ranks, batched gathers
+      int32_t brow[B2_JOIN_R];
+      const uint32_t emit = b2_dense_probe<B2_JOIN_R>(s, pk.cols[0], jt, mode, row0, brow);
+      uint32_t ballots[B2_JOIN_R];
+      int wtotal = 0;
 #pragma unroll
-    for (int j = 0; j < B2_JOIN_R; ++j) {
-      cnt[j] = 0;
-      first[j] = -1;
-      if ((bits >> j) & 1) {
-        int64_t key[B2_MAX_KEYS];
-        int m = 0;
+      for (int j = 0; j < B2_JOIN_R; ++j) {
+        ballots[j] = __ballot_sync(FULL_MASK, (emit >> j) & 1);
+        wtotal += __popc(ballots[j]);
+      }
+      if (lane == 0) sh[warp] = wtotal;
+      __syncthreads();
+      int64_t off = tile_off[tile];
+      for (int w = 0; w < warp; ++w) off += sh[w];
+      __syncthreads();
+      // output position = off + rel[j]; rel is 32-bit (a tile emits <= 4096 rows) to save registers
+      int32_t rel[B2_JOIN_R];
+      {
+        int run = 0;
+#pragma unroll
+        for (int j = 0; j < B2_JOIN_R; ++j) {
+          rel[j] = ((emit >> j) & 1) ? run + __popc(ballots[j] & lt_mask) : -1;
+          run += __popc(ballots[j]);
+        }
+      }
+      const bool semi = mode == B2_JOIN_SEMI || mode == B2_JOIN_ANTI;
+#pragma unroll
+      for (int j = 0; j < B2_JOIN_R; ++j) {
+        if (rel[j] < 0) continue;
+        if (out_probe) out_probe[off + rel[j]] = (int32_t)(row0 + (int64_t)j * 32);
+        if (out_build) out_build[off + rel[j]] = semi ? -1 : brow[j];
+        if (build_matched && brow[j] >= 0) build_matched[brow[j]] = 1;
+      }
+      for (int k = 0; k < g.nprobe; ++k) {
+        const b2_col_t& c = s.cols[g.probe_cols[k]];
+        const uint32_t v = (g.probe_valid[k] && c.valid) ? b2_valid_bits<B2_JOIN_R>(c.valid, row0, emit) : emit;
+#pragma unroll
+        for (int h = 0; h < B2_JOIN_R; h += 8) {   // two half-batches: 8 gathers in flight, 16 registers
+          int64_t raw[8];
+          if (c.dtype == B2_U8) {
+            const uint8_t* p = reinterpret_cast<const uint8_t*>(c.data) + row0;
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) raw[jj] = rel[h + jj] >= 0 ? (int64_t)p[(h + jj) * 32] : 0;
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj)
+              if (rel[h + jj] >= 0) reinterpret_cast<uint8_t*>(g.probe_out[k])[off + rel[h + jj]] = (uint8_t)raw[jj];
+          } else {
+            const int64_t* p = reinterpret_cast<const int64_t*>(c.data) + row0;
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) raw[jj] = rel[h + jj] >= 0 ? b2_ld_stream(p + (h + jj) * 32) : 0;
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj)
+              if (rel[h + jj] >= 0) reinterpret_cast<int64_t*>(g.probe_out[k])[off + rel[h + jj]] = raw[jj];
+          }
+        }
+        if (g.probe_valid[k]) {
+#pragma unroll
+          for (int j = 0; j < B2_JOIN_R; ++j)
+            if (rel[j] >= 0 && ((v >> j) & 1))
+              atomicOr(g.probe_valid[k] + ((off + rel[j]) >> 5), 1u << ((off + rel[j]) & 31));
+        }
+      }
+      for (int k = 0; k < g.nbuild; ++k) {
+        const b2_col_t& c = g.build_cols[k];
+#pragma unroll
+        for (int h = 0; h < B2_JOIN_R; h += 8) {
+          int64_t raw[8];
+          if (c.dtype == B2_U8) {
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj)
+              raw[jj] = (rel[h + jj] >= 0 && brow[h + jj] >= 0) ? reinterpret_cast<const uint8_t*>(c.data)[brow[h + jj]] : 0;
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj)
+              if (rel[h + jj] >= 0) reinterpret_cast<uint8_t*>(g.build_out[k])[off + rel[h + jj]] = (uint8_t)raw[jj];
+          } else {
+            const int64_t fill = c.dtype == B2_F64 ? 0x7ff8000000000000LL : 0;
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj)
+              raw[jj] = (rel[h + jj] >= 0 && brow[h + jj] >= 0)
+                            ? __ldg(reinterpret_cast<const long long*>(c.data) + brow[h + jj]) : fill;
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj)
+              if (rel[h + jj] >= 0) reinterpret_cast<int64_t*>(g.build_out[k])[off + rel[h + jj]] = raw[jj];
+          }
+        }
+        if (g.build_valid[k]) {
+#pragma unroll
+          for (int j = 0; j < B2_JOIN_R; ++j)
+            if (rel[j] >= 0 && brow[j] >= 0 && (!c.valid || b2_bit(c.valid, brow[j])))
+              atomicOr(g.build_valid[k] + ((off + rel[j]) >> 5), 1u << ((off + rel[j]) & 31));
+        }
+      }
+    } else {
+      // ---- chained table: any number of matches per probe row
+      const uint32_t bits = b2_eval_terms<B2_JOIN_R>(s, row0);
+      int cnt[B2_JOIN_R];
+      int32_t first[B2_JOIN_R];
+      int64_t wtotal = 0;
+#pragma unroll 1
+      for (int j = 0; j < B2_JOIN_R; ++j) {
+        int c = 0;
         int32_t f0 = -1;
-        if (b2_probe_key(s, pk, jt.nkeys, row0 + (int64_t)j * 32, key))
-          m = b2_for_matches(jt, key, [&](int32_t r) { if (f0 < 0) f0 = r; });
-        first[j] = f0;
-        cnt[j] = b2_emit_count(mode, m) | (m > 1 ? 0x40000000 : 0);  // flag: chain must be re-walked
+        if ((bits >> j) & 1) {
+          int64_t key[B2_MAX_KEYS];
+          int m = 0;
+          if (b2_probe_key(s, pk, jt.nkeys, row0 + (int64_t)j * 32, key))
+            m = b2_for_matches(jt, key, [&](int32_t r) { if (f0 < 0) f0 = r; });
+          c = b2_emit_count(mode, m) | (m > 1 ? 0x40000000 : 0);  // flag: chain must be re-walked
+        }
+#pragma unroll
+        for (int jj = 0; jj < B2_JOIN_R; ++jj)
+          if (jj == j) { cnt[jj] = c; first[jj] = f0; }
+        wtotal += c & 0x3fffffff;
       }
-      wtotal += cnt[j] & 0x3fffffff;
-    }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) wtotal += __shfl_xor_sync(FULL_MASK, wtotal, o);
-    if (lane == 0) sh[warp] = wtotal;
-    __syncthreads();
-    int64_t off = tile_off[tile];
-    for (int w = 0; w < warp; ++w) off += sh[w];
-    __syncthreads();
-    // pass 2: in-order output positions through a warp prefix sum per row group
+      for (int o = 16; o > 0; o >>= 1) wtotal += __shfl_xor_sync(FULL_MASK, wtotal, o);
+      if (lane == 0) sh[warp] = wtotal;
+      __syncthreads();
+      int64_t off = tile_off[tile];
+      for (int w = 0; w < warp; ++w) off += sh[w];
+      __syncthreads();
 #pragma unroll
-    for (int j = 0; j < B2_JOIN_R; ++j) {
-      const int c = cnt[j] & 0x3fffffff;
-      int incl = c;
+      for (int j = 0; j < B2_JOIN_R; ++j) {
+        const int c = cnt[j] & 0x3fffffff;
+        int incl = c;
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(FULL_MASK, incl, o);
-        if (lane >= o) incl += t;
-      }
-      const int total = __shfl_sync(FULL_MASK, incl, 31);
-      int64_t pos = off + incl - c;
-      off += total;
-      if (c == 0) continue;
-      const int32_t prow = (int32_t)(row0 + (int64_t)j * 32);
-      if (mode == B2_JOIN_SEMI || mode == B2_JOIN_ANTI) {
-        out_probe[pos] = prow;
-        if (out_build) out_build[pos] = -1;
-        if (build_matched && first[j] >= 0) build_matched[first[j]] = 1;
-      } else if (!(cnt[j] & 0x40000000)) {
-        out_probe[pos] = prow;
-        out_build[pos] = first[j];  // -1 for an unmatched LEFT row
-        if (build_matched && first[j] >= 0) build_matched[first[j]] = 1;
-      } else {
-        int64_t key[B2_MAX_KEYS];
-        b2_probe_key(s, pk, jt.nkeys, prow, key);
-        b2_for_matches(jt, key, [&](int32_t r) {
-          out_probe[pos] = prow;
-          out_build[pos] = r;
-          if (build_matched) build_matched[r] = 1;
-          ++pos;
-        });
+        for (int o = 1; o < 32; o <<= 1) {
+          const int t = __shfl_up_sync(FULL_MASK, incl, o);
+          if (lane >= o) incl += t;
+        }
+        const int total = __shfl_sync(FULL_MASK, incl, 31);
+        int64_t pos = off + incl - c;
+        off += total;
+        if (c == 0) continue;
+        const int64_t prow = row0 + (int64_t)j * 32;
+        if (mode == B2_JOIN_SEMI || mode == B2_JOIN_ANTI) {
+          b2_join_emit(s, g, pos, prow, -1, out_probe, out_build);
+          if (build_matched && first[j] >= 0) build_matched[first[j]] = 1;
+        } else if (!(cnt[j] & 0x40000000)) {
+          b2_join_emit(s, g, pos, prow, first[j], out_probe, out_build);  // first = -1 for an unmatched LEFT row
+          if (build_matched && first[j] >= 0) build_matched[first[j]] = 1;
+        } else {
+          int64_t key[B2_MAX_KEYS];
+          b2_probe_key(s, pk, jt.nkeys, prow, key);
+          b2_for_matches(jt, key, [&](int32_t r) {
+            b2_join_emit(s, g, pos, prow, r, out_probe, out_build);
+            if (build_matched) build_matched[r] = 1;
+            ++pos;
+          });
+        }
       }
     }
   }
@@ -274,8 +434,13 @@ int32_t b2_join_count(const b2_scan_t* scan, const int32_t* probe_keys, const b2
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t ntiles = b2_num_tiles(scan->n);
   if (ntiles > 0) {
-    int grid = b2_wave_grid(b2_join_count_kernel, B2_BLOCK, ntiles);
-    b2_join_count_kernel<<<grid, B2_BLOCK, 0, st>>>(*scan, pk, *jt, mode, ntiles, d_tile_off);
+    if (jt->dense) {
+      int grid = b2_wave_grid(b2_join_count_kernel<true>, B2_BLOCK, ntiles);
+      b2_join_count_kernel<true><<<grid, B2_BLOCK, 0, st>>>(*scan, pk, *jt, mode, ntiles, d_tile_off);
+    } else {
+      int grid = b2_wave_grid(b2_join_count_kernel<false>, B2_BLOCK, ntiles);
+      b2_join_count_kernel<false><<<grid, B2_BLOCK, 0, st>>>(*scan, pk, *jt, mode, ntiles, d_tile_off);
+    }
     B2_CHECK_LAUNCH("b2_join_count_kernel");
   }
   b2_exclusive_scan_kernel<<<1, B2_SCAN_THREADS, 0, st>>>(d_tile_off, ntiles);
@@ -283,21 +448,55 @@ int32_t b2_join_count(const b2_scan_t* scan, const int32_t* probe_keys, const b2
   return B2_OK;
 }
 
-int32_t b2_join_write(const b2_scan_t* scan, const int32_t* probe_keys, const b2_jointable_t* jt, int32_t mode,
-                      const int64_t* d_tile_off, int32_t* out_probe_idx, int32_t* out_build_idx,
-                      uint8_t* build_matched, void* stream) {
+int32_t b2_join_write_gather(const b2_scan_t* scan, const int32_t* probe_keys, const b2_jointable_t* jt,
+                             int32_t mode, const int64_t* d_tile_off, int32_t* out_probe_idx,
+                             int32_t* out_build_idx, uint8_t* build_matched, int32_t nprobe,
+                             const int32_t* probe_cols, void* const* probe_out, uint32_t* const* probe_valid,
+                             int32_t nbuild, const b2_col_t* build_cols, void* const* build_out,
+                             uint32_t* const* build_valid, void* stream) {
   b2_probekeys_arg pk;
   int32_t rc = b2_check_join(scan, probe_keys, jt, mode, &pk);
   if (rc) return rc;
-  B2_REQUIRE(d_tile_off && out_probe_idx, "null argument");
-  B2_REQUIRE(out_build_idx || mode == B2_JOIN_SEMI || mode == B2_JOIN_ANTI, "out_build_idx required");
+  B2_REQUIRE(d_tile_off, "null argument");
+  B2_REQUIRE(nprobe >= 0 && nprobe <= B2_MAX_GATHER && nbuild >= 0 && nbuild <= B2_MAX_GATHER, "too many gather columns");
+  b2_joingather_arg g;
+  memset(&g, 0, sizeof(g));
+  g.nprobe = nprobe;
+  g.nbuild = nbuild;
+  for (int k = 0; k < nprobe; ++k) {
+    B2_REQUIRE(probe_cols[k] >= 0 && probe_cols[k] < scan->ncols && probe_out[k], "bad probe gather");
+    g.probe_cols[k] = probe_cols[k];
+    g.probe_out[k] = probe_out[k];
+    g.probe_valid[k] = probe_valid ? probe_valid[k] : nullptr;
+  }
+  for (int k = 0; k < nbuild; ++k) {
+    B2_REQUIRE(build_out[k], "bad build gather");
+    g.build_cols[k] = build_cols[k];
+    g.build_out[k] = build_out[k];
+    g.build_valid[k] = build_valid ? build_valid[k] : nullptr;
+  }
   const int64_t ntiles = b2_num_tiles(scan->n);
   if (ntiles == 0) return B2_OK;
-  int grid = b2_wave_grid(b2_join_write_kernel, B2_BLOCK, ntiles);
-  b2_join_write_kernel<<<grid, B2_BLOCK, 0, (cudaStream_t)stream>>>(*scan, pk, *jt, mode, ntiles, d_tile_off,
-                                                                     out_probe_idx, out_build_idx, build_matched);
+  if (jt->dense) {
+    int grid = b2_wave_grid(b2_join_write_kernel<true>, B2_BLOCK, ntiles);
+    b2_join_write_kernel<true><<<grid, B2_BLOCK, 0, (cudaStream_t)stream>>>(
+        *scan, pk, *jt, mode, ntiles, d_tile_off, out_probe_idx, out_build_idx, build_matched, g);
+  } else {
+    int grid = b2_wave_grid(b2_join_write_kernel<false>, B2_BLOCK, ntiles);
+    b2_join_write_kernel<false><<<grid, B2_BLOCK, 0, (cudaStream_t)stream>>>(
+        *scan, pk, *jt, mode, ntiles, d_tile_off, out_probe_idx, out_build_idx, build_matched, g);
+  }
   B2_CHECK_LAUNCH("b2_join_write_kernel");
   return B2_OK;
+}
+
+int32_t b2_join_write(const b2_scan_t* scan, const int32_t* probe_keys, const b2_jointable_t* jt, int32_t mode,
+                      const int64_t* d_tile_off, int32_t* out_probe_idx, int32_t* out_build_idx,
+                      uint8_t* build_matched, void* stream) {
+  B2_REQUIRE(out_probe_idx, "null argument");
+  B2_REQUIRE(out_build_idx || mode == B2_JOIN_SEMI || mode == B2_JOIN_ANTI, "out_build_idx required");
+  return b2_join_write_gather(scan, probe_keys, jt, mode, d_tile_off, out_probe_idx, out_build_idx, build_matched,
+                              0, nullptr, nullptr, nullptr, 0, nullptr, nullptr, nullptr, stream);
 }
 
 }  // extern "C"

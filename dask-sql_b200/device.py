@@ -416,6 +416,43 @@ class JoinTable:
         self.struct.dense, self.struct.head, self.struct.next, self.struct.cap = 0, self.head.data_ptr(), self.next.data_ptr(), cap
 
 
+def join_probe_gather(scan, probe_keys, jt: JoinTable, mode, device, scan_cols, probe_gather, build_cols,
+                      build_nullable, build_matched=None):
+    """Probe and gather in one pass.  probe_gather: slots of scan columns to copy; build_cols: build-side
+    DeviceColumns to fetch by build row.  -> (probe outputs, build outputs, total)."""
+    n = scan.n
+    ntiles = L.num_tiles(n)
+    tile_off = torch.empty(ntiles + 1, dtype=torch.int64, device=device)
+    pk = (C.c_int32 * len(probe_keys))(*probe_keys)
+    L.join_count(C.byref(scan), pk, C.byref(jt.struct), mode, ptr(tile_off), stream_ptr())
+    total = int(tile_off[ntiles].item())
+    if total >= (1 << 31):
+        raise NotImplementedError("join output of one partition exceeds 2^31 rows; use more partitions")
+    pouts, pvalid, bouts, bvalid = [], [], [], []
+    for sl in probe_gather:
+        c = scan_cols[sl]
+        pouts.append(torch.empty(total, dtype=_TORCH_DTYPE[c.dtype], device=device))
+        pvalid.append(torch.zeros(bitmap_words(total), dtype=torch.int32, device=device) if c.valid is not None else None)
+    for c in build_cols:
+        bouts.append(torch.empty(total, dtype=_TORCH_DTYPE[c.dtype], device=device))
+        bvalid.append(torch.zeros(bitmap_words(total), dtype=torch.int32, device=device)
+                      if (c.valid is not None or build_nullable) else None)
+    if total > 0:
+        np_, nb = len(probe_gather), len(build_cols)
+        pc = (C.c_int32 * max(1, np_))(*probe_gather)
+        po = (C.c_void_p * max(1, np_))(*[t.data_ptr() for t in pouts])
+        pv = (C.c_void_p * max(1, np_))(*[(v.data_ptr() if v is not None else 0) for v in pvalid])
+        bc = (L.Col * max(1, nb))(*[c.as_struct() for c in build_cols])
+        bo = (C.c_void_p * max(1, nb))(*[t.data_ptr() for t in bouts])
+        bv = (C.c_void_p * max(1, nb))(*[(v.data_ptr() if v is not None else 0) for v in bvalid])
+        L.join_write_gather(C.byref(scan), pk, C.byref(jt.struct), mode, ptr(tile_off), None, None,
+                            ptr(build_matched), np_, pc, po, pv, nb, bc, bo, bv, stream_ptr())
+    pres = [DeviceColumn(o, v, scan_cols[sl].dtype, scan_cols[sl].logical)
+            for o, v, sl in zip(pouts, pvalid, probe_gather)]
+    bres = [DeviceColumn(o, v, c.dtype, c.logical) for o, v, c in zip(bouts, bvalid, build_cols)]
+    return pres, bres, total
+
+
 def join_probe(scan, probe_keys, jt: JoinTable, mode, device, build_matched=None):
     """-> (probe_idx int32, build_idx int32 or None, total)."""
     n = scan.n

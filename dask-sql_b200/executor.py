@@ -904,7 +904,14 @@ def try_star(src: AggSource, child: LazyFrame, gexprs, aggs, pred, sharded) -> O
     if d.n == 0:
         return None
     pk = d["__pk"]
-    pst = pk.ensure_stats()
+    def _stats(expr, col):
+        # a filtered subset lies within the table-level range, and table statistics are cached:
+        # no kernel and no host sync per query
+        if isinstance(expr, ColRef) and isinstance(dim.source, TableSource) and dist not in ("root", "sharded"):
+            return dim.source.table.column_stats(expr.name)
+        return col.ensure_stats()
+
+    pst = _stats(pk_e, pk)
     if pst.vmin is None:
         return None
     plan = AggPlan([(E.substitute(e, fact.exprs) if e is not None else None, o, f) for e, o, f in aggs],
@@ -916,7 +923,7 @@ def try_star(src: AggSource, child: LazyFrame, gexprs, aggs, pred, sharded) -> O
     gkey_cols = [d[g] for g in gcols]
     dense_groups = False
     if len(gcols) == 1 and gkey_cols[0].dtype in (I64,):
-        gst = gkey_cols[0].ensure_stats()
+        gst = _stats(E.substitute(gexprs[0], dim.exprs), gkey_cols[0])
         if gst.vmin is not None and gst.vmax - gst.vmin + 2 <= DENSE_MAX_SLOTS and \
                 (gst.vmax - gst.vmin) <= 8 * d.n + 1024:
             dense_groups = True
@@ -1064,19 +1071,31 @@ def run_join(js: JoinSource, needed: Set[str]) -> List[Part]:
             continue
         ctx = ScanCtx(part, ppred)
         kslots = [ctx.slot(e) for e in pk_exprs]
-        stats["launches"] += 3
-        pidx, bidx, total = D.join_probe(ctx.scan(), kslots, jt, mode, dev, build_matched)
-        res = Part({}, total)
-        # probe columns: gather the referenced source columns once, then evaluate expressions
         refs = sorted({r for n in probe_out for r in probe.exprs[n].refs()})
-        g = Part({r: D.gather(part[r], pidx, False) for r in refs}, total)
-        stats["launches"] += len(refs)
+        if len(refs) <= L.MAX_GATHER and len(build_out) <= L.MAX_GATHER:
+            # probe + gather of both sides' columns in one pass (b2_join_write_gather)
+            rslots = [ctx.slot(ColRef(r, part[r].dtype)) for r in refs]
+            stats["launches"] += 3
+            pres, bres, total = D.join_probe_gather(ctx.scan(), kslots, jt, mode, dev, ctx.cols, rslots,
+                                                    [bpart[n] for n in build_out], mode == L.JOIN_LEFT,
+                                                    build_matched)
+            g = Part(dict(zip(refs, pres)), total)
+            res = Part({}, total)
+            for n, col in zip(build_out, bres):
+                res[n] = col
+        else:
+            stats["launches"] += 3
+            pidx, bidx, total = D.join_probe(ctx.scan(), kslots, jt, mode, dev, build_matched)
+            res = Part({}, total)
+            g = Part({r: D.gather(part[r], pidx, False) for r in refs}, total)
+            stats["launches"] += len(refs)
+            for n in build_out:
+                stats["launches"] += 1
+                res[n] = D.gather(bpart[n], bidx, mode == L.JOIN_LEFT)
+        # probe-side output expressions are evaluated on the gathered source columns
         for n in probe_out:
             e = probe.exprs[n]
             res[n] = const_column(e.value, e.dtype, total, dev) if isinstance(e, Lit) else eval_expr(g, e)
-        for n in build_out:
-            stats["launches"] += 1
-            res[n] = D.gather(bpart[n], bidx, mode == L.JOIN_LEFT)
         outs.append(res)
     if how == "outer" and bpart.n > 0:
         # build rows nobody matched, with NULL probe columns

@@ -222,10 +222,14 @@ class LazyFrame:
             return e.dtype, e.logical
         return e.dtype, {I64: "int64", F64: "float64", U8: "bool"}[e.dtype]
 
+    def dtype_of(self, name):
+        """numpy / pandas dtype of one column (cheap: no Series is built)."""
+        return LazySeries(self.source, (), self.exprs[name]).dtype
+
     @property
     def dtypes(self):
         import pandas as pd
-        return pd.Series({n: LazySeries(self.source, (), e).dtype for n, e in self.exprs.items()})
+        return pd.Series({n: self.dtype_of(n) for n in self.exprs})
 
     @property
     def npartitions(self):

@@ -93,19 +93,29 @@ def sql_to_python_value(sql_type, literal_value):
     raise NotImplementedError(f"literal of SQL type {name}")
 
 
+_SIMILAR_CACHE = {}
+
+
 def similar_type(lhs, rhs) -> bool:
     """Same type family (int / float / bool): no cast needed (mappings.py:264-306)."""
+    key = (str(lhs), str(rhs))
+    hit = _SIMILAR_CACHE.get(key)
+    if hit is not None:
+        return hit
     pdt = pd.api.types
-    lhs, rhs = pd.api.types.pandas_dtype(lhs), pd.api.types.pandas_dtype(rhs)
+    l, r = pd.api.types.pandas_dtype(lhs), pd.api.types.pandas_dtype(rhs)
+    out = False
     for check in (pdt.is_bool_dtype, pdt.is_integer_dtype, pdt.is_float_dtype):
-        if check(lhs) and check(rhs):
-            return True
-    return False
+        if check(l) and check(r):
+            out = True
+            break
+    _SIMILAR_CACHE[key] = out
+    return out
 
 
 def cast_column_type(df: LazyFrame, column_name: str, expected_type) -> LazyFrame:
     """Cast df[column_name] only if its type family differs (mappings.py:309-329)."""
-    current = df.dtypes[column_name]
+    current = df.dtype_of(column_name)
     if expected_type is type(None) or similar_type(current, expected_type):
         return df
     casted = cast_column_to_type(df[column_name], expected_type)

@@ -14,6 +14,7 @@ class Pluggable:
     """Name -> plugin mapping per subclass (utils.py:61-91 in the reference)."""
 
     __plugins = defaultdict(dict)
+    version = 0
 
     @classmethod
     def add_plugin(cls, names, plugin, replace=True):
@@ -24,6 +25,7 @@ class Pluggable:
             return
         for n in names:
             registry[n] = plugin
+        Pluggable.version += 1   # invalidates plans cached by Context.sql
 
     @classmethod
     def get_plugin(cls, name):

@@ -287,6 +287,19 @@ int32_t b2_join_write(const b2_scan_t* scan, const int32_t* probe_keys, const b2
                       int32_t mode, const int64_t* d_tile_off, int32_t* out_probe_idx,
                       int32_t* out_build_idx, uint8_t* build_matched, void* stream);
 
+/* b2_join_write that also gathers output columns in the same pass (the take() on every column of
+ * both sides that ends pandas.merge, join.py:241-246): for each emitted pair, probe columns
+ * scan.cols[probe_cols[k]] are copied to probe_out[k] and build-side columns build_cols[k] (indexed
+ * by the build row, NULL for an unmatched LEFT row) to build_out[k].  *_valid[k]: validity words of
+ * the output (zero-initialised by the caller, bits are OR-ed in) or NULL.  out_probe_idx /
+ * out_build_idx may be NULL when the caller only wants the gathered columns. */
+int32_t b2_join_write_gather(const b2_scan_t* scan, const int32_t* probe_keys, const b2_jointable_t* jt,
+                             int32_t mode, const int64_t* d_tile_off, int32_t* out_probe_idx,
+                             int32_t* out_build_idx, uint8_t* build_matched, int32_t nprobe,
+                             const int32_t* probe_cols, void* const* probe_out, uint32_t* const* probe_valid,
+                             int32_t nbuild, const b2_col_t* build_cols, void* const* build_out,
+                             uint32_t* const* build_valid, void* stream);
+
 /* ---- fused filter -> join -> group-by (star pipeline) ----------------------------- */
 /* out_slot[i] = key[i]-kmin (NULL key -> null_slot) as int32: turns a dense group-key column of
  * the build side into group-table slot numbers. */

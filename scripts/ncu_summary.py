@@ -26,7 +26,8 @@ for r in rows[2:]:
     if nrows:
         print(f"  thread-instr/row {float(r[idx['smsp__inst_executed.sum']]) * 32 / nrows:.1f}   "
               f"GB/s(alg) n/a   dram B/row {(float(r[idx['dram__bytes_read.sum']])) * (1e9 if units[idx['dram__bytes_read.sum']]=='Gbyte' else 1e6) / nrows:.1f}")
-    src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + name.split('<')[0],
+    src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name",
+                          "regex:" + name.replace("void ", "").split('<')[0],
                           "--launch-count", "1"], capture_output=True, text=True).stdout
     srows = list(csv.reader(src.splitlines()))
     if len(srows) < 3:

@@ -28,7 +28,7 @@ def assert_same(got, exp, float_cols=(), rtol=1e-9, check_names=True):
     e.columns = g.columns
     assert len(g) == len(e), f"{len(g)} rows vs {len(e)}"
     for c, ce in zip(g.columns, exp.columns):
-        if str(ce) in float_cols:
+        if str(ce) in float_cols or str(c) in float_cols:
             np.testing.assert_allclose(g[c].to_numpy(), e[c].to_numpy(), rtol=rtol, equal_nan=True)
         else:
             np.testing.assert_array_equal(g[c].to_numpy(), e[c].to_numpy())
