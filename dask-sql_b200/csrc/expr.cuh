@@ -50,6 +50,8 @@ b2_expr_kernel(const __grid_constant__ b2_prog_t prog, const __grid_constant__ b
           int64_t v = sv[sp - 1]; sv[sp - 1] = v < 0 ? (int64_t)(0ULL - (uint64_t)v) : v;
         } else if (op == B2_OP_NEG_F) {
           sv[sp - 1] = __double_as_longlong(-__longlong_as_double(sv[sp - 1]));
+        } else if (op == B2_OP_SQRT_F) {
+          sv[sp - 1] = __double_as_longlong(sqrt(__longlong_as_double(sv[sp - 1])));
         } else if (op == B2_OP_ABS_F) {
           sv[sp - 1] = __double_as_longlong(fabs(__longlong_as_double(sv[sp - 1])));
         } else if (op == B2_OP_ORD2F) {
@@ -201,7 +203,7 @@ int32_t b2_expr_eval(const b2_prog_t* prog, const b2_col_t* cols, int32_t ncols,
       ++sp;
     } else if (op == B2_OP_CONST_I || op == B2_OP_CONST_F || op == B2_OP_CONST_NULL) ++sp;
     else if (op == B2_OP_I2F || op == B2_OP_F2I || op == B2_OP_NEG_I || op == B2_OP_ABS_I ||
-             op == B2_OP_NEG_F || op == B2_OP_ABS_F || op == B2_OP_NOT || op == B2_OP_ISNULL_I ||
+             op == B2_OP_NEG_F || op == B2_OP_ABS_F || op == B2_OP_SQRT_F || op == B2_OP_NOT || op == B2_OP_ISNULL_I ||
              op == B2_OP_ISNULL_F || op == B2_OP_ORD2F) { B2_REQUIRE(sp >= 1, "stack underflow"); }
     else if (op == B2_OP_CASE) { B2_REQUIRE(sp >= 3, "stack underflow"); sp -= 2; }
     else { B2_REQUIRE(sp >= 2, "stack underflow"); sp -= 1; }

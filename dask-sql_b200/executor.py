@@ -260,7 +260,10 @@ def materialize(src: Source, needed: Set[str]) -> List[Part]:
                 c = p[name]
                 if isinstance(c, HostColumn):
                     stats["h2d_bytes"] += c.nbytes()
-                    c = c.to_device(dev)
+                    hc, c = c, c.to_device(dev)
+                    if hc.stats is None:
+                        # statistics ride on the first upload and stay with the (immutable) host column
+                        hc.stats = c.ensure_stats()
                 cols[name] = c
             parts.append(Part(cols, n))
         return parts
@@ -390,6 +393,13 @@ def _nullable_fn(child: LazyFrame):
             has_bitmap = any(p[e.name].valid is not None for p in t.partitions)
             if e.dtype != F64:
                 return has_bitmap
+            # NaN is NULL for float inputs: whether a count must be kept next to the sum depends on
+            # the data.  One statistics pass per resident column (cached) saves an atomic per row
+            # on every later query; host-resident columns are not uploaded twice for this.
+            for p in t.partitions:
+                c = p[e.name]
+                if c.stats is None and isinstance(c, DeviceColumn):
+                    c.ensure_stats()
             sts = [p[e.name].stats for p in t.partitions]
             if all(s is not None for s in sts):
                 return has_bitmap or any(s.nulls > 0 for s in sts)
@@ -608,7 +618,8 @@ def grouped_aggregate(parts, pred, gexprs, gnames, plan: AggPlan, child, sharded
             D.groupby_dense(ctx.scan(), kslot, kmin, gs.table)
         if sharded:
             _allreduce_table(gs.table, plan)
-        return _finalize_dense(gs, kmin, rng, gnames[0], gexprs[0], glog[0], plan, dev)
+        key_nullable = E.may_be_null(gexprs[0], lambda n: any(n in p and p[n].valid is not None for p in parts))
+        return _finalize_dense(gs, kmin, rng, gnames[0], gexprs[0], glog[0], plan, dev, key_nullable)
 
     # ---- hash tables: size from the row count, grow on overflow
     stats["hash_groupby"] += 1
@@ -725,14 +736,28 @@ def _gather_state(gs: GroupState, idx, dev):
     return acc_cols, cnt_cols, rows_col
 
 
-def _finalize_dense(gs: GroupState, kmin, rng, gname, gexpr, glog, plan, dev) -> Part:
-    return finish(_extract_dense(gs, kmin, rng, gname, gexpr, glog, dev), plan)
+def _finalize_dense(gs: GroupState, kmin, rng, gname, gexpr, glog, plan, dev, key_nullable=True) -> Part:
+    return finish(_extract_dense(gs, kmin, rng, gname, gexpr, glog, dev, key_nullable), plan)
 
 
-def _extract_dense(gs: GroupState, kmin, rng, gname, gexpr, glog, dev) -> RawGroups:
+def _extract_dense(gs: GroupState, kmin, rng, gname, gexpr, glog, dev, key_nullable=True) -> RawGroups:
     nslots = rng + 1
     t = gs.table
     slot_keys = torch.arange(kmin, kmin + nslots, dtype=torch.int64, device=dev)
+    if not key_nullable and gexpr.dtype == I64:
+        # the key column has no NULLs, so the NULL slot stays empty: no validity work, no host sync
+        if t.rows is not None:
+            occ = DeviceColumn(t.rows, None, I64)
+            scan = D.make_scan([occ], [TermSpec(0, L.GT, 0)], nslots)
+        else:
+            occ = DeviceColumn(slot_keys, t.present, I64)
+            scan = D.make_scan([occ], [TermSpec(0, L.IS_NOT_NULL, 0)], nslots)
+        stats["launches"] += 4
+        idx, _, total = D.select(scan, dev, (), want_idx=True, cols=[occ])
+        kcol = D.gather(DeviceColumn(slot_keys, None, I64, glog), idx, False)
+        kcol = DeviceColumn(kcol.data, None, I64, glog)
+        acc_cols, cnt_cols, rows_col = _gather_state(gs, idx, dev)
+        return RawGroups({gname: kcol}, acc_cols, cnt_cols, rows_col, total)
     # occupied slots
     if t.rows is not None:
         occ = DeviceColumn(t.rows, None, I64)
@@ -1001,7 +1026,8 @@ def try_star(src: AggSource, child: LazyFrame, gexprs, aggs, pred, sharded) -> O
     if sharded:
         _allreduce_table(gs.table, plan)
     if dense_groups:
-        return _finalize_dense(gs, gmin, grng, src.group_cols[0], gexprs[0], glog[0], plan, dev)
+        return _finalize_dense(gs, gmin, grng, src.group_cols[0], gexprs[0], glog[0], plan, dev,
+                               key_nullable=gkey_cols[0].valid is not None)
     return _finalize_hashk(gs, tkeys, tnulls, nslots, src.group_cols, gexprs, glog, plan, dev)
 
 

@@ -127,6 +127,8 @@ def unop(op: str, a) -> Expr:
         return Call("neg", [cast(a, I64) if a.dtype == U8 else a], F64 if a.dtype == F64 else I64)
     if op == "abs":
         return Call("abs", [a], a.dtype)
+    if op == "sqrt":
+        return Call("sqrt", [cast(a, F64)], F64)
     if op == "not":
         return Call("not", [cast(a, U8)], U8)
     if op == "isnull":
@@ -288,6 +290,10 @@ class _Compiler:
         if op == "abs":
             self.visit(args[0])
             self.emit(L.OP_ABS_F if e.dtype == F64 else L.OP_ABS_I)
+            return
+        if op == "sqrt":
+            self.visit(args[0])
+            self.emit(L.OP_SQRT_F)
             return
         if op == "isnull":
             self.visit(args[0])

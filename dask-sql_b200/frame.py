@@ -144,6 +144,7 @@ class LazySeries:
     __hash__ = None
 
     def abs(self): return self._wrap(E.unop("abs", self.expr))
+    def sqrt(self): return self._wrap(E.unop("sqrt", self.expr))
     def isna(self): return self._wrap(E.unop("isnull", self.expr))
     isnull = isna
     def notna(self): return ~self.isna()

@@ -32,7 +32,13 @@ class DaskAggregatePlugin(BaseRelPlugin):
         "count": "count",
         "min": "min",
         "max": "max",
+        # (count, sum, sum of squares) recipes of aggregate.py:129-231
+        "stddev": "stddev_samp", "stddev_samp": "stddev_samp", "stddevsamp": "stddev_samp",
+        "stddev_pop": "stddev_pop", "stddevpop": "stddev_pop",
+        "variance": "var_samp", "var_samp": "var_samp", "var": "var_samp",
+        "var_pop": "var_pop", "variance_pop": "var_pop", "variancepop": "var_pop",
     }
+    _MOMENT_FUNCS = ("stddev_samp", "stddev_pop", "var_samp", "var_pop")
 
     def convert(self, rel, context) -> DataContainer:
         (dc,) = self.assert_inputs(rel, 1, context)
@@ -171,9 +177,27 @@ class DaskAggregatePlugin(BaseRelPlugin):
         if distinct_column:
             tmp_df = tmp_df.drop_duplicates(subset=(group_columns + [distinct_column]), **groupby_agg_options)
             logger.debug(f"Dropped duplicates from {distinct_column} before aggregation.")
-        spec = []
+        spec, moments = [], []
         for input_col, output_col, aggregation_f in aggregations:
             backend_in = cc.get_backend_by_frontend_name(input_col) if input_col is not None else None
-            spec.append((backend_in, output_col, aggregation_f))
+            if aggregation_f in self._MOMENT_FUNCS:
+                # STDDEV / VARIANCE from (count, sum, sum of squares), all accumulated in the same
+                # fused pass as the other aggregates (aggregate.py:129-231 uses the same three moments)
+                x = tmp_df[backend_in].astype("float64")
+                x_name, sq_name = new_temporary_column(tmp_df), new_temporary_column(tmp_df)
+                tmp_df = tmp_df.assign(**{x_name: x, sq_name: x * x})
+                s, s2, n = (f"{output_col}__{k}" for k in ("s", "s2", "n"))
+                spec += [(x_name, s, "sum"), (sq_name, s2, "sum"), (x_name, n, "count")]
+                moments.append((output_col, aggregation_f, s, s2, n))
+            else:
+                spec.append((backend_in, output_col, aggregation_f))
         logger.debug(f"Performing aggregation {spec}")
-        return LazyFrame(AggSource(tmp_df, group_columns, spec, groupby_agg_options))
+        frame = LazyFrame(AggSource(tmp_df, group_columns, spec, groupby_agg_options))
+        if moments:
+            new = {}
+            for output_col, f, s, s2, n in moments:
+                S, S2, N = frame[s], frame[s2], frame[n]
+                var = (S2 / N - (S / N) * (S / N)) if f.endswith("pop") else (S2 - S * S / N) / (N - 1)
+                new[output_col] = var.sqrt() if f.startswith("stddev") else var
+            frame = frame.assign(**new)[group_columns + [out for _, out, _ in aggregations]]
+        return frame

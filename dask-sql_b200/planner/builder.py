@@ -293,7 +293,7 @@ class Binder:
                     self.err("Aggregate function calls cannot be nested")
                 if name == "COUNT":
                     ty = "BIGINT"
-                elif name == "AVG":
+                elif name == "AVG" or name.startswith(("STDDEV", "VAR")):
                     ty = "DOUBLE"
                 elif name == "SUM":
                     ty = _norm_type(args[0].sql_type) if args[0].sql_type != "BOOLEAN" else "BIGINT"

@@ -91,7 +91,8 @@ for _n in ("Reference", "Call", "Literal", "Alias", "ScalarSubquery"):
 # ---------------------------------------------------------------------------------------------
 _ARROW = {"BIGINT": "Int64", "DOUBLE": "Float64", "BOOLEAN": "Boolean", "VARCHAR": "Utf8", "NULL": "Null",
           "INTEGER": "Int32", "FLOAT": "Float32"}
-AGG_FUNCS = {"SUM", "AVG", "COUNT", "MIN", "MAX", "MEAN"}
+AGG_FUNCS = {"SUM", "AVG", "COUNT", "MIN", "MAX", "MEAN", "STDDEV", "STDDEV_SAMP", "STDDEV_POP", "VAR_SAMP",
+             "VAR_POP", "VARIANCE"}
 
 
 class PyExpr:

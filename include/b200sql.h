@@ -155,6 +155,7 @@ typedef struct b2_prog {
 #define B2_OP_DIV_F    23
 #define B2_OP_NEG_F    24
 #define B2_OP_ABS_F    25
+#define B2_OP_SQRT_F   26   /* IEEE sqrt (STDDEV = sqrt(VAR), aggregate.py:200-231) */
 #define B2_OP_EQ_I     30   /* 30..35 = EQ NE LT LE GT GE on ints   */
 #define B2_OP_EQ_F     40   /* 40..45 = EQ NE LT LE GT GE on doubles (IEEE: NaN != x is true) */
 #define B2_OP_AND      50   /* Kleene */

@@ -139,6 +139,23 @@ def test_agg_count_sum_avg_min_max(c):
     eq_sqlite(c, "SELECT a, SUM(c) AS s FROM a GROUP BY a HAVING SUM(c) > 20", a=a)
 
 
+def test_stddev_variance(c):
+    # moment aggregates (aggregate.py:129-231): sample = ddof 1 like pandas std()/var(), pop = ddof 0
+    rng = np.random.default_rng(3)
+    df = pd.DataFrame({"k": rng.integers(0, 6, 500), "v": rng.normal(5, 2, 500), "i": rng.integers(-9, 9, 500)})
+    df.loc[rng.integers(0, 500, 40), "v"] = np.nan
+    c.create_table("t", df, npartitions=3)
+    got = c.sql("""SELECT k, STDDEV(v) AS sd, STDDEV_POP(v) AS sdp, VAR_SAMP(v) AS vs, VAR_POP(i) AS vp, AVG(v) AS m
+                   FROM t GROUP BY k""", return_futures=False)
+    g = df.groupby("k")
+    exp = pd.DataFrame({"k": sorted(df.k.unique()), "sd": g.v.std().values, "sdp": g.v.std(ddof=0).values,
+                        "vs": g.v.var().values, "vp": g.i.var(ddof=0).values, "m": g.v.mean().values})
+    assert_same(got, exp, ["sd", "sdp", "vs", "vp", "m"], rtol=1e-9)
+    got = c.sql("SELECT STDDEV_SAMP(i) AS sd, VARIANCE(v) AS vs FROM t WHERE k < 3", return_futures=False)
+    e = df[df.k < 3]
+    np.testing.assert_allclose([got.sd[0], got.vs[0]], [e.i.std(), e.v.var()], rtol=1e-9)
+
+
 def test_integration_filter_join_groupby(c):
     # shape of test_compatibility.py:1015-1036 (CTEs: filter + agg + inner + left join)
     a = make_rand_df(200, a=int, b=(int, 20), c=(float, 0))
