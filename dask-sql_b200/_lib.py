@@ -126,6 +126,8 @@ _SIGS = {
                              C.POINTER(Col), C.POINTER(_P), C.POINTER(_P), _P],
     "b2_dense_slots": [C.POINTER(Col), C.c_int64, C.c_int64, C.c_int32, _P, _P],
     "b2_star_build_dense": [C.POINTER(Col), _P, C.c_int64, _P, C.c_int64, C.c_int64, _P, _P, _P],
+    "b2_star_build_scan": [C.POINTER(Scan), C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int32, _P,
+                           _P, _P],
     "b2_star_build_hash": [C.POINTER(Col), _P, C.c_int64, _P, _P, _P, C.c_int64, _P, _P],
     "b2_star_agg": [C.POINTER(Scan), C.c_int32, C.POINTER(StarLookup), C.POINTER(Agg), C.c_int32,
                     C.POINTER(AggState), _P],
@@ -171,6 +173,7 @@ join_write = _wrap("b2_join_write")
 join_write_gather = _wrap("b2_join_write_gather")
 dense_slots = _wrap("b2_dense_slots")
 star_build_dense = _wrap("b2_star_build_dense")
+star_build_scan = _wrap("b2_star_build_scan")
 star_build_hash = _wrap("b2_star_build_hash")
 star_agg = _wrap("b2_star_agg")
 num_tiles = _lib.b2_num_tiles

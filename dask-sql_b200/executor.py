@@ -752,6 +752,34 @@ def _extract_dense(gs: GroupState, kmin, rng, gname, gexpr, glog, dev, key_nulla
         else:
             occ = DeviceColumn(slot_keys, t.present, I64)
             scan = D.make_scan([occ], [TermSpec(0, L.IS_NOT_NULL, 0)], nslots)
+        # compaction and gathers in one write pass: keys and every accumulator array ride along as
+        # gather columns of b2_select_write (<= 8), instead of one b2_gather launch each
+        cols = [occ, DeviceColumn(slot_keys, None, I64)]
+        where = {}
+        for i, (acc, cnt) in enumerate(zip(t.acc, t.cnt)):
+            if acc is not None:
+                where[("a", i)] = len(cols)
+                cols.append(DeviceColumn(acc, None, F64 if acc.dtype == torch.float64 else I64))
+            if cnt is not None:
+                where[("c", i)] = len(cols)
+                cols.append(DeviceColumn(cnt, None, I64))
+        if t.rows is not None:
+            where[("r", 0)] = 0
+        if len(cols) - 1 <= L.MAX_GATHER:
+            scan = D.make_scan(cols, [TermSpec(0, L.GT if t.rows is not None else L.IS_NOT_NULL, 0)], nslots)
+            gcols = list(range(1, len(cols))) if t.rows is None else list(range(0, len(cols)))
+            gcols = gcols[: L.MAX_GATHER] if len(gcols) <= L.MAX_GATHER else None
+        else:
+            gcols = None
+        if gcols is not None:
+            stats["launches"] += 3
+            _, outs, total = D.select(scan, dev, gcols, want_idx=False, cols=cols)
+            got = {g: DeviceColumn(o.data, None, o.dtype) for g, o in zip(gcols, outs)}
+            kcol = DeviceColumn(got[1].data, None, I64, glog)
+            acc_cols = [got.get(where.get(("a", i))) for i in range(len(t.acc))]
+            cnt_cols = [got.get(where.get(("c", i))) for i in range(len(t.cnt))]
+            rows_col = got.get(0) if t.rows is not None else None
+            return RawGroups({gname: kcol}, acc_cols, cnt_cols, rows_col, total)
         stats["launches"] += 4
         idx, _, total = D.select(scan, dev, (), want_idx=True, cols=[occ])
         kcol = D.gather(DeviceColumn(slot_keys, None, I64, glog), idx, False)
@@ -880,6 +908,92 @@ def _side_of(e: Expr, left_names: Set[str], right_names: Set[str]):
     return "both"
 
 
+def _star_dense_fast(src, fact, dim, fk_e, pk_e, gexprs, aggs, fact_pred, dim_pred, sharded, dev) -> Optional[Part]:
+    """Star pipeline when the dimension side is a registered table whose join key and (single)
+    group key are dense int64 columns: b2_star_build_scan per dim partition, b2_star_agg per fact
+    partition, one compaction at the end.  Returns None when the shape does not apply or a
+    duplicate build key shows up (the general path then takes over)."""
+    if len(gexprs) != 1 or not isinstance(dim.source, TableSource) or not isinstance(pk_e, ColRef):
+        return None
+    ge = E.substitute(gexprs[0], dim.exprs)
+    if not isinstance(ge, ColRef) or ge.dtype != I64 or pk_e.dtype != I64:
+        return None
+    rank, world = P.world()
+    dist = frame_distribution(dim)
+    if world > 1 and dist == "sharded":
+        return None
+    table = dim.source.table
+    owner = world == 1 or dist != "root" or rank == 0
+    meta = None
+    if owner:
+        pst, gst = table.column_stats(pk_e.name), table.column_stats(ge.name)
+        gnull = any(p[ge.name].valid is not None for p in table.partitions)
+        meta = (pst.vmin, pst.vmax, gst.vmin, gst.vmax, table.nrows, gnull)
+    if world > 1 and dist == "root":
+        meta = P.broadcast_object(meta, 0)
+    pmin, pmax, gmin, gmax, dn, gnull = meta
+    if pmin is None or gmin is None or dn == 0:
+        return None
+    prange, grng = pmax - pmin + 1, gmax - gmin + 1
+    if not (prange <= max(4 * dn, 1 << 16) and prange < (1 << 31)):
+        return None
+    if not (grng + 1 <= DENSE_MAX_SLOTS and grng <= 8 * dn + 1024):
+        return None
+    dpred, never = simplify_pred(dim.pred + [E.substitute(p, dim.exprs) for p in dim_pred])
+    fpred, fnever = simplify_pred(fact.pred + [E.substitute(p, fact.exprs) for p in fact_pred])
+    if never or fnever:
+        return None
+    nslots = grng + 1
+    lookup = torch.full((prange,), -1, dtype=torch.int32, device=dev)
+    flags = D.new_flags(dev)
+    if owner:
+        needed: Set[str] = {pk_e.name, ge.name}
+        for p in dpred:
+            p.refs(needed)
+        for part in materialize(dim.source, needed):
+            if part.n == 0:
+                continue
+            ctx = ScanCtx(part, dpred)
+            pk_slot, g_slot = ctx.slot(pk_e), ctx.slot(ge)     # slots first: scan() snapshots the columns
+            stats["launches"] += 1
+            L.star_build_scan(C.byref(ctx.scan()), pk_slot, g_slot, pmin, prange, gmin, nslots - 1,
+                              D.ptr(lookup), D.ptr(flags), D.stream_ptr())
+    if world > 1 and dist == "root":
+        # the build side crosses NVLink as the finished 4-byte-per-key lookup, not as its columns
+        P.broadcast_(lookup, 0)
+        P.broadcast_(flags, 0)
+    plan = AggPlan([(E.substitute(e, fact.exprs) if e is not None else None, o, f) for e, o, f in aggs],
+                   _nullable_fn(fact))
+    gs = GroupState(dev, nslots, plan, need_present=True, force_rows=sharded)
+    lk = L.StarLookup()
+    lk.dense, lk.lookup, lk.kmin, lk.range = 1, lookup.data_ptr(), pmin, prange
+    needed = set(fk_e.refs())
+    for ka in plan.kaggs:
+        ka.expr.refs(needed)
+    for p in fpred:
+        p.refs(needed)
+    for part in materialize(fact.source, needed):
+        if part.n == 0:
+            continue
+        ctx = ScanCtx(part, fpred)
+        fk_slot = ctx.slot(fk_e)
+        gs.bind(ctx)
+        stats["launches"] += 1
+        ev = _kernel_event_begin("b2_star_agg_kernel", part.n)
+        L.star_agg(C.byref(ctx.scan()), fk_slot, C.byref(lk), gs.table.aggs, len(gs.table.specs),
+                   C.byref(gs.table.state), D.stream_ptr())
+        _kernel_event_end(ev)
+    if sharded:
+        _allreduce_table(gs.table, plan)
+    glog = dim.col_type(gexprs[0].name)[1] if isinstance(gexprs[0], ColRef) else "int64"
+    out = _finalize_dense(gs, gmin, grng, src.group_cols[0], gexprs[0], glog, plan, dev, key_nullable=gnull)
+    # the duplicate-key check rides on the sync the compaction needed anyway
+    if int(flags[0].item()):
+        return None
+    stats["star_fused"] += 1
+    return out
+
+
 def try_star(src: AggSource, child: LazyFrame, gexprs, aggs, pred, sharded) -> Optional[Part]:
     js: JoinSource = child.source
     if js.how != "inner" or len(js.left_on) != 1:
@@ -912,6 +1026,12 @@ def try_star(src: AggSource, child: LazyFrame, gexprs, aggs, pred, sharded) -> O
     if fk_e.dtype != I64 or pk_e.dtype != I64:
         return None
     dev = _dev()
+
+    # ---- fast path: dense join key and dense group key straight from a registered table: the
+    # whole build side is one kernel per dim partition (filter -> slot -> lookup), no host sync
+    fast = _star_dense_fast(src, fact, dim, fk_e, pk_e, gexprs, aggs, fact_pred, dim_pred, sharded, dev)
+    if fast is not None:
+        return fast
 
     # ---- build side: filtered dim rows, their group slots, and the pk -> slot lookup
     dim_f = LazyFrame(dim.source, dim.exprs, dim.pred + [E.substitute(p, dim.exprs) for p in dim_pred])

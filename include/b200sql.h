@@ -313,6 +313,13 @@ int32_t b2_dense_slots(const b2_col_t* key, int64_t n, int64_t kmin, int32_t nul
 int32_t b2_star_build_dense(const b2_col_t* pk, const int32_t* sel, int64_t n_sel,
                             const int32_t* slot_of_row, int64_t kmin, int64_t range,
                             int32_t* lookup, int32_t* d_flags, void* stream);
+/* The same lookup straight from the UNFILTERED build partition when join key and group key are both
+ * dense int64: rows of `scan` passing its terms write lookup[pk-pk_min] = grp-grp_min (NULL grp ->
+ * null_slot, NULL pk skipped).  Fuses table_scan.py:80-119 (dim filter) into the build; nothing is
+ * materialised.  Call once per build partition; d_flags[0] = 1 on duplicate pk. */
+int32_t b2_star_build_scan(const b2_scan_t* scan, int32_t pk_col, int32_t grp_col, int64_t pk_min,
+                           int64_t pk_range, int64_t grp_min, int32_t null_slot, int32_t* lookup,
+                           int32_t* d_flags, void* stream);
 /* Hash variant: table_keys = int64[cap] pre-filled with B2_EMPTY_KEY, table_slots = int32[cap].
  * d_flags[0] = 1 on duplicate pk, d_flags[1] = 1 on overflow. */
 int32_t b2_star_build_hash(const b2_col_t* pk, const int32_t* sel, int64_t n_sel,
