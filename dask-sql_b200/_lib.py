@@ -124,6 +124,8 @@ _SIGS = {
     "b2_join_write_gather": [C.POINTER(Scan), C.POINTER(C.c_int32), C.POINTER(JoinTable), C.c_int32, _P, _P, _P,
                              _P, C.c_int32, C.POINTER(C.c_int32), C.POINTER(_P), C.POINTER(_P), C.c_int32,
                              C.POINTER(Col), C.POINTER(_P), C.POINTER(_P), _P],
+    "b2_iota": [_P, C.c_int64, _P],
+    "b2_sort_by": [C.POINTER(Col), C.c_int64, C.c_int32, C.c_int32, _P, _P, _P],
     "b2_dense_slots": [C.POINTER(Col), C.c_int64, C.c_int64, C.c_int32, _P, _P],
     "b2_star_build_dense": [C.POINTER(Col), _P, C.c_int64, _P, C.c_int64, C.c_int64, _P, _P, _P],
     "b2_star_build_scan": [C.POINTER(Scan), C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int32, _P,
@@ -134,6 +136,7 @@ _SIGS = {
 }
 
 EXPORTS = sorted(list(_SIGS) + ["b2_last_error", "b2_num_tiles", "b2_stats_ws_bytes", "b2_scan_agg_ws_bytes",
+                                "b2_sort_ws_bytes",
                                 "b2_f64_to_ordered", "b2_ordered_to_f64"])
 
 
@@ -171,6 +174,11 @@ join_build_dense = _wrap("b2_join_build_dense")
 join_count = _wrap("b2_join_count")
 join_write = _wrap("b2_join_write")
 join_write_gather = _wrap("b2_join_write_gather")
+iota = _wrap("b2_iota")
+sort_by = _wrap("b2_sort_by")
+_lib.b2_sort_ws_bytes.restype = C.c_int64
+_lib.b2_sort_ws_bytes.argtypes = [C.c_int64]
+sort_ws_bytes = _lib.b2_sort_ws_bytes
 dense_slots = _wrap("b2_dense_slots")
 star_build_dense = _wrap("b2_star_build_dense")
 star_build_scan = _wrap("b2_star_build_scan")

@@ -54,6 +54,8 @@ class Context:
         RelConverter.add_plugin_class(logical.DaskFilterPlugin, replace=False)
         RelConverter.add_plugin_class(logical.DaskJoinPlugin, replace=False)
         RelConverter.add_plugin_class(logical.DaskProjectPlugin, replace=False)
+        RelConverter.add_plugin_class(logical.DaskSortPlugin, replace=False)
+        RelConverter.add_plugin_class(logical.DaskLimitPlugin, replace=False)
         RelConverter.add_plugin_class(logical.SubqueryAlias, replace=False)
         RelConverter.add_plugin_class(logical.DaskTableScanPlugin, replace=False)
 

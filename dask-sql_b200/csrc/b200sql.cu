@@ -23,6 +23,7 @@ int b2_sm_count() {
 #include "filter.cuh"
 #include "groupby.cuh"
 #include "join.cuh"
+#include "sort.cuh"
 
 extern "C" {
 

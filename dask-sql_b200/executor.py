@@ -24,7 +24,7 @@ from . import expr as E
 from . import parallel as P
 from .device import DeviceColumn, TermSpec, I64, F64, U8
 from .expr import Expr, ColRef, Lit, Call
-from .frame import LazyFrame, Source, TableSource, JoinSource, AggSource
+from .frame import LazyFrame, Source, TableSource, JoinSource, AggSource, SortSource, LimitSource
 from .table import DeviceTable, HostColumn
 
 DENSE_MAX_SLOTS = 1 << 27          # direct-address group tables up to 128M slots
@@ -271,7 +271,55 @@ def materialize(src: Source, needed: Set[str]) -> List[Part]:
         return run_join(src, needed)
     if isinstance(src, AggSource):
         return [run_aggregate(src)]
+    if isinstance(src, SortSource):
+        return [run_sort(src, needed)]
+    if isinstance(src, LimitSource):
+        return [run_limit(src, needed)]
     raise TypeError(f"unknown source {type(src).__name__}")
+
+
+def run_sort(src: SortSource, needed: Set[str]) -> Part:
+    """ORDER BY: one stable radix sort of row ids per key (last key first), then one gather per
+    output column (b2_sort_by + b2_gather)."""
+    dev = _dev()
+    names = [n for n in src.child.columns if n in needed or any(n == k for k, _, _ in src.keys)]
+    whole = concat_parts(execute(src.child, names), names)
+    n = whole.n
+    if n <= 1:
+        return Part({k: whole[k] for k in names if k in needed}, n)
+    idx = torch.empty(n, dtype=torch.int32, device=dev)
+    L.iota(D.ptr(idx), n, D.stream_ptr())
+    ws = torch.empty(L.sort_ws_bytes(n), dtype=torch.uint8, device=dev)
+    for name, asc, nulls_first in reversed(src.keys):
+        cs = whole[name].as_struct()
+        stats["launches"] += 29
+        L.sort_by(C.byref(cs), n, 0 if asc else 1, 1 if nulls_first else 0, D.ptr(idx), D.ptr(ws), D.stream_ptr())
+    out = Part({}, n)
+    for k in names:
+        if k in needed:
+            stats["launches"] += 1
+            out[k] = D.gather(whole[k], idx, False)
+    return out
+
+
+def run_limit(src: LimitSource, needed: Set[str]) -> Part:
+    dev = _dev()
+    names = [n for n in src.child.columns if n in needed]
+    whole = concat_parts(execute(src.child, names), names)
+    lo = min(src.offset, whole.n)
+    hi = whole.n if src.fetch is None else min(whole.n, lo + int(src.fetch))
+    if lo == 0 and hi == whole.n:
+        return whole
+    idx = torch.arange(lo, hi, dtype=torch.int32, device=dev)
+    out = Part({}, hi - lo)
+    for k in names:
+        c = whole[k]
+        if c.valid is None:
+            out[k] = DeviceColumn(c.data[lo:hi], None, c.dtype, c.logical)   # a view: no copy
+        else:
+            stats["launches"] += 1
+            out[k] = D.gather(c, idx, False)
+    return out
 
 
 def empty_part(exprs: Dict[str, Expr]) -> Part:

@@ -81,6 +81,22 @@ class AggSource(Source):
                 self.schema[out] = (dt, lg)
 
 
+class SortSource(Source):
+    """ORDER BY: keys = [(child column, ascending, nulls_first)], most significant first."""
+
+    def __init__(self, child: "LazyFrame", keys):
+        self.child, self.keys = child, list(keys)
+        self.schema = OrderedDict((n, child.col_type(n)) for n in child.columns)
+
+
+class LimitSource(Source):
+    """LIMIT / OFFSET over the child's row order."""
+
+    def __init__(self, child: "LazyFrame", offset, fetch):
+        self.child, self.offset, self.fetch = child, int(offset or 0), fetch
+        self.schema = OrderedDict((n, child.col_type(n)) for n in child.columns)
+
+
 # ---------------------------------------------------------------------------------------------
 # series
 # ---------------------------------------------------------------------------------------------
@@ -288,7 +304,8 @@ class LazyFrame:
 
     def head(self, n=5, compute=True, npartitions=-1):
         if n != 0:
-            raise NotImplementedError("head(n>0) (LIMIT) is a 'next' row of the hot-path scope (SURVEY 8f)")
+            out = self.limit(n)
+            return out.compute() if compute else out
         out = LazyFrame(self.source, OrderedDict(self.exprs), self.pred + [Lit(False)])
         return out.compute() if compute else out
 
@@ -315,6 +332,18 @@ class LazyFrame:
 
     def reset_index(self, drop=False):
         return self
+
+    def sort_values(self, by, ascending=True, na_position="last", nulls_first=None):
+        by = [by] if isinstance(by, str) else list(by)
+        asc = [ascending] * len(by) if isinstance(ascending, bool) else list(ascending)
+        if nulls_first is None:
+            nulls_first = [na_position == "first"] * len(by)
+        elif isinstance(nulls_first, bool):
+            nulls_first = [nulls_first] * len(by)
+        return LazyFrame(SortSource(self, list(zip(by, asc, nulls_first))))
+
+    def limit(self, fetch=None, offset=0):
+        return LazyFrame(LimitSource(self, offset, fetch))
 
     # -- execution ------------------------------------------------------------------------
     def compute(self, **kwargs):

@@ -193,6 +193,8 @@ class PyExpr:
             return s
         if k == "alias":
             return self.name
+        if k == "sort":
+            return self.args[0].display()
         if k == "scalarfn":
             return f"{self.name.lower()}({', '.join(a.display() for a in self.args)})"
         return k
@@ -266,6 +268,16 @@ class PyExpr:
 
     def isNegated(self):
         return bool(self.negated)
+
+    # sort expressions (kind == "sort")
+    def isSortAscending(self):
+        return bool(getattr(self, "ascending", True))
+
+    def isSortNullsFirst(self):
+        return bool(getattr(self, "nulls_first", False))
+
+    def getSortExpr(self):
+        return self.args[0]
 
     def isDistinctAgg(self):
         return bool(self.distinct)
@@ -625,7 +637,17 @@ class Sort(LogicalPlan):
         self.schema = list(child.schema)
 
     def getCollation(self):
-        return self.keys
+        """Sort expressions with isSortAscending() / isSortNullsFirst() / column_name(rel), the
+        surface rel/logical/sort.py uses."""
+        out = []
+        for e, asc, nulls_first in self.keys:
+            s = PyExpr("sort", e.sql_type, args=[e]).with_inputs(self.inputs)
+            s.ascending, s.nulls_first = asc, nulls_first
+            out.append(s)
+        return out
+
+    def getNumRows(self):
+        return None
 
     def expressions(self):
         return [k[0] for k in self.keys]

@@ -301,6 +301,16 @@ int32_t b2_join_write_gather(const b2_scan_t* scan, const int32_t* probe_keys, c
                              int32_t nbuild, const b2_col_t* build_cols, void* const* build_out,
                              uint32_t* const* build_valid, void* stream);
 
+/* ---- ORDER BY ("next" row of the scope: the tail of TPC-H Q3) ------------------------------- */
+/* Stable LSD radix sort of row ids by one key column.  idx = int32[n] permutation (b2_iota for the
+ * identity) reordered in place so that col[idx[i]] is sorted (descending != 0: DESC; nulls_first
+ * != 0: NULL/NaN rows first).  Multi-key ORDER BY: call once per key from the LAST key to the FIRST.
+ * Replaces sort_values / nsmallest of physical/utils/sort.py:9-140.  ws >= b2_sort_ws_bytes(n). */
+int64_t b2_sort_ws_bytes(int64_t n);
+int32_t b2_iota(int32_t* out, int64_t n, void* stream);
+int32_t b2_sort_by(const b2_col_t* col, int64_t n, int32_t descending, int32_t nulls_first, int32_t* idx,
+                   void* ws, void* stream);
+
 /* ---- fused filter -> join -> group-by (star pipeline) ----------------------------- */
 /* out_slot[i] = key[i]-kmin (NULL key -> null_slot) as int32: turns a dense group-key column of
  * the build side into group-table slot numbers. */

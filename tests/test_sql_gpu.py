@@ -156,6 +156,45 @@ def test_stddev_variance(c):
     np.testing.assert_allclose([got.sd[0], got.vs[0]], [e.i.std(), e.v.var()], rtol=1e-9)
 
 
+def test_order_by_limit(c):
+    # ORDER BY / LIMIT (tests/integration/test_sort.py: results compared in order)
+    rng = np.random.default_rng(5)
+    n = 50_000
+    df = pd.DataFrame({"a": rng.integers(-20, 20, n), "b": rng.random(n), "c": rng.integers(0, 1000, n)})
+    df.loc[rng.integers(0, n, 300), "b"] = np.nan
+    df["k"] = pd.array(np.where(rng.random(n) < 0.02, None, rng.integers(-3, 4, n)), dtype="Int64")
+    c.create_table("t", df, npartitions=3)
+
+    def check(sql, exp, float_cols=("b",)):
+        got = c.sql(sql, return_futures=False).reset_index(drop=True)
+        exp = exp.reset_index(drop=True)
+        assert len(got) == len(exp)
+        for col in exp.columns:
+            g = got[col].to_numpy(dtype=float, na_value=np.nan)
+            e = exp[col].to_numpy(dtype=float, na_value=np.nan)
+            np.testing.assert_array_equal(g, e)
+
+    check("SELECT a, c FROM t ORDER BY a, c", df.sort_values(["a", "c"], kind="stable")[["a", "c"]])
+    check("SELECT a, c FROM t ORDER BY a DESC, c ASC", df.sort_values(["a", "c"], ascending=[False, True], kind="stable")[["a", "c"]])
+    # floats with NaN: ASC defaults to NULLS LAST, DESC to NULLS FIRST (postgres / DataFusion defaults)
+    check("SELECT b FROM t ORDER BY b", df.sort_values("b", na_position="last")[["b"]])
+    check("SELECT b FROM t ORDER BY b DESC", df.sort_values("b", ascending=False, na_position="first")[["b"]])
+    check("SELECT b FROM t ORDER BY b DESC NULLS LAST", df.sort_values("b", ascending=False, na_position="last")[["b"]])
+    check("SELECT k, c FROM t ORDER BY k NULLS FIRST, c DESC",
+          df.sort_values("c", ascending=False, kind="stable").sort_values("k", na_position="first", kind="stable")[["k", "c"]])
+    check("SELECT a, c FROM t ORDER BY a, c LIMIT 17", df.sort_values(["a", "c"], kind="stable")[["a", "c"]].head(17))
+    check("SELECT a, c FROM t ORDER BY a, c LIMIT 10 OFFSET 33",
+          df.sort_values(["a", "c"], kind="stable")[["a", "c"]].iloc[33:43])
+    check("SELECT a, c FROM t ORDER BY a + c DESC, c LIMIT 50",
+          df.assign(s=df.a + df.c).sort_values(["s", "c"], ascending=[False, True], kind="stable")[["a", "c"]].head(50))
+    # the real TPC-H Q3 tail: top groups by revenue
+    got = c.sql("SELECT a, SUM(c) AS rev FROM t WHERE c > 10 GROUP BY a ORDER BY rev DESC, a LIMIT 5",
+                return_futures=False)
+    e = df[df.c > 10].groupby("a", as_index=False).agg(rev=("c", "sum")).sort_values(
+        ["rev", "a"], ascending=[False, True], kind="stable").head(5)
+    assert got["a"].tolist() == e["a"].tolist() and got["rev"].tolist() == e["rev"].tolist()
+
+
 def test_integration_filter_join_groupby(c):
     # shape of test_compatibility.py:1015-1036 (CTEs: filter + agg + inner + left join)
     a = make_rand_df(200, a=int, b=(int, 20), c=(float, 0))
