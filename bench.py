@@ -33,7 +33,11 @@ QUERY = ("SELECT d.grp, SUM(f.val) AS rev FROM fact f JOIN dim d ON f.fk = d.pk 
 DIM_ROWS = 10_000_000
 N_GROUPS = 1_000_000
 BYTES_PER_FACT_ROW = 24       # fk + x + val, each read once
-PARTS_PER_GPU = 8
+TOTAL_PARTITIONS = 8      # BASELINE configs: "8 partitions"; spread over the GPUs of the run
+
+
+def parts_per_gpu(world):
+    return max(1, TOTAL_PARTITIONS // world)
 
 
 def parse_args():
@@ -74,7 +78,7 @@ def run_cpu_baseline(sample_rows, steps=1, warmup=0):
     from oracle import pandas_oracle as O
     cores = os.cpu_count() or 1
     fact, dim = cpu_tables(int(sample_rows))
-    parts = O.split(fact, max(PARTS_PER_GPU, cores))
+    parts = O.split(fact, max(TOTAL_PARTITIONS, cores))
     for _ in range(warmup):
         cpu_step(parts, dim, cores)
     ts = [cpu_step(parts, dim, cores)[0] for _ in range(max(1, steps))]
@@ -107,7 +111,7 @@ def reference_arm(args):
 def workload_config(args, n):
     return {"workload": "C4: TPC-H-Q3-shaped filter->join->groupby (BASELINE.json configs[3])",
             "fact_rows_total": int(args.rows), "fact_rows_per_gpu": int(args.rows) // n, "dim_rows": DIM_ROWS,
-            "groups": N_GROUPS, "partitions_per_gpu": PARTS_PER_GPU, "query": QUERY,
+            "groups": N_GROUPS, "partitions_per_gpu": parts_per_gpu(n), "query": QUERY,
             "l2": "inputs (24 B/row x rows) >> 126 MB L2, no flush needed",
             "planning": "Context.sql() is called every step; its plan (not its result) is served from the "
                         "prepared-statement cache after the first call; build side, lookup and group table "
@@ -120,27 +124,40 @@ def workload_config(args, n):
 # clocks
 # ---------------------------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
+    """nvidia-smi-equivalent clock / throttle-reason samples (NVML) taken only while `active`:
+    the thread and NVML are brought up before the warm-up so that the first sample falls inside
+    the timed region, which is only tens of milliseconds long."""
+
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
-
-    def run(self):
+        self.active = False
+        self.nv = self.h = None
         try:
             import pynvml as nv
             nv.nvmlInit()
-            h = nv.nvmlDeviceGetHandleByIndex(self.index)
-            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
-            names = {nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
-                     nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
-                     nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
-                     nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown"}
+            self.nv, self.h = nv, nv.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+        except Exception as e:  # pragma: no cover
+            self.reasons.add(f"sampler_error:{type(e).__name__}")
+
+    def run(self):
+        nv, h = self.nv, self.h
+        if nv is None:
+            return
+        names = {nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+                 nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                 nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown"}
+        try:
             while not self.stop_flag:
-                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
-                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                for bit, name in names.items():
-                    if r & bit:
-                        self.reasons.add(name)
-                time.sleep(0.004)   # the timed region is tens of milliseconds long
+                if self.active:
+                    self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                    for bit, name in names.items():
+                        if r & bit:
+                            self.reasons.add(name)
+                time.sleep(0.002)
         except Exception as e:  # pragma: no cover
             self.reasons.add(f"sampler_error:{type(e).__name__}")
 
@@ -198,7 +215,7 @@ def main():
     c = Context()
     fact_dist = "sharded" if world > 1 else "local"
     dim_dist = "root" if world > 1 else "local"
-    c.create_table("fact", {"fk": fk, "x": x, "val": val}, persist=True, npartitions=PARTS_PER_GPU,
+    c.create_table("fact", {"fk": fk, "x": x, "val": val}, persist=True, npartitions=parts_per_gpu(world),
                    distribution=fact_dist)
     c.create_table("dim", {"pk": pk, "flag": flag, "grp": grp}, persist=True, distribution=dim_dist)
 
@@ -219,12 +236,13 @@ def main():
         return executor.execute(lazy)
 
     # ---- value: device-resident inputs
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(args.warmup):
         parts = step_resident()
     n_groups_out = parts[0].n if args.warmup else None
-    sampler = ClockSampler(local)
-    sampler.start()
     barrier()
+    sampler.active = True
     launches0 = executor.stats["launches"]
     executor.kernel_events = []
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -234,6 +252,7 @@ def main():
         parts = step_resident()
     e1.record()
     barrier()
+    sampler.active = False
     wall = time.perf_counter() - w0
     dev_s = e0.elapsed_time(e1) * 1e-3
     t_step = max_over_ranks(max(dev_s, 0.0)) / args.steps
@@ -310,7 +329,7 @@ def run_e2e(args, torch, dist, dev, world, rank, fk, x, val, pk, flag, grp, fact
         host[name] = h
     torch.cuda.synchronize()
     c = Context()
-    c.create_table("fact", {k: host[k] for k in ("fk", "x", "val")}, persist=False, npartitions=PARTS_PER_GPU,
+    c.create_table("fact", {k: host[k] for k in ("fk", "x", "val")}, persist=False, npartitions=parts_per_gpu(world),
                    distribution=fact_dist)
     c.create_table("dim", {k: host[k] for k in ("pk", "flag", "grp")}, persist=False, distribution=dim_dist)
     steps = max(2, min(args.steps, 5))

@@ -125,6 +125,7 @@ _SIGS = {
                              _P, C.c_int32, C.POINTER(C.c_int32), C.POINTER(_P), C.POINTER(_P), C.c_int32,
                              C.POINTER(Col), C.POINTER(_P), C.POINTER(_P), _P],
     "b2_iota": [_P, C.c_int64, _P],
+    "b2_bitmap_or": [_P, _P, C.c_int64, _P],
     "b2_sort_by": [C.POINTER(Col), C.c_int64, C.c_int32, C.c_int32, _P, _P, _P],
     "b2_dense_slots": [C.POINTER(Col), C.c_int64, C.c_int64, C.c_int32, _P, _P],
     "b2_star_build_dense": [C.POINTER(Col), _P, C.c_int64, _P, C.c_int64, C.c_int64, _P, _P, _P],
@@ -175,6 +176,7 @@ join_count = _wrap("b2_join_count")
 join_write = _wrap("b2_join_write")
 join_write_gather = _wrap("b2_join_write_gather")
 iota = _wrap("b2_iota")
+bitmap_or = _wrap("b2_bitmap_or")
 sort_by = _wrap("b2_sort_by")
 _lib.b2_sort_ws_bytes.restype = C.c_int64
 _lib.b2_sort_ws_bytes.argtypes = [C.c_int64]

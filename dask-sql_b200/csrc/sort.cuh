@@ -140,7 +140,24 @@ b2_iota_kernel(int32_t* __restrict__ out, int64_t n) {
   for (int64_t i = (int64_t)blockIdx.x * B2_BLOCK + threadIdx.x; i < n; i += (int64_t)gridDim.x * B2_BLOCK) out[i] = (int32_t)i;
 }
 
+__global__ void __launch_bounds__(B2_BLOCK)
+b2_bitmap_or_kernel(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, int64_t nwords) {
+  for (int64_t i = (int64_t)blockIdx.x * B2_BLOCK + threadIdx.x; i < nwords; i += (int64_t)gridDim.x * B2_BLOCK)
+    dst[i] |= src[i];
+}
+
 extern "C" {
+
+// dst |= src over nwords 32-bit words: merges the presence bitmaps of per-GPU dense group tables
+// (NCCL offers no bitwise reduction).
+int32_t b2_bitmap_or(uint32_t* dst, const uint32_t* src, int64_t nwords, void* stream) {
+  B2_REQUIRE((dst && src) || nwords == 0, "null argument");
+  if (nwords <= 0) return B2_OK;
+  int grid = b2_wave_grid(b2_bitmap_or_kernel, B2_BLOCK, (nwords + B2_BLOCK - 1) / B2_BLOCK);
+  b2_bitmap_or_kernel<<<grid, B2_BLOCK, 0, (cudaStream_t)stream>>>(dst, src, nwords);
+  B2_CHECK_LAUNCH("b2_bitmap_or_kernel");
+  return B2_OK;
+}
 
 int64_t b2_sort_ws_bytes(int64_t n) {
   const int64_t nblocks = (n + B2_SORT_CHUNK - 1) / B2_SORT_CHUNK;

@@ -655,7 +655,7 @@ def grouped_aggregate(parts, pred, gexprs, gnames, plan: AggPlan, child, sharded
     if mode == "dense":
         stats["dense_groupby"] += 1
         nslots = rng + 1
-        gs = GroupState(dev, nslots, plan, need_present=True, force_rows=sharded)
+        gs = GroupState(dev, nslots, plan, need_present=True)
         for part in parts:
             if part.n == 0:
                 continue
@@ -717,6 +717,18 @@ def _allreduce_table(table: D.GroupTable, plan: AggPlan):
             P.allreduce_(cnt, "sum")
     if table.rows is not None:
         P.allreduce_(table.rows, "sum")
+    if table.present is not None:
+        # presence bitmaps are OR-ed: NCCL has no bitwise reduction, so every rank gathers the
+        # (nslots/8-byte) bitmaps and folds them with b2_bitmap_or -- far cheaper than keeping a
+        # row counter per slot (one more atomic per input row) just to be able to sum it
+        import torch.distributed as dist
+        size = P.world()[1]
+        if size > 1:
+            gathered = [torch.empty_like(table.present) for _ in range(size)]
+            dist.all_gather(gathered, table.present)
+            for g in gathered:
+                stats["launches"] += 1
+                L.bitmap_or(D.ptr(table.present), D.ptr(g), table.present.numel(), D.stream_ptr())
 
 
 class RawGroups:
@@ -1012,7 +1024,7 @@ def _star_dense_fast(src, fact, dim, fk_e, pk_e, gexprs, aggs, fact_pred, dim_pr
         P.broadcast_(flags, 0)
     plan = AggPlan([(E.substitute(e, fact.exprs) if e is not None else None, o, f) for e, o, f in aggs],
                    _nullable_fn(fact))
-    gs = GroupState(dev, nslots, plan, need_present=True, force_rows=sharded)
+    gs = GroupState(dev, nslots, plan, need_present=True)
     lk = L.StarLookup()
     lk.dense, lk.lookup, lk.kmin, lk.range = 1, lookup.data_ptr(), pmin, prange
     needed = set(fk_e.refs())
@@ -1143,7 +1155,7 @@ def try_star(src: AggSource, child: LazyFrame, gexprs, aggs, pred, sharded) -> O
         if int(flags[0].item()):
             return None
         nslots = cap
-    gs = GroupState(dev, nslots, plan, need_present=True, force_rows=sharded)
+    gs = GroupState(dev, nslots, plan, need_present=True)
 
     # pk -> slot lookup
     lk = L.StarLookup()

@@ -69,7 +69,12 @@ def _host_column(values, pin=True) -> HostColumn:
         else:
             raise NotImplementedError(
                 f"column dtype {logical} is outside the int64/float64/bool hot path of the B200 layer")
-        t = torch.from_numpy(np.ascontiguousarray(vals))
+        import warnings
+        with warnings.catch_warnings():
+            # pandas hands out read-only views; the tensor is only ever read (H2D source), so the
+            # zero-copy view is what we want
+            warnings.simplefilter("ignore", UserWarning)
+            t = torch.from_numpy(np.ascontiguousarray(vals))
     if pin and torch.cuda.is_available() and not t.is_pinned():
         t = t.pin_memory()
     v = None

@@ -248,6 +248,10 @@ int32_t b2_groupby_hashk(const b2_scan_t* scan, const int32_t* key_cols, int32_t
                          int64_t cap, const b2_agg_t* aggs, int32_t naggs,
                          const b2_aggstate_t* st, int32_t* d_flags, void* stream);
 
+/* dst |= src over nwords 32-bit words: merges the presence bitmaps of per-GPU dense group tables
+ * after an all-gather (NCCL has no bitwise reduction). */
+int32_t b2_bitmap_or(uint32_t* dst, const uint32_t* src, int64_t nwords, void* stream);
+
 /* bit-exact order-preserving double<->int64 images used by float MIN/MAX accumulators */
 int64_t b2_f64_to_ordered(double x);
 double  b2_ordered_to_f64(int64_t k);

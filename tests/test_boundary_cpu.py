@@ -154,6 +154,26 @@ def test_q3_plan_shape_and_lazy_graph():
     assert isinstance(join.right.source, TableSource) and len(join.right.pred) == 2
 
 
+def test_order_by_limit_and_moment_aggregates_plan():
+    from dask_sql_b200.frame import AggSource, LimitSource, SortSource
+    c = _ctx()
+    q = """SELECT d.grp, SUM(f.val) AS rev, STDDEV(f.val) AS sd FROM fact f JOIN dim d ON f.fk = d.pk
+           WHERE f.x > 0 GROUP BY d.grp ORDER BY rev DESC, d.grp LIMIT 10 OFFSET 2"""
+    plan = c.explain(q).splitlines()
+    assert plan[0] == "Limit: skip=2, fetch=10" and plan[1].strip() == "Sort: rev DESC, d.grp ASC"
+    lazy = c.sql(q)
+    assert lazy.columns == ["grp", "rev", "sd"]
+    lim = lazy.source
+    assert isinstance(lim, LimitSource) and (lim.offset, lim.fetch) == (2, 10)
+    srt = lim.child.source
+    assert isinstance(srt, SortSource) and [(a, nf) for _, a, nf in srt.keys] == [(False, True), (True, False)]
+    # STDDEV = sqrt of the (count, sum, sum of squares) recipe, accumulated in the same AggSource
+    agg = srt.child.source
+    assert isinstance(agg, AggSource)
+    fns = sorted(f for _, _, f in agg.aggs)
+    assert fns == ["count", "sum", "sum", "sum"]
+
+
 def test_unoptimized_plan_keeps_filter_node():
     c = _ctx()
     lazy = c.sql("SELECT x FROM fact WHERE x > 0", config_options={"sql.optimize": False})
