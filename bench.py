@@ -175,6 +175,12 @@ def main():
     if args.impl == "reference":
         return reference_arm(args)
 
+    # stdout carries exactly ONE JSON line: libraries that write to fd 1 (NCCL prints its version
+    # banner there) are pointed at stderr for the whole run
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
 
@@ -313,7 +319,7 @@ def main():
             "groups_out": n_groups_out, "wall_ms_per_step": wall / args.steps * 1e3,
             "fused_star_pipeline": executor.stats["star_fused"] > 0,
         }
-        print(json.dumps(line), flush=True)
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 

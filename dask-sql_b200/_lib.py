@@ -11,6 +11,7 @@ LIB_PATH = os.environ.get("B200SQL_LIB") or os.path.join(HERE, "libb200sql.so") 
 
 # ---- constants (mirror include/b200sql.h) ----
 I64, F64, U8 = 0, 1, 2
+U32 = 3          # storage-only: narrowed key-ordered join payload
 MAX_COLS, MAX_TERMS, MAX_AGGS, MAX_KEYS, MAX_GATHER, MAX_PROG = 16, 8, 8, 4, 8, 64
 TILE = 4096
 EQ, NE, LT, LE, GT, GE, IS_NULL, IS_NOT_NULL, IS_TRUE = range(9)
@@ -124,6 +125,15 @@ _SIGS = {
     "b2_join_write_gather": [C.POINTER(Scan), C.POINTER(C.c_int32), C.POINTER(JoinTable), C.c_int32, _P, _P, _P,
                              _P, C.c_int32, C.POINTER(C.c_int32), C.POINTER(_P), C.POINTER(_P), C.c_int32,
                              C.POINTER(Col), C.POINTER(_P), C.POINTER(_P), _P],
+    "b2_join_key_layout": [C.POINTER(Col), C.c_int64, C.c_int64, C.c_int64, C.POINTER(Col), C.c_int32, C.c_int64,
+                           _P, _P, _P, _P],
+    "b2_join_write_gather_keyed": [C.POINTER(Scan), C.POINTER(C.c_int32), C.POINTER(JoinTable), C.c_int32, _P, _P,
+                                   _P, _P, C.c_int32, C.POINTER(C.c_int32), C.POINTER(_P), C.POINTER(_P),
+                                   C.c_int32, C.POINTER(Col), C.POINTER(C.c_int64), C.POINTER(_P), C.POINTER(_P),
+                                   _P],
+    "b2_join_onepass": [C.POINTER(Scan), C.POINTER(C.c_int32), C.POINTER(JoinTable), C.c_int32, _P, _P, C.c_int32,
+                        C.POINTER(C.c_int32), C.POINTER(_P), C.POINTER(_P), C.c_int32, C.POINTER(Col),
+                        C.POINTER(C.c_int64), C.POINTER(_P), C.POINTER(_P), _P],
     "b2_iota": [_P, C.c_int64, _P],
     "b2_bitmap_or": [_P, _P, C.c_int64, _P],
     "b2_sort_by": [C.POINTER(Col), C.c_int64, C.c_int32, C.c_int32, _P, _P, _P],
@@ -175,6 +185,9 @@ join_build_dense = _wrap("b2_join_build_dense")
 join_count = _wrap("b2_join_count")
 join_write = _wrap("b2_join_write")
 join_write_gather = _wrap("b2_join_write_gather")
+join_write_gather_keyed = _wrap("b2_join_write_gather_keyed")
+join_key_layout = _wrap("b2_join_key_layout")
+join_onepass = _wrap("b2_join_onepass")
 iota = _wrap("b2_iota")
 bitmap_or = _wrap("b2_bitmap_or")
 sort_by = _wrap("b2_sort_by")

@@ -22,6 +22,7 @@ struct b2_joingather_arg {
   b2_col_t build_cols[B2_MAX_GATHER];
   void* build_out[B2_MAX_GATHER];
   uint32_t* build_valid[B2_MAX_GATHER];
+  int64_t build_base[B2_MAX_GATHER];  // B2_U32 storage: value = base + (uint32)stored
 };
 
 // normalised key image: -0.0 -> +0.0 so float keys compare like pandas; ints unchanged
@@ -65,6 +66,33 @@ b2_join_build_dense_kernel(const __grid_constant__ b2_col_t key, int64_t n, int6
     const uint64_t d = (uint64_t)raw - (uint64_t)kmin;
     if (d >= (uint64_t)range) continue;
     if (atomicExch(lookup + d, (int32_t)i) != -1) flags[0] = 1;
+  }
+}
+
+// Key-ordered layout of one build column of a unique dense-key table: out[key - kmin] = col[row]
+// (optionally narrowed to uint32 offsets from `base`), so that a probe reaches the payload with ONE
+// random access at the key offset instead of lookup[key] -> row -> col[row]; `present` marks the
+// offsets that hold a build row (it replaces the int32 lookup: range/8 bytes instead of range*4).
+__global__ void __launch_bounds__(B2_BLOCK)
+b2_join_key_layout_kernel(const __grid_constant__ b2_col_t key, int64_t n, int64_t kmin, int64_t range,
+                          const __grid_constant__ b2_col_t col, int has_col, int out_dtype, int64_t base,
+                          void* __restrict__ out_data, uint32_t* __restrict__ out_valid,
+                          uint32_t* __restrict__ present) {
+  for (int64_t i = (int64_t)blockIdx.x * B2_BLOCK + threadIdx.x; i < n; i += (int64_t)gridDim.x * B2_BLOCK) {
+    const int64_t kraw = b2_load_raw(key, i);
+    if (b2_is_null(key, i, kraw)) continue;
+    const uint64_t d = (uint64_t)kraw - (uint64_t)kmin;
+    if (d >= (uint64_t)range) continue;
+    if (present) atomicOr(present + (d >> 5), 1u << (d & 31));
+    if (!has_col) continue;
+    if (col.dtype == B2_U8) {
+      reinterpret_cast<uint8_t*>(out_data)[d] = reinterpret_cast<const uint8_t*>(col.data)[i];
+    } else {
+      const int64_t v = b2_load_raw(col, i);
+      if (out_dtype == B2_U32) reinterpret_cast<uint32_t*>(out_data)[d] = (uint32_t)((uint64_t)v - (uint64_t)base);
+      else reinterpret_cast<int64_t*>(out_data)[d] = v;
+    }
+    if (out_valid && (!col.valid || b2_bit(col.valid, i))) atomicOr(out_valid + (d >> 5), 1u << (d & 31));
   }
 }
 
@@ -124,10 +152,25 @@ __device__ __forceinline__ uint32_t b2_dense_probe(const b2_scan_t& s, int key_c
   if (kc.valid) live &= b2_valid_bits<R>(kc.valid, row0, bits);
   uint32_t matched = 0;
   const uint64_t range = (uint64_t)jt.range;
+  if (jt.dense == 2) {
+    // key-ordered layout: `lookup` is the presence bitmap and the build row IS the key offset
+    uint32_t word[R];
 #pragma unroll
-  for (int j = 0; j < R; ++j) {
-    const uint64_t d = (uint64_t)key[j] - (uint64_t)jt.kmin;
-    brow[j] = (((live >> j) & 1) && d < range) ? __ldg(jt.lookup + d) : -1;
+    for (int j = 0; j < R; ++j) {
+      const uint64_t d = (uint64_t)key[j] - (uint64_t)jt.kmin;
+      word[j] = (((live >> j) & 1) && d < range) ? (uint32_t)b2_ld_keep_i32(jt.lookup + (d >> 5)) : 0u;
+    }
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      const uint64_t d = (uint64_t)key[j] - (uint64_t)jt.kmin;
+      brow[j] = ((word[j] >> (d & 31)) & 1) ? (int32_t)d : -1;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      const uint64_t d = (uint64_t)key[j] - (uint64_t)jt.kmin;
+      brow[j] = (((live >> j) & 1) && d < range) ? b2_ld_keep_i32(jt.lookup + d) : -1;
+    }
   }
 #pragma unroll
   for (int j = 0; j < R; ++j) matched |= (uint32_t)(brow[j] >= 0) << j;
@@ -211,8 +254,12 @@ b2_join_write_kernel(const __grid_constant__ b2_scan_t s, const __grid_constant_
                      const __grid_constant__ b2_jointable_t jt, int mode, int64_t ntiles,
                      const int64_t* __restrict__ tile_off, int32_t* __restrict__ out_probe,
                      int32_t* __restrict__ out_build, uint8_t* __restrict__ build_matched,
-                     const __grid_constant__ b2_joingather_arg g) {
+                     const __grid_constant__ b2_joingather_arg g, uint64_t* __restrict__ lb_status,
+                     int64_t* __restrict__ lb_total) {
+  // lb_status != NULL (direct-address tables only): single pass, the tile's output offset comes from
+  // a decoupled look-back over the tiles' own counts instead of a separate counting kernel
   __shared__ int64_t sh[B2_WARPS];
+  __shared__ int64_t sh_excl;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t lt_mask = (1u << lane) - 1;
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -230,7 +277,22 @@ b2_join_write_kernel(const __grid_constant__ b2_scan_t s, const __grid_constant_
       }
       if (lane == 0) sh[warp] = wtotal;
       __syncthreads();
-      int64_t off = tile_off[tile];
+      int64_t off;
+      if (lb_status) {
+        if (warp == 0) {
+          int64_t agg = 0;
+          for (int w = 0; w < B2_WARPS; ++w) agg += sh[w];
+          const int64_t ex = b2_lookback(lb_status, tile, agg, lane);
+          if (lane == 0) {
+            sh_excl = ex;
+            if (tile == ntiles - 1) *lb_total = ex + agg;
+          }
+        }
+        __syncthreads();
+        off = sh_excl;
+      } else {
+        off = tile_off[tile];
+      }
       for (int w = 0; w < warp; ++w) off += sh[w];
       __syncthreads();
       // output position = off + rel[j]; rel is 32-bit (a tile emits <= 4096 rows) to save registers
@@ -292,12 +354,21 @@ b2_join_write_kernel(const __grid_constant__ b2_scan_t s, const __grid_constant_
 #pragma unroll
             for (int jj = 0; jj < 8; ++jj)
               if (rel[h + jj] >= 0) reinterpret_cast<uint8_t*>(g.build_out[k])[off + rel[h + jj]] = (uint8_t)raw[jj];
+          } else if (c.dtype == B2_U32) {   // narrowed key-ordered payload
+            const int64_t base = g.build_base[k];
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj)
+              raw[jj] = (rel[h + jj] >= 0 && brow[h + jj] >= 0)
+                            ? base + (int64_t)(uint32_t)b2_ld_keep_i32(reinterpret_cast<const int32_t*>(c.data) + brow[h + jj]) : 0;
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj)
+              if (rel[h + jj] >= 0) reinterpret_cast<int64_t*>(g.build_out[k])[off + rel[h + jj]] = raw[jj];
           } else {
             const int64_t fill = c.dtype == B2_F64 ? 0x7ff8000000000000LL : 0;
 #pragma unroll
             for (int jj = 0; jj < 8; ++jj)
               raw[jj] = (rel[h + jj] >= 0 && brow[h + jj] >= 0)
-                            ? __ldg(reinterpret_cast<const long long*>(c.data) + brow[h + jj]) : fill;
+                            ? b2_ld_keep_i64(reinterpret_cast<const int64_t*>(c.data) + brow[h + jj]) : fill;
 #pragma unroll
             for (int jj = 0; jj < 8; ++jj)
               if (rel[h + jj] >= 0) reinterpret_cast<int64_t*>(g.build_out[k])[off + rel[h + jj]] = raw[jj];
@@ -407,6 +478,28 @@ int32_t b2_join_build_dense(const b2_col_t* key, int64_t n, int64_t kmin, int64_
   return B2_OK;
 }
 
+int32_t b2_join_key_layout(const b2_col_t* key, int64_t n, int64_t kmin, int64_t range, const b2_col_t* col,
+                           int32_t out_dtype, int64_t base, void* out_data, uint32_t* out_valid,
+                           uint32_t* present, void* stream) {
+  B2_REQUIRE(key, "null argument");
+  B2_REQUIRE(key->dtype == B2_I64, "dense join needs an int64 key");
+  B2_REQUIRE(range > 0 && range < (1LL << 31), "bad range");
+  B2_REQUIRE(col || present, "nothing to lay out");
+  b2_col_t c;
+  memset(&c, 0, sizeof(c));
+  if (col) {
+    B2_REQUIRE(out_data, "null output");
+    B2_REQUIRE(out_dtype == col->dtype || (out_dtype == B2_U32 && col->dtype == B2_I64), "bad output type");
+    c = *col;
+  }
+  if (n <= 0) return B2_OK;
+  int grid = b2_wave_grid(b2_join_key_layout_kernel, B2_BLOCK, (n + B2_BLOCK - 1) / B2_BLOCK);
+  b2_join_key_layout_kernel<<<grid, B2_BLOCK, 0, (cudaStream_t)stream>>>(*key, n, kmin, range, c, col ? 1 : 0,
+                                                                         out_dtype, base, out_data, out_valid, present);
+  B2_CHECK_LAUNCH("b2_join_key_layout_kernel");
+  return B2_OK;
+}
+
 static int32_t b2_check_join(const b2_scan_t* scan, const int32_t* probe_keys, const b2_jointable_t* jt,
                              int32_t mode, b2_probekeys_arg* pk) {
   int32_t rc = b2_check_scan(scan);
@@ -448,16 +541,19 @@ int32_t b2_join_count(const b2_scan_t* scan, const int32_t* probe_keys, const b2
   return B2_OK;
 }
 
-int32_t b2_join_write_gather(const b2_scan_t* scan, const int32_t* probe_keys, const b2_jointable_t* jt,
-                             int32_t mode, const int64_t* d_tile_off, int32_t* out_probe_idx,
-                             int32_t* out_build_idx, uint8_t* build_matched, int32_t nprobe,
-                             const int32_t* probe_cols, void* const* probe_out, uint32_t* const* probe_valid,
-                             int32_t nbuild, const b2_col_t* build_cols, void* const* build_out,
-                             uint32_t* const* build_valid, void* stream) {
+static int32_t b2_join_write_impl(const b2_scan_t* scan, const int32_t* probe_keys, const b2_jointable_t* jt,
+                                  int32_t mode, const int64_t* d_tile_off, int32_t* out_probe_idx,
+                                  int32_t* out_build_idx, uint8_t* build_matched, int32_t nprobe,
+                                  const int32_t* probe_cols, void* const* probe_out,
+                                  uint32_t* const* probe_valid, int32_t nbuild, const b2_col_t* build_cols,
+                                  const int64_t* build_base, void* const* build_out,
+                                  uint32_t* const* build_valid, uint64_t* lb_status, int64_t* lb_total,
+                                  void* stream) {
   b2_probekeys_arg pk;
   int32_t rc = b2_check_join(scan, probe_keys, jt, mode, &pk);
   if (rc) return rc;
-  B2_REQUIRE(d_tile_off, "null argument");
+  B2_REQUIRE(d_tile_off || lb_status, "null argument");
+  B2_REQUIRE(!lb_status || (jt->dense && lb_total), "single-pass probe needs a direct-address table");
   B2_REQUIRE(nprobe >= 0 && nprobe <= B2_MAX_GATHER && nbuild >= 0 && nbuild <= B2_MAX_GATHER, "too many gather columns");
   b2_joingather_arg g;
   memset(&g, 0, sizeof(g));
@@ -471,7 +567,9 @@ int32_t b2_join_write_gather(const b2_scan_t* scan, const int32_t* probe_keys, c
   }
   for (int k = 0; k < nbuild; ++k) {
     B2_REQUIRE(build_out[k], "bad build gather");
+    B2_REQUIRE(build_cols[k].dtype != B2_U32 || (jt->dense == 2 && build_base), "uint32 payloads need a key-ordered table");
     g.build_cols[k] = build_cols[k];
+    g.build_base[k] = build_base ? build_base[k] : 0;
     g.build_out[k] = build_out[k];
     g.build_valid[k] = build_valid ? build_valid[k] : nullptr;
   }
@@ -480,14 +578,49 @@ int32_t b2_join_write_gather(const b2_scan_t* scan, const int32_t* probe_keys, c
   if (jt->dense) {
     int grid = b2_wave_grid(b2_join_write_kernel<true>, B2_BLOCK, ntiles);
     b2_join_write_kernel<true><<<grid, B2_BLOCK, 0, (cudaStream_t)stream>>>(
-        *scan, pk, *jt, mode, ntiles, d_tile_off, out_probe_idx, out_build_idx, build_matched, g);
+        *scan, pk, *jt, mode, ntiles, d_tile_off, out_probe_idx, out_build_idx, build_matched, g, lb_status, lb_total);
   } else {
     int grid = b2_wave_grid(b2_join_write_kernel<false>, B2_BLOCK, ntiles);
     b2_join_write_kernel<false><<<grid, B2_BLOCK, 0, (cudaStream_t)stream>>>(
-        *scan, pk, *jt, mode, ntiles, d_tile_off, out_probe_idx, out_build_idx, build_matched, g);
+        *scan, pk, *jt, mode, ntiles, d_tile_off, out_probe_idx, out_build_idx, build_matched, g, nullptr, nullptr);
   }
   B2_CHECK_LAUNCH("b2_join_write_kernel");
   return B2_OK;
+}
+
+int32_t b2_join_write_gather_keyed(const b2_scan_t* scan, const int32_t* probe_keys, const b2_jointable_t* jt,
+                                   int32_t mode, const int64_t* d_tile_off, int32_t* out_probe_idx,
+                                   int32_t* out_build_idx, uint8_t* build_matched, int32_t nprobe,
+                                   const int32_t* probe_cols, void* const* probe_out,
+                                   uint32_t* const* probe_valid, int32_t nbuild, const b2_col_t* build_cols,
+                                   const int64_t* build_base, void* const* build_out,
+                                   uint32_t* const* build_valid, void* stream) {
+  B2_REQUIRE(d_tile_off, "null argument");
+  return b2_join_write_impl(scan, probe_keys, jt, mode, d_tile_off, out_probe_idx, out_build_idx, build_matched,
+                            nprobe, probe_cols, probe_out, probe_valid, nbuild, build_cols, build_base, build_out,
+                            build_valid, nullptr, nullptr, stream);
+}
+
+int32_t b2_join_onepass(const b2_scan_t* scan, const int32_t* probe_keys, const b2_jointable_t* jt, int32_t mode,
+                        uint64_t* d_status, int64_t* d_total, int32_t nprobe, const int32_t* probe_cols,
+                        void* const* probe_out, uint32_t* const* probe_valid, int32_t nbuild,
+                        const b2_col_t* build_cols, const int64_t* build_base, void* const* build_out,
+                        uint32_t* const* build_valid, void* stream) {
+  B2_REQUIRE(d_status && d_total, "null argument");
+  return b2_join_write_impl(scan, probe_keys, jt, mode, nullptr, nullptr, nullptr, nullptr, nprobe, probe_cols,
+                            probe_out, probe_valid, nbuild, build_cols, build_base, build_out, build_valid,
+                            d_status, d_total, stream);
+}
+
+int32_t b2_join_write_gather(const b2_scan_t* scan, const int32_t* probe_keys, const b2_jointable_t* jt,
+                             int32_t mode, const int64_t* d_tile_off, int32_t* out_probe_idx,
+                             int32_t* out_build_idx, uint8_t* build_matched, int32_t nprobe,
+                             const int32_t* probe_cols, void* const* probe_out, uint32_t* const* probe_valid,
+                             int32_t nbuild, const b2_col_t* build_cols, void* const* build_out,
+                             uint32_t* const* build_valid, void* stream) {
+  return b2_join_write_gather_keyed(scan, probe_keys, jt, mode, d_tile_off, out_probe_idx, out_build_idx,
+                                    build_matched, nprobe, probe_cols, probe_out, probe_valid, nbuild, build_cols,
+                                    nullptr, build_out, build_valid, stream);
 }
 
 int32_t b2_join_write(const b2_scan_t* scan, const int32_t* probe_keys, const b2_jointable_t* jt, int32_t mode,

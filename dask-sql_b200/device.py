@@ -21,8 +21,21 @@ def require_cuda():
         raise RuntimeError("dask_sql_b200 executes on a CUDA device (B200, sm_100a); no CPU fallback exists")
 
 
+_stream = [None]
+
+
 def stream_ptr():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    """Current torch stream as a C pointer.  torch.cuda.current_stream() costs ~15 us of Python per
+    call and a query makes dozens of launches, so the pointer is cached until reset_stream() (the
+    executor calls it on entry to every query and before resolving a pending result)."""
+    s = _stream[0]
+    if s is None:
+        s = _stream[0] = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return s
+
+
+def reset_stream():
+    _stream[0] = None
 
 
 def ptr(t: Optional[torch.Tensor]):
@@ -237,6 +250,7 @@ def _workspace(device, nbytes):
 
 
 def col_stats(col: DeviceColumn) -> Stats:
+    reset_stream()          # a blocking call anyway: also the point where table loading picks up the stream
     out = torch.empty(4, dtype=torch.int64, device=col.device)
     ws = _workspace(col.device, L.stats_ws_bytes())
     st = col.as_struct()
@@ -310,6 +324,24 @@ def select(scan: L.Scan, device, gather_cols: Sequence[int] = (), want_idx=True,
     return idx, res, total
 
 
+def select_launch(scan: L.Scan, device, gather_cols: Sequence[int], cols: Sequence[DeviceColumn]):
+    """select() without the host round trip: outputs are allocated at their upper bound (scan.n rows),
+    count and write kernels are both enqueued, and the count stays on the device.  Only for inputs
+    without validity bitmaps.  -> ([output tensors of scan.n rows], 1-element int64 count tensor)"""
+    n = scan.n
+    ntiles = L.num_tiles(n)
+    tile_off = torch.empty(ntiles + 1, dtype=torch.int64, device=device)
+    L.select_count(C.byref(scan), ptr(tile_off), stream_ptr())
+    outs = [torch.empty(n, dtype=_TORCH_DTYPE[cols[g].dtype], device=device) for g in gather_cols]
+    k = len(gather_cols)
+    gc = (C.c_int32 * max(1, k))(*gather_cols)
+    od = (C.c_void_p * max(1, k))(*[o.data_ptr() for o in outs])
+    ov = (C.c_void_p * max(1, k))(*[0] * k)
+    if n > 0:
+        L.select_write(C.byref(scan), ptr(tile_off), C.c_void_p(0), k, gc, od, ov, stream_ptr())
+    return outs, tile_off[ntiles:ntiles + 1]
+
+
 def gather(col: DeviceColumn, idx: torch.Tensor, nullable: bool) -> DeviceColumn:
     n = int(idx.shape[0])
     out = torch.empty(n, dtype=_TORCH_DTYPE[col.dtype], device=col.device)
@@ -329,8 +361,14 @@ def _pow2_at_least(x):
 class GroupTable:
     """Caller-owned accumulator arrays of one group-by (dense / hash1 / hashk)."""
 
-    def __init__(self, device, nslots, agg_specs, agg_dtypes, need_cnt, need_rows, need_present):
+    def __init__(self, device, nslots, agg_specs, agg_dtypes, need_cnt, need_rows, need_present, indicator=None):
+        """indicator: index of a float SUM accumulator whose input is never NULL.  It starts at -0.0
+        instead of +0.0; the kernels add x + 0.0 (never -0.0), so a slot still holding the -0.0 bit
+        pattern (= INT64_MIN = EMPTY_KEY) received no row.  That makes the accumulator itself the
+        "group exists" flag and saves the per-row presence-bitmap lookup (an L1 wavefront per row on
+        a path whose bound is the SM's load/store issue rate)."""
         self.device, self.nslots = device, nslots
+        self.indicator = indicator
         self.specs = list(agg_specs)
         self.aggs = make_aggs(self.specs)
         self.state = L.AggState()
@@ -344,7 +382,7 @@ class GroupTable:
                 elif op == L.AGG_MAX:
                     acc = torch.full((nslots,), -(1 << 63), dtype=torch.int64, device=device)
                 elif op == L.AGG_SUMF or dt == F64:
-                    acc = torch.zeros(nslots, dtype=torch.float64, device=device)
+                    acc = torch.full((nslots,), -0.0 if a == indicator else 0.0, dtype=torch.float64, device=device)
                 else:
                     acc = torch.zeros(nslots, dtype=torch.int64, device=device)
             if col >= 0 and (op == L.AGG_COUNT or need_cnt[a]):
@@ -354,6 +392,7 @@ class GroupTable:
             self.state.acc[a] = acc.data_ptr() if acc is not None else 0
             self.state.cnt[a] = cnt.data_ptr() if cnt is not None else 0
         self.rows = torch.zeros(nslots, dtype=torch.int64, device=device) if need_rows else None
+        need_present = need_present and indicator is None
         self.present = torch.zeros(bitmap_words(nslots), dtype=torch.int32, device=device) if need_present else None
         self.state.rows = self.rows.data_ptr() if self.rows is not None else 0
         self.state.present = self.present.data_ptr() if self.present is not None else 0
@@ -415,6 +454,39 @@ class JoinTable:
         L.join_build(arr, len(keys), n, ptr(self.head), ptr(self.next), cap, stream_ptr())
         self.struct.dense, self.struct.head, self.struct.next, self.struct.cap = 0, self.head.data_ptr(), self.next.data_ptr(), cap
 
+    def key_layout(self, cols: Sequence[DeviceColumn]):
+        """Re-lay build-side columns of a unique dense-key table in key order (b2_join_key_layout):
+        the probe then fetches a payload with one random access at key-kmin, the int32 row lookup
+        shrinks to a presence bitmap, and int64 payloads with a 32-bit value range are stored as
+        uint32 offsets (half the L2 footprint).  After this the table matches by key offset
+        (struct.dense == 2) and only join_probe_gather may be used with it."""
+        assert self.dense and self.struct.dense == 1
+        dev, kmin, rng, n = self.keys[0].device, self.struct.kmin, self.struct.range, self.n
+        ks = self.keys[0].as_struct()
+        present = torch.zeros(bitmap_words(rng), dtype=torch.int32, device=dev)
+        store = {L.U32: torch.int32, I64: torch.int64, F64: torch.float64, U8: torch.uint8}
+        self.keyed_cols, self.keyed_base = [], []
+        first = True
+        for c in cols:
+            out_dtype, base = c.dtype, 0
+            if c.dtype == I64:
+                st = c.ensure_stats()
+                if st.vmin is not None and st.vmax - st.vmin < (1 << 32):
+                    out_dtype, base = L.U32, int(st.vmin)
+            out = torch.empty(rng, dtype=store[out_dtype], device=dev)     # only present offsets are read
+            ovalid = torch.zeros(bitmap_words(rng), dtype=torch.int32, device=dev) if c.valid is not None else None
+            cs = c.as_struct()
+            L.join_key_layout(C.byref(ks), n, kmin, rng, C.byref(cs), out_dtype, base, ptr(out), ptr(ovalid),
+                              ptr(present) if first else None, stream_ptr())
+            first = False
+            self.keyed_cols.append(DeviceColumn(out, ovalid, out_dtype, c.logical))
+            self.keyed_base.append(base)
+        if first:
+            L.join_key_layout(C.byref(ks), n, kmin, rng, None, 0, 0, None, None, ptr(present), stream_ptr())
+        self.present = present
+        self.lookup = None
+        self.struct.dense, self.struct.lookup = 2, present.data_ptr()
+
 
 def join_probe_gather(scan, probe_keys, jt: JoinTable, mode, device, scan_cols, probe_gather, build_cols,
                       build_nullable, build_matched=None):
@@ -442,19 +514,74 @@ def join_probe_gather(scan, probe_keys, jt: JoinTable, mode, device, scan_cols, 
         pc = (C.c_int32 * max(1, np_))(*probe_gather)
         po = (C.c_void_p * max(1, np_))(*[t.data_ptr() for t in pouts])
         pv = (C.c_void_p * max(1, np_))(*[(v.data_ptr() if v is not None else 0) for v in pvalid])
-        bc = (L.Col * max(1, nb))(*[c.as_struct() for c in build_cols])
         bo = (C.c_void_p * max(1, nb))(*[t.data_ptr() for t in bouts])
         bv = (C.c_void_p * max(1, nb))(*[(v.data_ptr() if v is not None else 0) for v in bvalid])
-        L.join_write_gather(C.byref(scan), pk, C.byref(jt.struct), mode, ptr(tile_off), None, None,
-                            ptr(build_matched), np_, pc, po, pv, nb, bc, bo, bv, stream_ptr())
+        if jt.struct.dense == 2:
+            assert len(jt.keyed_cols) == nb and build_matched is None
+            bc = (L.Col * max(1, nb))(*[c.as_struct() for c in jt.keyed_cols])
+            bb = (C.c_int64 * max(1, nb))(*jt.keyed_base)
+            L.join_write_gather_keyed(C.byref(scan), pk, C.byref(jt.struct), mode, ptr(tile_off), None, None,
+                                      None, np_, pc, po, pv, nb, bc, bb, bo, bv, stream_ptr())
+        else:
+            bc = (L.Col * max(1, nb))(*[c.as_struct() for c in build_cols])
+            L.join_write_gather(C.byref(scan), pk, C.byref(jt.struct), mode, ptr(tile_off), None, None,
+                                ptr(build_matched), np_, pc, po, pv, nb, bc, bo, bv, stream_ptr())
     pres = [DeviceColumn(o, v, scan_cols[sl].dtype, scan_cols[sl].logical)
             for o, v, sl in zip(pouts, pvalid, probe_gather)]
     bres = [DeviceColumn(o, v, c.dtype, c.logical) for o, v, c in zip(bouts, bvalid, build_cols)]
     return pres, bres, total
 
 
+def join_probe_onepass(scan, probe_keys, jt: JoinTable, mode, device, scan_cols, probe_gather, build_cols,
+                       build_nullable):
+    """join_probe_gather for direct-address tables without the counting pass and without the host
+    round trip: one kernel (b2_join_onepass: tile offsets by decoupled look-back), outputs allocated
+    at their upper bound (one row per probe row), the row count stays on the device.
+    -> (probe outputs, build outputs, 1-element int64 count tensor); slice with `trim` once known."""
+    assert jt.dense
+    n = scan.n
+    ntiles = L.num_tiles(n)
+    ws = torch.zeros(ntiles + 1, dtype=torch.int64, device=device)      # look-back status words + total
+    pk = (C.c_int32 * len(probe_keys))(*probe_keys)
+    pouts, pvalid, bouts, bvalid = [], [], [], []
+    for sl in probe_gather:
+        c = scan_cols[sl]
+        pouts.append(torch.empty(n, dtype=_TORCH_DTYPE[c.dtype], device=device))
+        pvalid.append(torch.zeros(bitmap_words(n), dtype=torch.int32, device=device) if c.valid is not None else None)
+    for c in build_cols:
+        bouts.append(torch.empty(n, dtype=_TORCH_DTYPE[c.dtype], device=device))
+        bvalid.append(torch.zeros(bitmap_words(n), dtype=torch.int32, device=device)
+                      if (c.valid is not None or build_nullable) else None)
+    np_, nb = len(probe_gather), len(build_cols)
+    pc = (C.c_int32 * max(1, np_))(*probe_gather)
+    po = (C.c_void_p * max(1, np_))(*[t.data_ptr() for t in pouts])
+    pv = (C.c_void_p * max(1, np_))(*[(v.data_ptr() if v is not None else 0) for v in pvalid])
+    bo = (C.c_void_p * max(1, nb))(*[t.data_ptr() for t in bouts])
+    bv = (C.c_void_p * max(1, nb))(*[(v.data_ptr() if v is not None else 0) for v in bvalid])
+    if jt.struct.dense == 2:
+        assert len(jt.keyed_cols) == nb
+        bc = (L.Col * max(1, nb))(*[c.as_struct() for c in jt.keyed_cols])
+        bb = (C.c_int64 * max(1, nb))(*jt.keyed_base)
+    else:
+        bc = (L.Col * max(1, nb))(*[c.as_struct() for c in build_cols])
+        bb = None
+    L.join_onepass(C.byref(scan), pk, C.byref(jt.struct), mode, ptr(ws), C.c_void_p(ws.data_ptr() + 8 * ntiles),
+                   np_, pc, po, pv, nb, bc, bb, bo, bv, stream_ptr())
+
+    def trim(total):
+        w = bitmap_words(total)
+        pres = [DeviceColumn(o[:total], v[:w] if v is not None else None, scan_cols[sl].dtype, scan_cols[sl].logical)
+                for o, v, sl in zip(pouts, pvalid, probe_gather)]
+        bres = [DeviceColumn(o[:total], v[:w] if v is not None else None, c.dtype, c.logical)
+                for o, v, c in zip(bouts, bvalid, build_cols)]
+        return pres, bres
+
+    return trim, ws[ntiles:]
+
+
 def join_probe(scan, probe_keys, jt: JoinTable, mode, device, build_matched=None):
     """-> (probe_idx int32, build_idx int32 or None, total)."""
+    assert jt.struct.dense != 2, "a key-ordered table yields key offsets, not build rows"
     n = scan.n
     ntiles = L.num_tiles(n)
     tile_off = torch.empty(ntiles + 1, dtype=torch.int64, device=device)

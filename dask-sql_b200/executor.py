@@ -13,6 +13,7 @@ There is no CPU fallback anywhere in this module: every row-level operation is a
 libb200sql.so; host code only plans, allocates and moves metadata.
 """
 import ctypes as C
+import os
 from typing import Dict, List, Optional, Sequence, Set
 
 import numpy as np
@@ -33,7 +34,7 @@ _LOGICAL = {I64: "int64", F64: "float64", U8: "bool"}
 
 # counters the bench / tests read to prove which kernels ran
 stats = {"launches": 0, "star_fused": 0, "dense_groupby": 0, "hash_groupby": 0, "dense_join": 0,
-         "chain_join": 0, "h2d_bytes": 0, "d2h_bytes": 0}
+         "chain_join": 0, "keyed_join": 0, "h2d_bytes": 0, "d2h_bytes": 0}
 
 
 # Optional per-launch timing of the dominant kernels (bench.py sets this to a list): each entry
@@ -67,6 +68,87 @@ class Part(dict):
     def __init__(self, cols=(), n=0):
         super().__init__(cols)
         self.n = int(n)
+
+    def resolve(self):
+        return self
+
+
+class PendingPart(Part):
+    """A partition whose row count is still on the device.
+
+    The kernels that produce it are already enqueued (outputs allocated at their upper bound), the
+    count travels to a pinned host word behind them; the first access to `.n` or to a column waits
+    for it and finishes the partition.  A query whose result nobody looks at yet -- the next
+    Context.sql() of a loop, the next operator's launch code -- therefore never stalls the host
+    behind the GPU: the reference's lazy dask graph, restated as "kernels first, sync on use"."""
+
+    def __init__(self, thunk):
+        dict.__init__(self)
+        self._thunk = thunk
+        self._n = 0
+
+    @property
+    def resolved(self):
+        return self._thunk is None
+
+    def resolve(self):
+        if self._thunk is not None:
+            thunk, self._thunk = self._thunk, None
+            D.reset_stream()
+            real = thunk().resolve()
+            dict.update(self, real)
+            self._n = real.n
+        return self
+
+    @property
+    def n(self):
+        return self.resolve()._n
+
+    @n.setter
+    def n(self, v):
+        self._n = int(v)
+
+    def __getitem__(self, k):
+        return dict.__getitem__(self.resolve(), k)
+
+    def __iter__(self):
+        return dict.__iter__(self.resolve())
+
+    def __len__(self):
+        return dict.__len__(self.resolve())
+
+    def __contains__(self, k):
+        return dict.__contains__(self.resolve(), k)
+
+    def keys(self):
+        return dict.keys(self.resolve())
+
+    def values(self):
+        return dict.values(self.resolve())
+
+    def items(self):
+        return dict.items(self.resolve())
+
+    def get(self, k, default=None):
+        return dict.get(self.resolve(), k, default)
+
+
+class DeviceCount:
+    """An int64 count produced on the device, copied to pinned host memory behind the kernels
+    that wrote it; .get() waits for that copy only."""
+
+    def __init__(self, *tensors):
+        flat = torch.cat([t.reshape(-1).to(torch.int64) for t in tensors]) if len(tensors) > 1 else \
+            tensors[0].reshape(-1)
+        self.host = torch.empty(flat.shape, dtype=flat.dtype, pin_memory=True)
+        self.host.copy_(flat, non_blocking=True)
+        self.event = torch.cuda.Event()
+        self.event.record()
+
+    def get(self):
+        self.event.synchronize()
+        stats["d2h_bytes"] += self.host.numel() * 8
+        return self.host.tolist()
 
 
 # ---------------------------------------------------------------------------------------------
@@ -333,6 +415,7 @@ def empty_part(exprs: Dict[str, Expr]) -> Part:
 
 def execute(frame: LazyFrame, needed: Optional[Sequence[str]] = None) -> List[Part]:
     """Materialise `needed` output columns of `frame`, partition by partition."""
+    D.reset_stream()
     names = list(needed) if needed is not None else frame.columns
     exprs = {n: frame.exprs[n] for n in names}
     pred, never = simplify_pred(frame.pred)
@@ -344,8 +427,8 @@ def execute(frame: LazyFrame, needed: Optional[Sequence[str]] = None) -> List[Pa
     for p in pred:
         p.refs(src_needed)
     parts = materialize(frame.source, src_needed)
-    out = []
-    for part in parts:
+
+    def project(part: Part) -> Part:
         if pred:
             colrefs = sorted({r for e in exprs.values() for r in e.refs()})
             part = select_part(part, pred, colrefs)
@@ -355,7 +438,14 @@ def execute(frame: LazyFrame, needed: Optional[Sequence[str]] = None) -> List[Pa
                 res[n] = const_column(e.value, e.dtype, part.n, _dev())
             else:
                 res[n] = eval_expr(part, e)
-        out.append(res)
+        return res
+
+    out = []
+    for part in parts:
+        if isinstance(part, PendingPart) and not part.resolved:
+            out.append(PendingPart(lambda part=part: project(part.resolve())))   # stays lazy
+        else:
+            out.append(project(part))
     return out
 
 
@@ -363,10 +453,10 @@ def execute(frame: LazyFrame, needed: Optional[Sequence[str]] = None) -> List[Pa
 # aggregation
 # ---------------------------------------------------------------------------------------------
 class KAgg:
-    __slots__ = ("expr", "op", "need_cnt", "dtype")
+    __slots__ = ("expr", "op", "need_cnt", "dtype", "nullable")
 
-    def __init__(self, expr, op, dtype):
-        self.expr, self.op, self.need_cnt, self.dtype = expr, op, False, dtype
+    def __init__(self, expr, op, dtype, nullable=True):
+        self.expr, self.op, self.need_cnt, self.dtype, self.nullable = expr, op, False, dtype, nullable
 
 
 class AggPlan:
@@ -394,10 +484,10 @@ class AggPlan:
                     self.need_rows = True
                     self.outs.append((out, "count", None, "rows", e.dtype, lg))
             elif fn == "sum":
-                a = self._slot(e, L.AGG_SUM)
+                a = self._slot(e, L.AGG_SUM, nul)
                 self.outs.append((out, "sum", a, self._cnt(e) if nul else None, e.dtype, lg))
             elif fn in ("mean", "avg"):
-                a = self._slot(e, L.AGG_SUM if e.dtype == F64 else L.AGG_SUMF)
+                a = self._slot(e, L.AGG_SUM if e.dtype == F64 else L.AGG_SUMF, nul)
                 if nul:
                     c = self._cnt(e)
                 else:
@@ -405,18 +495,26 @@ class AggPlan:
                     c = "rows"
                 self.outs.append((out, "mean", a, c, e.dtype, lg))
             elif fn in ("min", "max"):
-                a = self._slot(e, L.AGG_MIN if fn == "min" else L.AGG_MAX)
+                a = self._slot(e, L.AGG_MIN if fn == "min" else L.AGG_MAX, nul)
                 self.outs.append((out, fn, a, self._cnt(e) if nul else None, e.dtype, lg))
             else:
                 raise NotImplementedError(f"aggregate function {fn} is a 'next' row of the hot-path scope")
         if len(self.kaggs) > L.MAX_AGGS:
             raise NotImplementedError(f"more than {L.MAX_AGGS} distinct accumulators in one GROUP BY")
+        # a float SUM over a never-NULL input receives an add from every row of its group: started
+        # at -0.0 it doubles as the group's existence flag (device.GroupTable.indicator)
+        self.indicator = None
+        if not self.need_rows and os.environ.get("B200SQL_NO_INDICATOR") != "1":
+            for i, k in enumerate(self.kaggs):
+                if not k.nullable and (k.op == L.AGG_SUMF or (k.op == L.AGG_SUM and k.dtype == F64)):
+                    self.indicator = i
+                    break
 
-    def _slot(self, e, op):
+    def _slot(self, e, op, nullable=True):
         for i, k in enumerate(self.kaggs):
             if k.op == op and repr(k.expr) == repr(e):
                 return i
-        self.kaggs.append(KAgg(e, op, e.dtype))
+        self.kaggs.append(KAgg(e, op, e.dtype, nullable))
         return len(self.kaggs) - 1
 
     def _cnt(self, e):
@@ -424,7 +522,7 @@ class AggPlan:
             if repr(k.expr) == repr(e):
                 k.need_cnt = True
                 return i
-        self.kaggs.append(KAgg(e, L.AGG_COUNT, e.dtype))
+        self.kaggs.append(KAgg(e, L.AGG_COUNT, e.dtype, True))
         self.kaggs[-1].need_cnt = True
         return len(self.kaggs) - 1
 
@@ -468,14 +566,14 @@ def _one_row(value, dtype, logical, dev) -> DeviceColumn:
     return c
 
 
-def run_aggregate(src: AggSource) -> Part:
+def run_aggregate(src: AggSource, allow_fast=True) -> Part:
     child = src.child
     pred, never = simplify_pred(child.pred)
     gexprs = [child.exprs[g] for g in src.group_cols]
     aggs = [(child.exprs[i] if i is not None else None, out, fn) for i, out, fn in src.aggs]
     sharded = P.world()[1] > 1 and frame_distribution(child) in ("sharded", "root")
     if gexprs and isinstance(child.source, JoinSource) and not never:
-        res = try_star(src, child, gexprs, aggs, pred, sharded)
+        res = try_star(src, child, gexprs, aggs, pred, sharded, allow_fast)
         if res is not None:
             return res
     needed: Set[str] = set()
@@ -582,7 +680,8 @@ class GroupState:
         specs = [(0, ka.op) for ka in plan.kaggs]
         self.table = D.GroupTable(dev, nslots, specs, [ka.dtype for ka in plan.kaggs],
                                   [ka.need_cnt for ka in plan.kaggs], need_rows,
-                                  need_present and not need_rows)
+                                  need_present and not need_rows,
+                                  indicator=None if need_rows else plan.indicator)
         self.plan = plan
         self.nslots = nslots
 
@@ -796,8 +895,64 @@ def _gather_state(gs: GroupState, idx, dev):
     return acc_cols, cnt_cols, rows_col
 
 
-def _finalize_dense(gs: GroupState, kmin, rng, gname, gexpr, glog, plan, dev, key_nullable=True) -> Part:
-    return finish(_extract_dense(gs, kmin, rng, gname, gexpr, glog, dev, key_nullable), plan)
+def _occupancy(t: D.GroupTable, keys: torch.Tensor):
+    """(column, predicate term) selecting the slots that received at least one row."""
+    if t.rows is not None:
+        return DeviceColumn(t.rows, None, I64), TermSpec(0, L.GT, 0)
+    if t.indicator is not None:
+        # untouched float SUM accumulator = -0.0 = the INT64_MIN bit pattern
+        return DeviceColumn(t.acc[t.indicator].view(torch.int64), None, I64), TermSpec(0, L.NE, L.EMPTY_KEY)
+    return DeviceColumn(keys, t.present, I64), TermSpec(0, L.IS_NOT_NULL, 0)
+
+
+DEFER_MAX_SLOTS = 1 << 23    # deferred compaction allocates its outputs at nslots rows
+
+
+def _finalize_dense(gs: GroupState, kmin, rng, gname, gexpr, glog, plan, dev, key_nullable=True,
+                    check=None, fallback=None) -> Part:
+    """Dense table -> result partition.  `check`: optional int32 device flags whose first word must
+    be 0 for the result to stand (star pipeline: duplicate build keys), else `fallback()` is the
+    result.  With a NULL-free int64 key the compaction is enqueued without waiting for its count
+    (PendingPart); the flags ride on the same host copy."""
+    nslots = rng + 1
+    t = gs.table
+    ncols = 1 + sum(a is not None for a in t.acc) + sum(c is not None for c in t.cnt) + (t.rows is not None)
+    if not key_nullable and gexpr.dtype == I64 and nslots <= DEFER_MAX_SLOTS and ncols <= L.MAX_GATHER \
+            and os.environ.get("B200SQL_NO_DEFER") != "1":
+        slot_keys = torch.arange(kmin, kmin + nslots, dtype=torch.int64, device=dev)
+        occ, term = _occupancy(t, slot_keys)
+        cols, where = [occ, DeviceColumn(slot_keys, None, I64)], {}
+        for i, (acc, cnt) in enumerate(zip(t.acc, t.cnt)):
+            if acc is not None:
+                where[("a", i)] = len(cols)
+                cols.append(DeviceColumn(acc, None, F64 if acc.dtype == torch.float64 else I64))
+            if cnt is not None:
+                where[("c", i)] = len(cols)
+                cols.append(DeviceColumn(cnt, None, I64))
+        if t.rows is not None:
+            where[("r", 0)] = len(cols)
+            cols.append(DeviceColumn(t.rows, None, I64))
+        gcols = list(range(1, len(cols)))
+        stats["launches"] += 3
+        outs, count = D.select_launch(D.make_scan(cols, [term], nslots), dev, gcols, cols)
+        pending = DeviceCount(count, check) if check is not None else DeviceCount(count)
+
+        def thunk():
+            vals = pending.get()
+            total = int(vals[0])
+            if check is not None and vals[1]:
+                return fallback()
+            got = {g: DeviceColumn(o[:total], None, cols[g].dtype) for g, o in zip(gcols, outs)}
+            kcol = DeviceColumn(got[1].data, None, I64, glog)
+            acc_cols = [got.get(where.get(("a", i))) for i in range(len(t.acc))]
+            cnt_cols = [got.get(where.get(("c", i))) for i in range(len(t.cnt))]
+            return finish(RawGroups({gname: kcol}, acc_cols, cnt_cols, got.get(where.get(("r", 0))), total), plan)
+
+        return PendingPart(thunk)
+    out = finish(_extract_dense(gs, kmin, rng, gname, gexpr, glog, dev, key_nullable), plan)
+    if check is not None and int(check[0].item()):
+        return fallback()
+    return out
 
 
 def _extract_dense(gs: GroupState, kmin, rng, gname, gexpr, glog, dev, key_nullable=True) -> RawGroups:
@@ -806,12 +961,7 @@ def _extract_dense(gs: GroupState, kmin, rng, gname, gexpr, glog, dev, key_nulla
     slot_keys = torch.arange(kmin, kmin + nslots, dtype=torch.int64, device=dev)
     if not key_nullable and gexpr.dtype == I64:
         # the key column has no NULLs, so the NULL slot stays empty: no validity work, no host sync
-        if t.rows is not None:
-            occ = DeviceColumn(t.rows, None, I64)
-            scan = D.make_scan([occ], [TermSpec(0, L.GT, 0)], nslots)
-        else:
-            occ = DeviceColumn(slot_keys, t.present, I64)
-            scan = D.make_scan([occ], [TermSpec(0, L.IS_NOT_NULL, 0)], nslots)
+        occ, term = _occupancy(t, slot_keys)
         # compaction and gathers in one write pass: keys and every accumulator array ride along as
         # gather columns of b2_select_write (<= 8), instead of one b2_gather launch each
         cols = [occ, DeviceColumn(slot_keys, None, I64)]
@@ -826,7 +976,7 @@ def _extract_dense(gs: GroupState, kmin, rng, gname, gexpr, glog, dev, key_nulla
         if t.rows is not None:
             where[("r", 0)] = 0
         if len(cols) - 1 <= L.MAX_GATHER:
-            scan = D.make_scan(cols, [TermSpec(0, L.GT if t.rows is not None else L.IS_NOT_NULL, 0)], nslots)
+            scan = D.make_scan(cols, [term], nslots)
             gcols = list(range(1, len(cols))) if t.rows is None else list(range(0, len(cols)))
             gcols = gcols[: L.MAX_GATHER] if len(gcols) <= L.MAX_GATHER else None
         else:
@@ -841,18 +991,15 @@ def _extract_dense(gs: GroupState, kmin, rng, gname, gexpr, glog, dev, key_nulla
             rows_col = got.get(0) if t.rows is not None else None
             return RawGroups({gname: kcol}, acc_cols, cnt_cols, rows_col, total)
         stats["launches"] += 4
+        scan = D.make_scan([occ], [term], nslots)
         idx, _, total = D.select(scan, dev, (), want_idx=True, cols=[occ])
         kcol = D.gather(DeviceColumn(slot_keys, None, I64, glog), idx, False)
         kcol = DeviceColumn(kcol.data, None, I64, glog)
         acc_cols, cnt_cols, rows_col = _gather_state(gs, idx, dev)
         return RawGroups({gname: kcol}, acc_cols, cnt_cols, rows_col, total)
     # occupied slots
-    if t.rows is not None:
-        occ = DeviceColumn(t.rows, None, I64)
-        scan = D.make_scan([occ], [TermSpec(0, L.GT, 0)], nslots)
-    else:
-        occ = DeviceColumn(slot_keys, t.present, I64)
-        scan = D.make_scan([occ], [TermSpec(0, L.IS_NOT_NULL, 0)], nslots)
+    occ, term = _occupancy(t, slot_keys)
+    scan = D.make_scan([occ], [term], nslots)
     stats["launches"] += 3
     idx, _, total = D.select(scan, dev, (), want_idx=True, cols=[occ])
     # key column: the last slot is the NULL group
@@ -918,12 +1065,8 @@ def _finalize_hashk(gs, tkeys, tnulls, cap, gnames, gexprs, glogs, plan, dev) ->
 
 def _extract_hashk(gs, tkeys, tnulls, cap, gnames, gexprs, glogs, dev) -> RawGroups:
     t = gs.table
-    if t.rows is not None:
-        occ = DeviceColumn(t.rows, None, I64)
-        scan = D.make_scan([occ], [TermSpec(0, L.GT, 0)], cap)
-    else:
-        occ = DeviceColumn(tkeys[:cap], t.present, I64)
-        scan = D.make_scan([occ], [TermSpec(0, L.IS_NOT_NULL, 0)], cap)
+    occ, term = _occupancy(t, tkeys[:cap])
+    scan = D.make_scan([occ], [term], cap)
     stats["launches"] += 3
     idx, _, total = D.select(scan, dev, (), want_idx=True, cols=[occ])
     stats["launches"] += 1
@@ -990,7 +1133,13 @@ def _star_dense_fast(src, fact, dim, fk_e, pk_e, gexprs, aggs, fact_pred, dim_pr
         gnull = any(p[ge.name].valid is not None for p in table.partitions)
         meta = (pst.vmin, pst.vmax, gst.vmin, gst.vmax, table.nrows, gnull)
     if world > 1 and dist == "root":
-        meta = P.broadcast_object(meta, 0)
+        # key ranges of the root-only table: one object broadcast per (table, columns), then cached on
+        # the (immutable) table object of every rank -- a blocking host round trip per query otherwise
+        cache = table.__dict__.setdefault("_root_meta", {})
+        ck = (pk_e.name, ge.name)
+        if ck not in cache:
+            cache[ck] = P.broadcast_object(meta, 0)
+        meta = cache[ck]
     pmin, pmax, gmin, gmax, dn, gnull = meta
     if pmin is None or gmin is None or dn == 0:
         return None
@@ -1004,8 +1153,10 @@ def _star_dense_fast(src, fact, dim, fk_e, pk_e, gexprs, aggs, fact_pred, dim_pr
     if never or fnever:
         return None
     nslots = grng + 1
-    lookup = torch.full((prange,), -1, dtype=torch.int32, device=dev)
-    flags = D.new_flags(dev)
+    # lookup and the 4 flag words share one buffer: one broadcast carries both
+    buf = torch.full((prange + 4,), -1, dtype=torch.int32, device=dev)
+    lookup, flags = buf[:prange], buf[prange:]
+    flags.zero_()
     if owner:
         needed: Set[str] = {pk_e.name, ge.name}
         for p in dpred:
@@ -1020,8 +1171,7 @@ def _star_dense_fast(src, fact, dim, fk_e, pk_e, gexprs, aggs, fact_pred, dim_pr
                               D.ptr(lookup), D.ptr(flags), D.stream_ptr())
     if world > 1 and dist == "root":
         # the build side crosses NVLink as the finished 4-byte-per-key lookup, not as its columns
-        P.broadcast_(lookup, 0)
-        P.broadcast_(flags, 0)
+        P.broadcast_(buf, 0)
     plan = AggPlan([(E.substitute(e, fact.exprs) if e is not None else None, o, f) for e, o, f in aggs],
                    _nullable_fn(fact))
     gs = GroupState(dev, nslots, plan, need_present=True)
@@ -1046,15 +1196,18 @@ def _star_dense_fast(src, fact, dim, fk_e, pk_e, gexprs, aggs, fact_pred, dim_pr
     if sharded:
         _allreduce_table(gs.table, plan)
     glog = dim.col_type(gexprs[0].name)[1] if isinstance(gexprs[0], ColRef) else "int64"
-    out = _finalize_dense(gs, gmin, grng, src.group_cols[0], gexprs[0], glog, plan, dev, key_nullable=gnull)
-    # the duplicate-key check rides on the sync the compaction needed anyway
-    if int(flags[0].item()):
-        return None
     stats["star_fused"] += 1
-    return out
+
+    def general():   # a duplicate build key showed up: the general path redoes the query
+        stats["star_fused"] -= 1
+        return run_aggregate(src, allow_fast=False)
+
+    # the duplicate-key flags ride on the (deferred) host copy of the group count
+    return _finalize_dense(gs, gmin, grng, src.group_cols[0], gexprs[0], glog, plan, dev, key_nullable=gnull,
+                           check=flags, fallback=general)
 
 
-def try_star(src: AggSource, child: LazyFrame, gexprs, aggs, pred, sharded) -> Optional[Part]:
+def try_star(src: AggSource, child: LazyFrame, gexprs, aggs, pred, sharded, allow_fast=True) -> Optional[Part]:
     js: JoinSource = child.source
     if js.how != "inner" or len(js.left_on) != 1:
         return None
@@ -1089,7 +1242,8 @@ def try_star(src: AggSource, child: LazyFrame, gexprs, aggs, pred, sharded) -> O
 
     # ---- fast path: dense join key and dense group key straight from a registered table: the
     # whole build side is one kernel per dim partition (filter -> slot -> lookup), no host sync
-    fast = _star_dense_fast(src, fact, dim, fk_e, pk_e, gexprs, aggs, fact_pred, dim_pred, sharded, dev)
+    fast = _star_dense_fast(src, fact, dim, fk_e, pk_e, gexprs, aggs, fact_pred, dim_pred, sharded, dev) \
+        if allow_fast else None
     if fast is not None:
         return fast
 
@@ -1260,6 +1414,15 @@ def run_join(js: JoinSource, needed: Set[str]) -> List[Part]:
     stats["launches"] += 1
     stats["dense_join" if jt.dense else "chain_join"] += 1
     build_matched = torch.zeros(max(bpart.n, 1), dtype=torch.uint8, device=dev) if how == "outer" else None
+    prefs = sorted({r for n in probe_out for r in probe.exprs[n].refs()})
+    fused_gather = len(prefs) <= L.MAX_GATHER and len(build_out) <= L.MAX_GATHER
+    if jt.dense and fused_gather and how != "outer" and estimated_rows(probe) >= bpart.n \
+            and os.environ.get("B200SQL_NO_KEY_LAYOUT") != "1":
+        # unique dense keys probed by at least as many rows as were built: one pass over the build
+        # columns puts them in key order, every probe row then saves a random access
+        stats["launches"] += max(1, len(build_out))
+        stats["keyed_join"] += 1
+        jt.key_layout([bpart[n] for n in build_out])
 
     # ---- probe side, partition by partition
     ppred, never = simplify_pred(probe.pred)
@@ -1277,8 +1440,30 @@ def run_join(js: JoinSource, needed: Set[str]) -> List[Part]:
             continue
         ctx = ScanCtx(part, ppred)
         kslots = [ctx.slot(e) for e in pk_exprs]
-        refs = sorted({r for n in probe_out for r in probe.exprs[n].refs()})
-        if len(refs) <= L.MAX_GATHER and len(build_out) <= L.MAX_GATHER:
+        refs = prefs
+        if fused_gather and jt.dense and build_matched is None and os.environ.get("B200SQL_NO_ONEPASS") != "1":
+            # direct-address table: single-pass probe (look-back offsets), row count left on the device
+            rslots = [ctx.slot(ColRef(r, part[r].dtype)) for r in refs]
+            stats["launches"] += 1
+            trim, count = D.join_probe_onepass(ctx.scan(), kslots, jt, mode, dev, ctx.cols, rslots,
+                                               [bpart[n] for n in build_out], mode == L.JOIN_LEFT)
+            pending = DeviceCount(count)
+
+            def finish_part(trim=trim, pending=pending, keep=(ctx, jt, bpart)):
+                total = int(pending.get()[0])
+                pres, bres = trim(total)
+                g = Part(dict(zip(refs, pres)), total)
+                res = Part({}, total)
+                for n, col in zip(build_out, bres):
+                    res[n] = col
+                for n in probe_out:
+                    e = probe.exprs[n]
+                    res[n] = const_column(e.value, e.dtype, total, dev) if isinstance(e, Lit) else eval_expr(g, e)
+                return res
+
+            outs.append(PendingPart(finish_part))
+            continue
+        if fused_gather:
             # probe + gather of both sides' columns in one pass (b2_join_write_gather)
             rslots = [ctx.slot(ColRef(r, part[r].dtype)) for r in refs]
             stats["launches"] += 3
@@ -1356,7 +1541,7 @@ def compute_frame(frame: LazyFrame):
 
 def persist_frame(frame: LazyFrame) -> LazyFrame:
     parts = execute(frame)
-    table = DeviceTable([dict(p) for p in parts], frame_distribution(frame))
+    table = DeviceTable([dict(p.resolve()) for p in parts], frame_distribution(frame))
     return LazyFrame(TableSource(table))
 
 

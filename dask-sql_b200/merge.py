@@ -118,7 +118,7 @@ def merge_partials(parts: List, plan, nkeys: int):
 
     names = list(parts[0].keys())
     whole = concat_parts(parts, names)
-    table = DeviceTable([dict(whole)], "local")
+    table = DeviceTable([dict(whole.resolve())], "local")
     frame = LazyFrame(TableSource(table))
     aggs = []
     for n in names:

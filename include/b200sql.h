@@ -37,6 +37,8 @@ extern "C" {
 #define B2_I64 0   /* int64  (BIGINT and narrower ints, widened at ingest) */
 #define B2_F64 1   /* float64 (DOUBLE) */
 #define B2_U8  2   /* boolean, one byte per row (0/1) */
+#define B2_U32 3   /* storage only: uint32 offsets from a base, for key-ordered join payloads
+                    * (b2_join_key_layout / b2_join_write_gather_keyed); never a column type */
 
 #define B2_MAX_COLS   16
 #define B2_MAX_TERMS   8
@@ -272,7 +274,9 @@ int32_t b2_join_build_dense(const b2_col_t* key, int64_t n, int64_t kmin, int64_
 typedef struct b2_jointable {
   b2_col_t  keys[B2_MAX_KEYS];  /* build-side key columns */
   int32_t   nkeys;
-  int32_t   dense;              /* 0 = chained (head/next/cap), 1 = direct (lookup/kmin/range) */
+  int32_t   dense;              /* 0 = chained (head/next/cap), 1 = direct (lookup/kmin/range),
+                                 * 2 = key-ordered: lookup is the presence BITMAP (uint32 words,
+                                 *     range bits) and the build row of a match is key-kmin */
   const int32_t* head;
   const int32_t* next;
   int64_t   cap;
@@ -304,6 +308,43 @@ int32_t b2_join_write_gather(const b2_scan_t* scan, const int32_t* probe_keys, c
                              const int32_t* probe_cols, void* const* probe_out, uint32_t* const* probe_valid,
                              int32_t nbuild, const b2_col_t* build_cols, void* const* build_out,
                              uint32_t* const* build_valid, void* stream);
+
+/* Key-ordered layout for a unique dense-key build side (the broadcast dimension of C3): the probe's
+ * "take" on a build column (join.py:241-246) then costs ONE random access at the key offset instead
+ * of lookup[key] -> row -> col[row], and int64 payloads whose value range fits 32 bits are stored as
+ * uint32 offsets so the whole payload array stays L2-resident.
+ *   out_data[key[i]-kmin] = col[i]           out_dtype == col->dtype  (8 or 1 bytes per key)
+ *   out_data[key[i]-kmin] = col[i] - base    out_dtype == B2_U32      (col int64, 4 bytes per key)
+ * out_valid (may be NULL): validity words in key order, zero-initialised by the caller.
+ * present (may be NULL): bit key-kmin is set for every build row; it is the `lookup` of a
+ * b2_jointable_t with dense == 2.  col may be NULL to produce only `present`.  Rows with a NULL key
+ * or a key outside [kmin, kmin+range) are skipped.  Unique keys are the caller's responsibility
+ * (b2_join_build_dense reports duplicates). */
+int32_t b2_join_key_layout(const b2_col_t* key, int64_t n, int64_t kmin, int64_t range, const b2_col_t* col,
+                           int32_t out_dtype, int64_t base, void* out_data, uint32_t* out_valid,
+                           uint32_t* present, void* stream);
+/* b2_join_write_gather for build columns in key order: build_cols[k].dtype may be B2_U32 with
+ * build_base[k] the base of the offsets (build_base may be NULL when no column is narrowed). */
+int32_t b2_join_write_gather_keyed(const b2_scan_t* scan, const int32_t* probe_keys, const b2_jointable_t* jt,
+                                   int32_t mode, const int64_t* d_tile_off, int32_t* out_probe_idx,
+                                   int32_t* out_build_idx, uint8_t* build_matched, int32_t nprobe,
+                                   const int32_t* probe_cols, void* const* probe_out,
+                                   uint32_t* const* probe_valid, int32_t nbuild, const b2_col_t* build_cols,
+                                   const int64_t* build_base, void* const* build_out,
+                                   uint32_t* const* build_valid, void* stream);
+
+/* Single-pass probe of a direct-address table (jt->dense 1 or 2; every probe row emits at most one
+ * output row in all four modes): no counting kernel, no host round trip.  Each 4096-row tile learns
+ * its output offset by a decoupled look-back over d_status (uint64[b2_num_tiles(n)], zeroed by the
+ * caller); outputs are caller-allocated at their upper bound (scan.n rows) and filled in probe-row
+ * order; *d_total (device int64, zeroed by the caller) receives the number of rows emitted.
+ * Gather arguments as for b2_join_write_gather_keyed.  Per probe row this reads the key and the
+ * gathered probe columns once and writes the output once: the algorithmic traffic of the join. */
+int32_t b2_join_onepass(const b2_scan_t* scan, const int32_t* probe_keys, const b2_jointable_t* jt, int32_t mode,
+                        uint64_t* d_status, int64_t* d_total, int32_t nprobe, const int32_t* probe_cols,
+                        void* const* probe_out, uint32_t* const* probe_valid, int32_t nbuild,
+                        const b2_col_t* build_cols, const int64_t* build_base, void* const* build_out,
+                        uint32_t* const* build_valid, void* stream);
 
 /* ---- ORDER BY ("next" row of the scope: the tail of TPC-H Q3) ------------------------------- */
 /* Stable LSD radix sort of row ids by one key column.  idx = int32[n] permutation (b2_iota for the

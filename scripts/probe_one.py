@@ -1,4 +1,4 @@
-"""Run one BASELINE config repeatedly (for launch lists / event timing).  usage: probe_one.py c1|c2|c4 rows reps"""
+"""Run one BASELINE config repeatedly (for launch lists / event timing).  usage: probe_one.py c1|c2|c2i|c3|c4 rows reps [nparts]"""
 import sys, os, time, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -18,6 +18,17 @@ elif cfg == "c2":
     t = table({"key": torch.randint(0, 1_000_000, (n,), dtype=torch.int64, device=dev, generator=g),
                "vf": torch.rand(n, dtype=torch.float64, device=dev, generator=g)}, nparts)
     q = LazyFrame(AggSource(t, ["key"], [("vf", "s", "sum")])); bpr = 16
+elif cfg == "c2i":
+    t = table({"key": torch.randint(0, 1_000_000, (n,), dtype=torch.int64, device=dev, generator=g),
+               "vi": torch.randint(-1000, 1001, (n,), dtype=torch.int64, device=dev, generator=g)}, nparts)
+    q = LazyFrame(AggSource(t, ["key"], [("vi", "s", "sum")])); bpr = 16
+elif cfg == "c3":
+    nd = 10_000_000
+    f = table({"fk": torch.randint(0, int(nd * 1.25), (n,), dtype=torch.int64, device=dev, generator=g),
+               "v": torch.rand(n, dtype=torch.float64, device=dev, generator=g)}, nparts)
+    d = table({"pk": torch.randperm(nd, device=dev, generator=g),
+               "w": torch.randint(0, 1000, (nd,), dtype=torch.int64, device=dev, generator=g)}, 1)
+    q = f.merge(d, left_on=["fk"], right_on=["pk"], how="inner")[["fk", "v", "w"]]; bpr = 35.4
 else:
     nd = 10_000_000
     f = table({"fk": torch.randint(0, nd, (n,), dtype=torch.int64, device=dev, generator=g),

@@ -293,3 +293,119 @@ def test_host_resident_table_streams_per_query():
     got = agg(_table(df, 4, persist=False), ["key"], [("val", "s", "sum")])
     exp = df.groupby("key").agg(s=("val", "sum")).reset_index()
     assert_frames(got, exp, float_cols=("s",), sort_by=["key"])
+
+
+def test_float_sum_accumulator_doubles_as_group_flag():
+    """Dense group-by over a NULL-free float column keeps no presence bitmap: the SUM accumulator
+    starts at -0.0 and an untouched slot is an absent group.  Groups whose values are all -0.0 /
+    +0.0 / cancel to 0 must still exist (pandas: running sum from +0.0 -> +0.0), absent keys must not."""
+    from dask_sql_b200 import executor
+    key = np.array([0, 0, 2, 2, 5, 5, 7, 9, 9, 9], dtype=np.int64)          # 1,3,4,6,8 absent
+    val = np.array([-0.0, -0.0, 0.0, -0.0, 1.5, -1.5, -0.0, 1e-300, -1e-300, 0.0])
+    df = pd.DataFrame({"key": key, "val": val})
+    before = executor.stats["dense_groupby"]
+    got = agg(_table(df, 2), ["key"], [("val", "s", "sum")])
+    assert executor.stats["dense_groupby"] == before + 1
+    exp = df.groupby("key").agg(s=("val", "sum")).reset_index()
+    assert_frames(got, exp, float_cols=("s",), sort_by=["key"])
+    g = _sorted(got, ["key"])
+    assert not np.signbit(g["s"].to_numpy()).any(), "sum of zeros must be +0.0 like pandas"
+
+
+@pytest.mark.parametrize("env", ["B200SQL_NO_INDICATOR", "B200SQL_NO_DEFER"])
+def test_dense_groupby_same_result_without_shortcuts(env, monkeypatch):
+    rng = np.random.default_rng(21)
+    n = 200_000
+    df = pd.DataFrame({"key": rng.integers(0, 5000, n) * 2, "val": rng.random(n), "w": rng.integers(-9, 9, n)})
+    spec = [("val", "s", "sum"), ("w", "sw", "sum"), ("val", "mx", "max")]
+    a = agg(_table(df, 4), ["key"], spec)
+    monkeypatch.setenv(env, "1")
+    b = agg(_table(df, 4), ["key"], spec)
+    assert_frames(a, b, float_cols=("s",), sort_by=["key"])     # float atomics: order varies run to run
+    exp = df.groupby("key").agg(s=("val", "sum"), sw=("w", "sum"), mx=("val", "max")).reset_index()
+    assert_frames(a, exp, float_cols=("s",), sort_by=["key"])
+
+
+def test_dense_result_is_pending_until_used():
+    """The compaction of a dense group table is enqueued without waiting for its row count."""
+    from dask_sql_b200 import executor
+    from dask_sql_b200.frame import AggSource, LazyFrame
+    rng = np.random.default_rng(22)
+    n = 100_000
+    df = pd.DataFrame({"key": rng.integers(0, 1000, n), "val": rng.random(n)})
+    frame = LazyFrame(AggSource(_table(df, 2), ["key"], [("val", "s", "sum")]))
+    parts = executor.execute(frame)
+    assert isinstance(parts[0], executor.PendingPart) and not parts[0].resolved
+    assert parts[0].n == df["key"].nunique() and parts[0].resolved
+    assert set(parts[0].keys()) == {"key", "s"} and parts[0]["s"].n == parts[0].n
+    exp = df.groupby("key").agg(s=("val", "sum")).reset_index()
+    assert_frames(frame.compute(), exp, float_cols=("s",), sort_by=["key"])
+    # an empty selection resolves to an empty partition
+    f = _table(df, 2)
+    empty = LazyFrame(AggSource(f[f["val"] > 2.0], ["key"], [("val", "s", "sum")])).compute()
+    assert len(empty) == 0 and list(empty.columns) == ["key", "s"]
+
+
+@pytest.mark.parametrize("how", ["inner", "left", "leftsemi", "leftanti"])
+def test_join_key_ordered_payload_layout(how, monkeypatch):
+    """Unique dense build keys: build columns are re-laid in key order (narrow uint32 offsets for
+    small-range ints, 8 bytes otherwise, bool, nullable) and probed by key offset."""
+    from dask_sql_b200 import executor
+    rng = np.random.default_rng(31)
+    nd, nf = 20_000, 150_003
+    pk = rng.permutation(nd * 2)[:nd].astype(np.int64) - 777           # unique, with holes, negative kmin
+    dim = pd.DataFrame({
+        "pk": pk,
+        "w": rng.integers(-500, 500, nd),                                # narrow int
+        "big": rng.integers(-2**62, 2**62, nd),                          # wide int stays 8 bytes
+        "f": rng.random(nd),
+        "b": rng.integers(0, 2, nd).astype(bool),
+        "ni": pd.array(np.where(rng.random(nd) < 0.2, None, rng.integers(0, 9, nd)), dtype="Int64"),
+    })
+    fk = rng.integers(-2000, nd * 2 + 500, nf).astype(np.int64)         # some outside [kmin, kmax], some in holes
+    fact = pd.DataFrame({"fk": pd.array(np.where(rng.random(nf) < 0.05, None, fk), dtype="Int64"),
+                         "v": rng.random(nf)})
+    f, d = _table(fact, 3), _table(dim)
+    before = executor.stats["keyed_join"]
+    got = f.merge(d, left_on=["fk"], right_on=["pk"], how=how).compute()
+    assert executor.stats["keyed_join"] == before + 1
+    monkeypatch.setenv("B200SQL_NO_KEY_LAYOUT", "1")
+    plain = f.merge(d, left_on=["fk"], right_on=["pk"], how=how).compute()
+    assert executor.stats["keyed_join"] == before + 1
+    pd.testing.assert_frame_equal(got, plain)                            # same rows, same order, same dtypes
+    from oracle import pandas_oracle as O
+    exp = O.join_on_columns(fact, dim, ["fk"], ["pk"], how)
+    assert_frames(got[list(exp.columns)], exp, sort_by=["fk", "v"])
+
+
+@pytest.mark.parametrize("how", ["inner", "left", "leftsemi", "leftanti"])
+@pytest.mark.parametrize("match", [0.0, 0.03, 0.8, 1.0])
+def test_join_single_pass_lookback_equals_two_pass(how, match, monkeypatch):
+    """b2_join_onepass (tile offsets by decoupled look-back, count left on the device) must emit
+    exactly the rows, in exactly the order, of the count + write protocol -- across many tiles,
+    with tiles that emit nothing and with a pushed-down probe filter."""
+    from dask_sql_b200 import executor
+    rng = np.random.default_rng(int(match * 100) + 41)
+    nd, nf = 50_000, 3_000_017
+    dim = pd.DataFrame({"pk": rng.permutation(nd).astype(np.int64), "w": rng.integers(0, 1000, nd), "g": rng.random(nd)})
+    hit = rng.random(nf) < match
+    fk = np.where(hit, rng.integers(0, nd, nf), rng.integers(nd, 2 * nd, nf)).astype(np.int64)
+    fk[1_000_000:1_300_000] = nd + 7                                   # a long run of tiles without matches
+    fact = pd.DataFrame({"fk": fk, "v": rng.random(nf), "x": rng.integers(-5, 5, nf)})
+    f, d = _table(fact, 3), _table(dim)
+
+    def run():
+        j = f[f["x"] > -3].merge(d, left_on=["fk"], right_on=["pk"], how=how)
+        parts = executor.execute(j)
+        return parts, j.compute()
+
+    parts, got = run()
+    assert all(isinstance(p, executor.PendingPart) for p in parts)
+    monkeypatch.setenv("B200SQL_NO_ONEPASS", "1")
+    parts2, two_pass = run()
+    assert not any(isinstance(p, executor.PendingPart) for p in parts2)
+    pd.testing.assert_frame_equal(got, two_pass)
+    from oracle import pandas_oracle as O
+    exp = O.join_on_columns(fact[fact["x"] > -3], dim, ["fk"], ["pk"], how)
+    assert len(got) == len(exp)
+    assert_frames(got[list(exp.columns)], exp, sort_by=["fk", "v"])
