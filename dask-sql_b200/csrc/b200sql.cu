@@ -4,6 +4,7 @@
 #include <limits.h>
 #include <string.h>
 
+#include <cstdlib>
 thread_local char g_b2_err[512] = {0};
 
 static int g_sm_count_cache[64] = {0};
@@ -15,6 +16,17 @@ int b2_sm_count() {
     int n = 0;
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
     g_sm_count_cache[dev] = n;
+    // First use of this device: optionally set aside part of L2 for evict_last ("persisting") lines --
+    // the lookup / payload / group tables the kernels mark with b2_policy_keep().  B200SQL_L2_PERSIST_MB
+    // (default 0 = leave the driver default) is clamped to the device maximum.
+    const char* e = getenv("B200SQL_L2_PERSIST_MB");
+    if (e && atoi(e) > 0) {
+      int maxb = 0;
+      cudaDeviceGetAttribute(&maxb, cudaDevAttrMaxPersistingL2CacheSize, dev);
+      size_t want = (size_t)atoi(e) << 20;
+      if (maxb > 0 && want > (size_t)maxb) want = (size_t)maxb;
+      if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) != cudaSuccess) cudaGetLastError();
+    }
   }
   return g_sm_count_cache[dev];
 }

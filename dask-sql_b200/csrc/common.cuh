@@ -144,6 +144,11 @@ __device__ __forceinline__ int32_t b2_ld_keep_i32(const int32_t* p) {
   asm("ld.global.nc.L2::cache_hint.b32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(b2_policy_keep()));
   return v;
 }
+// streaming stores: result columns are written once and not read again by the kernel, so they must
+// not push the randomly accessed tables (evict_last) out of L2
+__device__ __forceinline__ void b2_st_stream(int64_t* p, int64_t v) {
+  asm volatile("st.global.L2::cache_hint.b64 [%0], %1, %2;" ::"l"(p), "l"(v), "l"(b2_policy_stream()) : "memory");
+}
 __device__ __forceinline__ int64_t b2_ld_keep_i64(const int64_t* p) {
   int64_t v;
   asm("ld.global.nc.L2::cache_hint.b64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(b2_policy_keep()));

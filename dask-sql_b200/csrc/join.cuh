@@ -254,12 +254,8 @@ b2_join_write_kernel(const __grid_constant__ b2_scan_t s, const __grid_constant_
                      const __grid_constant__ b2_jointable_t jt, int mode, int64_t ntiles,
                      const int64_t* __restrict__ tile_off, int32_t* __restrict__ out_probe,
                      int32_t* __restrict__ out_build, uint8_t* __restrict__ build_matched,
-                     const __grid_constant__ b2_joingather_arg g, uint64_t* __restrict__ lb_status,
-                     int64_t* __restrict__ lb_total) {
-  // lb_status != NULL (direct-address tables only): single pass, the tile's output offset comes from
-  // a decoupled look-back over the tiles' own counts instead of a separate counting kernel
+                     const __grid_constant__ b2_joingather_arg g) {
   __shared__ int64_t sh[B2_WARPS];
-  __shared__ int64_t sh_excl;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t lt_mask = (1u << lane) - 1;
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -277,22 +273,7 @@ b2_join_write_kernel(const __grid_constant__ b2_scan_t s, const __grid_constant_
       }
       if (lane == 0) sh[warp] = wtotal;
       __syncthreads();
-      int64_t off;
-      if (lb_status) {
-        if (warp == 0) {
-          int64_t agg = 0;
-          for (int w = 0; w < B2_WARPS; ++w) agg += sh[w];
-          const int64_t ex = b2_lookback(lb_status, tile, agg, lane);
-          if (lane == 0) {
-            sh_excl = ex;
-            if (tile == ntiles - 1) *lb_total = ex + agg;
-          }
-        }
-        __syncthreads();
-        off = sh_excl;
-      } else {
-        off = tile_off[tile];
-      }
+      int64_t off = tile_off[tile];
       for (int w = 0; w < warp; ++w) off += sh[w];
       __syncthreads();
       // output position = off + rel[j]; rel is 32-bit (a tile emits <= 4096 rows) to save registers
@@ -444,6 +425,256 @@ b2_join_write_kernel(const __grid_constant__ b2_scan_t s, const __grid_constant_
   }
 }
 
+// ---- single-pass probe of a direct-address table ------------------------------------------------
+// Every probe row emits at most one output row, so one kernel can do the whole join: each 2048-row
+// tile counts its emitting rows, learns its output offset by a decoupled look-back over the tiles
+// before it (b2_lookback) and writes.  The loads are front-loaded so that a tile costs two
+// dependent memory round trips instead of one per gathered column:
+//   trip 1: probe key, predicate columns and the first other 8-byte probe column (streaming)
+//   trip 2: presence word and -- on a key-ordered table (dense == 2) -- the first build column's
+//           payload at the key offset, fetched speculatively together with the presence word
+// Remaining columns (rare: more than two per side) are gathered after the offsets are known.
+#define B2_JOP_R 8
+#define B2_JOP_TILE (B2_BLOCK * B2_JOP_R)
+
+#ifndef B2_JOP_MINB
+#define B2_JOP_MINB 2
+#endif
+__global__ void __launch_bounds__(B2_BLOCK, B2_JOP_MINB)
+b2_join_onepass_kernel(const __grid_constant__ b2_scan_t s, int key_col, const __grid_constant__ b2_jointable_t jt,
+                       int mode, int64_t ntiles, uint64_t* __restrict__ status, const int64_t* __restrict__ tile_off,
+                       const uint32_t* __restrict__ match_mask, int64_t* __restrict__ total,
+                       const __grid_constant__ b2_joingather_arg g) {
+  // tile_off != NULL: offsets were counted by b2_join_count8_kernel + scan (three launches, still no
+  // host round trip); tile_off == NULL: decoupled look-back over `status` (one launch)
+  constexpr int R = B2_JOP_R;
+  __shared__ int64_t sh[B2_WARPS];
+  __shared__ int64_t sh_excl;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t lt_mask = (1u << lane) - 1;
+  const b2_col_t& kc = s.cols[key_col];
+  int preA = -1;   // probe gather column held in registers from trip 1
+  for (int k = 0; k < g.nprobe; ++k) {
+    if (g.probe_cols[k] != key_col && s.cols[g.probe_cols[k]].dtype != B2_U8) { preA = k; break; }
+  }
+  const bool spec = jt.dense == 2 && g.nbuild > 0 && g.build_cols[0].dtype != B2_U8;
+  const bool spec32 = spec && g.build_cols[0].dtype == B2_U32;
+  const uint64_t range = (uint64_t)jt.range;
+
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t row0 = tile * B2_JOP_TILE + (int64_t)warp * (32 * R) + lane;
+    bool full;
+    uint32_t bits, known = 0;
+    if (match_mask) {
+      // counted mode: which rows found a build row is already known; an INNER / SEMI probe then
+      // touches only the rows it emits (no predicate columns, no loads for the others)
+      const uint32_t* mw = match_mask + ((row0 - lane) >> 5);
+#pragma unroll
+      for (int j = 0; j < R; ++j)
+        if (row0 - lane + (int64_t)j * 32 < s.n) known |= ((__ldg(mw + j) >> lane) & 1u) << j;
+      if (mode == B2_JOIN_INNER || mode == B2_JOIN_SEMI) { bits = known; full = false; }
+      else bits = b2_eval_terms<R>(s, row0, full);
+    } else {
+      bits = b2_eval_terms<R>(s, row0, full);
+    }
+    int64_t key[R], pre[R];
+    b2_load_batch<R>(kc, row0, bits, full, key);
+    if (preA >= 0) b2_load_batch64<R>(s.cols[g.probe_cols[preA]].data, row0, bits, full, pre);
+    uint32_t live = bits;
+    if (kc.valid) live &= b2_valid_bits<R>(kc.valid, row0, bits);
+
+    int32_t brow[R];
+    int64_t pay[R];
+    if (match_mask) {
+#pragma unroll
+      for (int j = 0; j < R; ++j) {
+        const uint64_t d = (uint64_t)key[j] - (uint64_t)jt.kmin;
+        const bool ok = (known >> j) & 1;
+        brow[j] = !ok ? -1 : (jt.dense == 2 ? (int32_t)d : b2_ld_keep_i32(jt.lookup + d));
+        pay[j] = 0;
+        if (spec && ok) {
+          pay[j] = spec32 ? (int64_t)(uint32_t)b2_ld_keep_i32(reinterpret_cast<const int32_t*>(g.build_cols[0].data) + d)
+                          : b2_ld_keep_i64(reinterpret_cast<const int64_t*>(g.build_cols[0].data) + d);
+        }
+      }
+    } else if (jt.dense == 2) {
+      uint32_t word[R];
+#pragma unroll
+      for (int j = 0; j < R; ++j) {
+        const uint64_t d = (uint64_t)key[j] - (uint64_t)jt.kmin;
+        const bool ok = ((live >> j) & 1) && d < range;
+        word[j] = ok ? (uint32_t)b2_ld_keep_i32(jt.lookup + (d >> 5)) : 0u;
+        pay[j] = 0;
+        if (spec && ok) {
+          pay[j] = spec32 ? (int64_t)(uint32_t)b2_ld_keep_i32(reinterpret_cast<const int32_t*>(g.build_cols[0].data) + d)
+                          : b2_ld_keep_i64(reinterpret_cast<const int64_t*>(g.build_cols[0].data) + d);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < R; ++j) {
+        const uint64_t d = (uint64_t)key[j] - (uint64_t)jt.kmin;
+        brow[j] = ((word[j] >> (d & 31)) & 1) ? (int32_t)d : -1;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < R; ++j) {
+        const uint64_t d = (uint64_t)key[j] - (uint64_t)jt.kmin;
+        brow[j] = (((live >> j) & 1) && d < range) ? b2_ld_keep_i32(jt.lookup + d) : -1;
+      }
+    }
+    uint32_t matched = 0;
+#pragma unroll
+    for (int j = 0; j < R; ++j) matched |= (uint32_t)(brow[j] >= 0) << j;
+    uint32_t emit;
+    switch (mode) {
+      case B2_JOIN_INNER:
+      case B2_JOIN_SEMI: emit = matched; break;
+      case B2_JOIN_LEFT: emit = bits; break;
+      default: emit = bits & ~matched; break;  // ANTI
+    }
+
+    // ---- positions: ballot ranks inside the warp, warps inside the tile, tiles by look-back
+    int32_t rel[R];
+    int wtotal = 0;
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      const uint32_t b = __ballot_sync(FULL_MASK, (emit >> j) & 1);
+      rel[j] = ((emit >> j) & 1) ? wtotal + __popc(b & lt_mask) : -1;
+      wtotal += __popc(b);
+    }
+    int64_t off;
+    if (tile_off) {
+      // counted mode: warp-granular offsets, no barrier -- warps of a block drift freely
+      off = __ldg(tile_off + tile * B2_WARPS + warp);
+      if (tile == ntiles - 1 && threadIdx.x == 0) *total = tile_off[ntiles * B2_WARPS];
+    } else {
+      if (lane == 0) sh[warp] = wtotal;
+      __syncthreads();
+      if (warp == 0) {
+        int64_t agg = 0;
+#pragma unroll
+        for (int w = 0; w < B2_WARPS; ++w) agg += sh[w];
+        const int64_t ex = b2_lookback(status, tile, agg, lane);
+        if (lane == 0) {
+          sh_excl = ex;
+          if (tile == ntiles - 1) *total = ex + agg;
+        }
+      }
+      __syncthreads();
+      off = sh_excl;
+      for (int w = 0; w < warp; ++w) off += sh[w];
+      __syncthreads();
+    }
+
+    // ---- probe-side columns
+    for (int k = 0; k < g.nprobe; ++k) {
+      const b2_col_t& c = s.cols[g.probe_cols[k]];
+      if (c.dtype == B2_U8) {
+        const uint8_t* p = reinterpret_cast<const uint8_t*>(c.data) + row0;
+        uint8_t raw[R];
+#pragma unroll
+        for (int j = 0; j < R; ++j) raw[j] = rel[j] >= 0 ? p[j * 32] : 0;
+#pragma unroll
+        for (int j = 0; j < R; ++j)
+          if (rel[j] >= 0) reinterpret_cast<uint8_t*>(g.probe_out[k])[off + rel[j]] = raw[j];
+      } else {
+        int64_t* out = reinterpret_cast<int64_t*>(g.probe_out[k]);
+        if (g.probe_cols[k] == key_col) {
+#pragma unroll
+          for (int j = 0; j < R; ++j)
+            if (rel[j] >= 0) b2_st_stream(out + off + rel[j], key[j]);
+        } else if (k == preA) {
+#pragma unroll
+          for (int j = 0; j < R; ++j)
+            if (rel[j] >= 0) b2_st_stream(out + off + rel[j], pre[j]);
+        } else {
+          const int64_t* p = reinterpret_cast<const int64_t*>(c.data) + row0;
+          int64_t raw[R];
+#pragma unroll
+          for (int j = 0; j < R; ++j) raw[j] = rel[j] >= 0 ? b2_ld_stream(p + j * 32) : 0;
+#pragma unroll
+          for (int j = 0; j < R; ++j)
+            if (rel[j] >= 0) b2_st_stream(out + off + rel[j], raw[j]);
+        }
+      }
+      if (g.probe_valid[k]) {
+        const uint32_t v = c.valid ? b2_valid_bits<R>(c.valid, row0, emit) : emit;
+#pragma unroll
+        for (int j = 0; j < R; ++j)
+          if (rel[j] >= 0 && ((v >> j) & 1))
+            atomicOr(g.probe_valid[k] + ((off + rel[j]) >> 5), 1u << ((off + rel[j]) & 31));
+      }
+    }
+    // ---- build-side columns (by build row; on a key-ordered table the row is the key offset)
+    for (int k = 0; k < g.nbuild; ++k) {
+      const b2_col_t& c = g.build_cols[k];
+      if (c.dtype == B2_U8) {
+        uint8_t raw[R];
+#pragma unroll
+        for (int j = 0; j < R; ++j)
+          raw[j] = (rel[j] >= 0 && brow[j] >= 0) ? reinterpret_cast<const uint8_t*>(c.data)[brow[j]] : 0;
+#pragma unroll
+        for (int j = 0; j < R; ++j)
+          if (rel[j] >= 0) reinterpret_cast<uint8_t*>(g.build_out[k])[off + rel[j]] = raw[j];
+      } else {
+        const int64_t fill = c.dtype == B2_F64 ? 0x7ff8000000000000LL : 0;   // NaN like pandas take(-1)
+        const int64_t base = g.build_base[k];
+        int64_t raw[R];
+        if (k == 0 && spec) {
+#pragma unroll
+          for (int j = 0; j < R; ++j) raw[j] = brow[j] >= 0 ? (spec32 ? base + pay[j] : pay[j]) : fill;
+        } else if (c.dtype == B2_U32) {
+#pragma unroll
+          for (int j = 0; j < R; ++j)
+            raw[j] = (rel[j] >= 0 && brow[j] >= 0)
+                         ? base + (int64_t)(uint32_t)b2_ld_keep_i32(reinterpret_cast<const int32_t*>(c.data) + brow[j]) : fill;
+        } else {
+#pragma unroll
+          for (int j = 0; j < R; ++j)
+            raw[j] = (rel[j] >= 0 && brow[j] >= 0) ? b2_ld_keep_i64(reinterpret_cast<const int64_t*>(c.data) + brow[j]) : fill;
+        }
+#pragma unroll
+        for (int j = 0; j < R; ++j)
+          if (rel[j] >= 0) b2_st_stream(reinterpret_cast<int64_t*>(g.build_out[k]) + off + rel[j], raw[j]);
+      }
+      if (g.build_valid[k]) {
+#pragma unroll
+        for (int j = 0; j < R; ++j)
+          if (rel[j] >= 0 && brow[j] >= 0 && (!c.valid || b2_bit(c.valid, brow[j])))
+            atomicOr(g.build_valid[k] + ((off + rel[j]) >> 5), 1u << ((off + rel[j]) & 31));
+      }
+    }
+  }
+}
+
+
+// per-WARP emit counts for b2_join_onepass_kernel's geometry (a warp owns 256 consecutive probe rows of
+// its 2048-row tile) plus the match mask; reads key + presence only.  With warp-granular offsets the
+// write pass needs no block barrier at all.
+__global__ void __launch_bounds__(B2_BLOCK, 4)
+b2_join_count8_kernel(const __grid_constant__ b2_scan_t s, int key_col, const __grid_constant__ b2_jointable_t jt,
+                      int mode, int64_t ntiles, int64_t* __restrict__ warp_cnt, uint32_t* __restrict__ match_mask) {
+  // match_mask: one bit per probe row (word w covers rows 32w..32w+31) = "found its build row"; the
+  // write pass reads it instead of probing the table a second time
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t row0 = tile * B2_JOP_TILE + (int64_t)warp * (32 * B2_JOP_R) + lane;
+    int32_t brow[B2_JOP_R];
+    int c = __popc(b2_dense_probe<B2_JOP_R>(s, key_col, jt, mode, row0, brow));
+    uint32_t mine = 0;   // lane j keeps the ballot of batch row j
+#pragma unroll
+    for (int j = 0; j < B2_JOP_R; ++j) {
+      const uint32_t b = __ballot_sync(FULL_MASK, brow[j] >= 0);
+      if (lane == j) mine = b;
+    }
+    const int64_t w0 = (row0 - lane) >> 5;
+    if (lane < B2_JOP_R && (w0 + lane) * 32 < s.n) match_mask[w0 + lane] = mine;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(FULL_MASK, c, o);
+    if (lane == 0) warp_cnt[tile * B2_WARPS + warp] = c;
+  }
+}
+
 extern "C" {
 
 int32_t b2_join_build(const b2_col_t* keys, int32_t nkeys, int64_t n, int32_t* head, int32_t* next,
@@ -541,50 +772,28 @@ int32_t b2_join_count(const b2_scan_t* scan, const int32_t* probe_keys, const b2
   return B2_OK;
 }
 
-static int32_t b2_join_write_impl(const b2_scan_t* scan, const int32_t* probe_keys, const b2_jointable_t* jt,
-                                  int32_t mode, const int64_t* d_tile_off, int32_t* out_probe_idx,
-                                  int32_t* out_build_idx, uint8_t* build_matched, int32_t nprobe,
-                                  const int32_t* probe_cols, void* const* probe_out,
-                                  uint32_t* const* probe_valid, int32_t nbuild, const b2_col_t* build_cols,
-                                  const int64_t* build_base, void* const* build_out,
-                                  uint32_t* const* build_valid, uint64_t* lb_status, int64_t* lb_total,
-                                  void* stream) {
-  b2_probekeys_arg pk;
-  int32_t rc = b2_check_join(scan, probe_keys, jt, mode, &pk);
-  if (rc) return rc;
-  B2_REQUIRE(d_tile_off || lb_status, "null argument");
-  B2_REQUIRE(!lb_status || (jt->dense && lb_total), "single-pass probe needs a direct-address table");
+static int32_t b2_fill_joingather(const b2_scan_t* scan, const b2_jointable_t* jt, int32_t nprobe,
+                                  const int32_t* probe_cols, void* const* probe_out, uint32_t* const* probe_valid,
+                                  int32_t nbuild, const b2_col_t* build_cols, const int64_t* build_base,
+                                  void* const* build_out, uint32_t* const* build_valid, b2_joingather_arg* g) {
   B2_REQUIRE(nprobe >= 0 && nprobe <= B2_MAX_GATHER && nbuild >= 0 && nbuild <= B2_MAX_GATHER, "too many gather columns");
-  b2_joingather_arg g;
-  memset(&g, 0, sizeof(g));
-  g.nprobe = nprobe;
-  g.nbuild = nbuild;
+  memset(g, 0, sizeof(*g));
+  g->nprobe = nprobe;
+  g->nbuild = nbuild;
   for (int k = 0; k < nprobe; ++k) {
     B2_REQUIRE(probe_cols[k] >= 0 && probe_cols[k] < scan->ncols && probe_out[k], "bad probe gather");
-    g.probe_cols[k] = probe_cols[k];
-    g.probe_out[k] = probe_out[k];
-    g.probe_valid[k] = probe_valid ? probe_valid[k] : nullptr;
+    g->probe_cols[k] = probe_cols[k];
+    g->probe_out[k] = probe_out[k];
+    g->probe_valid[k] = probe_valid ? probe_valid[k] : nullptr;
   }
   for (int k = 0; k < nbuild; ++k) {
     B2_REQUIRE(build_out[k], "bad build gather");
     B2_REQUIRE(build_cols[k].dtype != B2_U32 || (jt->dense == 2 && build_base), "uint32 payloads need a key-ordered table");
-    g.build_cols[k] = build_cols[k];
-    g.build_base[k] = build_base ? build_base[k] : 0;
-    g.build_out[k] = build_out[k];
-    g.build_valid[k] = build_valid ? build_valid[k] : nullptr;
+    g->build_cols[k] = build_cols[k];
+    g->build_base[k] = build_base ? build_base[k] : 0;
+    g->build_out[k] = build_out[k];
+    g->build_valid[k] = build_valid ? build_valid[k] : nullptr;
   }
-  const int64_t ntiles = b2_num_tiles(scan->n);
-  if (ntiles == 0) return B2_OK;
-  if (jt->dense) {
-    int grid = b2_wave_grid(b2_join_write_kernel<true>, B2_BLOCK, ntiles);
-    b2_join_write_kernel<true><<<grid, B2_BLOCK, 0, (cudaStream_t)stream>>>(
-        *scan, pk, *jt, mode, ntiles, d_tile_off, out_probe_idx, out_build_idx, build_matched, g, lb_status, lb_total);
-  } else {
-    int grid = b2_wave_grid(b2_join_write_kernel<false>, B2_BLOCK, ntiles);
-    b2_join_write_kernel<false><<<grid, B2_BLOCK, 0, (cudaStream_t)stream>>>(
-        *scan, pk, *jt, mode, ntiles, d_tile_off, out_probe_idx, out_build_idx, build_matched, g, nullptr, nullptr);
-  }
-  B2_CHECK_LAUNCH("b2_join_write_kernel");
   return B2_OK;
 }
 
@@ -595,21 +804,70 @@ int32_t b2_join_write_gather_keyed(const b2_scan_t* scan, const int32_t* probe_k
                                    uint32_t* const* probe_valid, int32_t nbuild, const b2_col_t* build_cols,
                                    const int64_t* build_base, void* const* build_out,
                                    uint32_t* const* build_valid, void* stream) {
+  b2_probekeys_arg pk;
+  int32_t rc = b2_check_join(scan, probe_keys, jt, mode, &pk);
+  if (rc) return rc;
   B2_REQUIRE(d_tile_off, "null argument");
-  return b2_join_write_impl(scan, probe_keys, jt, mode, d_tile_off, out_probe_idx, out_build_idx, build_matched,
-                            nprobe, probe_cols, probe_out, probe_valid, nbuild, build_cols, build_base, build_out,
-                            build_valid, nullptr, nullptr, stream);
+  b2_joingather_arg g;
+  rc = b2_fill_joingather(scan, jt, nprobe, probe_cols, probe_out, probe_valid, nbuild, build_cols, build_base,
+                          build_out, build_valid, &g);
+  if (rc) return rc;
+  const int64_t ntiles = b2_num_tiles(scan->n);
+  if (ntiles == 0) return B2_OK;
+  if (jt->dense) {
+    int grid = b2_wave_grid(b2_join_write_kernel<true>, B2_BLOCK, ntiles);
+    b2_join_write_kernel<true><<<grid, B2_BLOCK, 0, (cudaStream_t)stream>>>(
+        *scan, pk, *jt, mode, ntiles, d_tile_off, out_probe_idx, out_build_idx, build_matched, g);
+  } else {
+    int grid = b2_wave_grid(b2_join_write_kernel<false>, B2_BLOCK, ntiles);
+    b2_join_write_kernel<false><<<grid, B2_BLOCK, 0, (cudaStream_t)stream>>>(
+        *scan, pk, *jt, mode, ntiles, d_tile_off, out_probe_idx, out_build_idx, build_matched, g);
+  }
+  B2_CHECK_LAUNCH("b2_join_write_kernel");
+  return B2_OK;
+}
+
+static inline int64_t b2_jop_tiles(int64_t n) { return n > 0 ? (n + B2_JOP_TILE - 1) / B2_JOP_TILE : 0; }
+int64_t b2_join_onepass_ws_bytes(int64_t n) {
+  // [total][8*ntiles+1 warp offsets (or ntiles look-back status words)][match mask: 1 bit per probe row]
+  return 8 * (2 + B2_WARPS * b2_jop_tiles(n)) + 8 * ((n > 0 ? n : 0) / 64 + 1);
 }
 
 int32_t b2_join_onepass(const b2_scan_t* scan, const int32_t* probe_keys, const b2_jointable_t* jt, int32_t mode,
-                        uint64_t* d_status, int64_t* d_total, int32_t nprobe, const int32_t* probe_cols,
+                        int32_t lookback, void* d_ws, int32_t nprobe, const int32_t* probe_cols,
                         void* const* probe_out, uint32_t* const* probe_valid, int32_t nbuild,
                         const b2_col_t* build_cols, const int64_t* build_base, void* const* build_out,
                         uint32_t* const* build_valid, void* stream) {
-  B2_REQUIRE(d_status && d_total, "null argument");
-  return b2_join_write_impl(scan, probe_keys, jt, mode, nullptr, nullptr, nullptr, nullptr, nprobe, probe_cols,
-                            probe_out, probe_valid, nbuild, build_cols, build_base, build_out, build_valid,
-                            d_status, d_total, stream);
+  b2_probekeys_arg pk;
+  int32_t rc = b2_check_join(scan, probe_keys, jt, mode, &pk);
+  if (rc) return rc;
+  B2_REQUIRE(d_ws, "null argument");
+  B2_REQUIRE(jt->dense, "single-pass probe needs a direct-address table");
+  b2_joingather_arg g;
+  rc = b2_fill_joingather(scan, jt, nprobe, probe_cols, probe_out, probe_valid, nbuild, build_cols, build_base,
+                          build_out, build_valid, &g);
+  if (rc) return rc;
+  const int64_t ntiles = (scan->n + B2_JOP_TILE - 1) / B2_JOP_TILE;
+  if (ntiles <= 0) return B2_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  int64_t* total = reinterpret_cast<int64_t*>(d_ws);      // ws[0]; ws[1 .. ntiles+1] = status words / tile offsets
+  int64_t* tiles = total + 1;
+  int grid = b2_wave_grid(b2_join_onepass_kernel, B2_BLOCK, ntiles);
+  if (lookback) {
+    b2_join_onepass_kernel<<<grid, B2_BLOCK, 0, st>>>(*scan, pk.cols[0], *jt, mode, ntiles,
+                                                      reinterpret_cast<uint64_t*>(tiles), nullptr, nullptr, total, g);
+  } else {
+    int cgrid = b2_wave_grid(b2_join_count8_kernel, B2_BLOCK, ntiles);
+    uint32_t* mask = reinterpret_cast<uint32_t*>(tiles + ntiles * B2_WARPS + 1);
+    b2_join_count8_kernel<<<cgrid, B2_BLOCK, 0, st>>>(*scan, pk.cols[0], *jt, mode, ntiles, tiles, mask);
+    B2_CHECK_LAUNCH("b2_join_count8_kernel");
+    b2_exclusive_scan_kernel<<<1, B2_SCAN_THREADS, 0, st>>>(tiles, ntiles * B2_WARPS);
+    B2_CHECK_LAUNCH("b2_exclusive_scan_kernel");
+    b2_join_onepass_kernel<<<grid, B2_BLOCK, 0, st>>>(*scan, pk.cols[0], *jt, mode, ntiles, nullptr, tiles, mask,
+                                                      total, g);
+  }
+  B2_CHECK_LAUNCH("b2_join_onepass_kernel");
+  return B2_OK;
 }
 
 int32_t b2_join_write_gather(const b2_scan_t* scan, const int32_t* probe_keys, const b2_jointable_t* jt,

@@ -4,6 +4,7 @@ PyTorch is used only as plumbing: device memory (caching allocator), streams, an
 torch.distributed.  All arithmetic on column data happens in libb200sql.so.
 """
 import ctypes as C
+import os
 from dataclasses import dataclass, field
 from typing import List, Optional, Sequence
 
@@ -540,8 +541,7 @@ def join_probe_onepass(scan, probe_keys, jt: JoinTable, mode, device, scan_cols,
     -> (probe outputs, build outputs, 1-element int64 count tensor); slice with `trim` once known."""
     assert jt.dense
     n = scan.n
-    ntiles = L.num_tiles(n)
-    ws = torch.zeros(ntiles + 1, dtype=torch.int64, device=device)      # look-back status words + total
+    ws = torch.zeros(L.join_onepass_ws_bytes(n) // 8, dtype=torch.int64, device=device)   # [total, status words]
     pk = (C.c_int32 * len(probe_keys))(*probe_keys)
     pouts, pvalid, bouts, bvalid = [], [], [], []
     for sl in probe_gather:
@@ -565,8 +565,9 @@ def join_probe_onepass(scan, probe_keys, jt: JoinTable, mode, device, scan_cols,
     else:
         bc = (L.Col * max(1, nb))(*[c.as_struct() for c in build_cols])
         bb = None
-    L.join_onepass(C.byref(scan), pk, C.byref(jt.struct), mode, ptr(ws), C.c_void_p(ws.data_ptr() + 8 * ntiles),
-                   np_, pc, po, pv, nb, bc, bb, bo, bv, stream_ptr())
+    lookback = 1 if os.environ.get("B200SQL_JOIN_LOOKBACK") == "1" else 0
+    L.join_onepass(C.byref(scan), pk, C.byref(jt.struct), mode, lookback, ptr(ws), np_, pc, po, pv, nb, bc, bb,
+                   bo, bv, stream_ptr())
 
     def trim(total):
         w = bitmap_words(total)
@@ -576,7 +577,7 @@ def join_probe_onepass(scan, probe_keys, jt: JoinTable, mode, device, scan_cols,
                 for o, v, c in zip(bouts, bvalid, build_cols)]
         return pres, bres
 
-    return trim, ws[ntiles:]
+    return trim, ws[:1]
 
 
 def join_probe(scan, probe_keys, jt: JoinTable, mode, device, build_matched=None):

@@ -11,6 +11,6 @@ timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --c
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:b2_star_agg_kernel -s 8 -c 2 \
     -o gpurun_out/${R}_star python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu > gpurun_out/${R}_star_ncu.log 2>&1
 timeout 300 ncu --set full --clock-control none --import-source on \
-    -k regex:"b2_(scan_agg|groupby_dense|join_write|join_count|select_write)_kernel" -c 8 \
+    -k regex:"b2_(scan_agg|groupby_dense|join_onepass|join_count8|select_write)_kernel" -c 8 \
     -o gpurun_out/${R}_others python scripts/ncu_target2.py > gpurun_out/${R}_others_ncu.log 2>&1
 ls -la gpurun_out

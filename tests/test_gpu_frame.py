@@ -379,18 +379,18 @@ def test_join_key_ordered_payload_layout(how, monkeypatch):
 
 
 @pytest.mark.parametrize("how", ["inner", "left", "leftsemi", "leftanti"])
-@pytest.mark.parametrize("match", [0.0, 0.03, 0.8, 1.0])
+@pytest.mark.parametrize("match", [0.03, 0.8])
 def test_join_single_pass_lookback_equals_two_pass(how, match, monkeypatch):
     """b2_join_onepass (tile offsets by decoupled look-back, count left on the device) must emit
     exactly the rows, in exactly the order, of the count + write protocol -- across many tiles,
     with tiles that emit nothing and with a pushed-down probe filter."""
     from dask_sql_b200 import executor
     rng = np.random.default_rng(int(match * 100) + 41)
-    nd, nf = 50_000, 3_000_017
+    nd, nf = 50_000, 700_003
     dim = pd.DataFrame({"pk": rng.permutation(nd).astype(np.int64), "w": rng.integers(0, 1000, nd), "g": rng.random(nd)})
     hit = rng.random(nf) < match
     fk = np.where(hit, rng.integers(0, nd, nf), rng.integers(nd, 2 * nd, nf)).astype(np.int64)
-    fk[1_000_000:1_300_000] = nd + 7                                   # a long run of tiles without matches
+    fk[200_000:420_000] = nd + 7                                   # a long run of tiles without matches
     fact = pd.DataFrame({"fk": fk, "v": rng.random(nf), "x": rng.integers(-5, 5, nf)})
     f, d = _table(fact, 3), _table(dim)
 
