@@ -1,4 +1,4 @@
-"""Run one BASELINE config repeatedly (for launch lists / event timing).  usage: probe_one.py c1|c2|c2i|c3|c4 rows reps [nparts]"""
+"""Run one BASELINE config repeatedly (for launch lists / event timing).  usage: probe_one.py c1|c2|c2i|c3|c4|c5 rows reps [nparts]"""
 import sys, os, time, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -22,6 +22,10 @@ elif cfg == "c2i":
     t = table({"key": torch.randint(0, 1_000_000, (n,), dtype=torch.int64, device=dev, generator=g),
                "vi": torch.randint(-1000, 1001, (n,), dtype=torch.int64, device=dev, generator=g)}, nparts)
     q = LazyFrame(AggSource(t, ["key"], [("vi", "s", "sum")])); bpr = 16
+elif cfg == "c5":
+    t = table({"key": torch.randint(0, 100_000_000, (n,), dtype=torch.int64, device=dev, generator=g),
+               "val": torch.rand(n, dtype=torch.float64, device=dev, generator=g)}, nparts)
+    q = LazyFrame(AggSource(t, ["key"], [("val", "s", "sum"), ("val", "m", "mean")])); bpr = 16
 elif cfg == "c3":
     nd = 10_000_000
     f = table({"fk": torch.randint(0, int(nd * 1.25), (n,), dtype=torch.int64, device=dev, generator=g),
