@@ -19,7 +19,7 @@ from .datacontainer import ColumnContainer, DataContainer, SchemaContainer, Stat
 from .frame import LazyFrame, TableSource
 from .mappings import python_to_sql_type
 from .physical.rel import RelConverter
-from .physical.rel import logical
+from .physical.rel import custom, logical
 from .physical.rex import RexConverter
 from .physical.rex import core
 from .planner import LogicalPlan, plan_sql
@@ -58,6 +58,9 @@ class Context:
         RelConverter.add_plugin_class(logical.DaskLimitPlugin, replace=False)
         RelConverter.add_plugin_class(logical.SubqueryAlias, replace=False)
         RelConverter.add_plugin_class(logical.DaskTableScanPlugin, replace=False)
+        RelConverter.add_plugin_class(custom.CreateMemoryTablePlugin, replace=False)
+        RelConverter.add_plugin_class(custom.CreateTablePlugin, replace=False)
+        RelConverter.add_plugin_class(custom.DropTablePlugin, replace=False)
 
         RexConverter.add_plugin_class(core.RexAliasPlugin, replace=False)
         RexConverter.add_plugin_class(core.RexCallPlugin, replace=False)
@@ -75,7 +78,8 @@ class Context:
         """Register a table (context.py:168-293).
 
         input_table: pandas.DataFrame, dict of column -> numpy array / torch tensor, pyarrow.Table,
-        a DeviceTable, or a LazyFrame (e.g. the result of another query).
+        a DeviceTable, a LazyFrame (e.g. the result of another query), or the path of a Parquet /
+        CSV file (format = "parquet" | "csv", default by extension; kwargs `columns=[...]` reads a subset).
         persist=True uploads the columns to HBM once; persist=False (the reference's default:
         'the data will be lazily loaded') keeps them in pinned host memory and streams them to the
         GPU for every query.  kwargs: npartitions (default 1, pandaslike.py:26) and
@@ -91,11 +95,15 @@ class Context:
                 table = input_table
             else:
                 if isinstance(input_table, str):
-                    raise NotImplementedError(
-                        "loading tables from storage locations is outside the hot-path scope (SURVEY 2 row 8)")
-                if hasattr(input_table, "to_pandas") and not isinstance(input_table, pd.DataFrame):
-                    input_table = input_table.to_pandas()           # pyarrow.Table
-                if isinstance(input_table, pd.DataFrame):
+                    # storage location (input_utils/location.py:11-54): Parquet / CSV column chunks are
+                    # read with pyarrow and laid out on the device without a pandas detour
+                    from .table import read_location
+                    input_table = read_location(input_table, format, **kwargs)
+                    kwargs = {}
+                if type(input_table).__module__.startswith("pyarrow") and hasattr(input_table, "column_names"):
+                    from .table import arrow_columns
+                    columns = arrow_columns(input_table)            # pyarrow.Table: buffers used as they are
+                elif isinstance(input_table, pd.DataFrame):
                     columns = {str(c): input_table[c] for c in input_table.columns}
                 elif isinstance(input_table, dict):
                     columns = {str(k): v for k, v in input_table.items()}

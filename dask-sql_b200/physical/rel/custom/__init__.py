@@ -1,0 +1,5 @@
+from .create_memory_table import CreateMemoryTablePlugin
+from .create_table import CreateTablePlugin
+from .drop_table import DropTablePlugin
+
+__all__ = [CreateMemoryTablePlugin, CreateTablePlugin, DropTablePlugin]

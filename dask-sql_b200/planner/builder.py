@@ -47,6 +47,13 @@ class Binder:
     def bind_statement(self, node: Node) -> P.LogicalPlan:
         if node.kind == "explain":
             return P.Explain(self.bind_query(node.query, {}))
+        if node.kind == "create_memory_table":
+            return P.CreateMemoryTable(self.bind_query(node.query, {}), node.name, node.or_replace,
+                                       node.if_not_exists, node.is_table)
+        if node.kind == "create_table":
+            return P.CreateTable(node.name, node.kwargs, node.or_replace, node.if_not_exists)
+        if node.kind == "drop_table":
+            return P.DropTable(node.name, node.if_exists)
         return self.bind_query(node, {})
 
     def bind_query(self, q: Node, ctes: Dict[str, P.LogicalPlan]) -> P.LogicalPlan:

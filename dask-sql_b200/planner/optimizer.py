@@ -198,8 +198,10 @@ def _refresh_schemas(plan: P.LogicalPlan):
 
 
 def optimize(plan: P.LogicalPlan) -> P.LogicalPlan:
-    if isinstance(plan, P.Explain):
+    if isinstance(plan, (P.Explain, P.CreateMemoryTable)):
         plan.inputs = [optimize(plan.inputs[0])]
+        return plan
+    if isinstance(plan, (P.CreateTable, P.DropTable)):
         return plan
     plan = push_filters(plan, [])
     plan = prune_columns(plan)

@@ -688,6 +688,92 @@ class Explain(LogicalPlan):
         return "Explain"
 
 
+class CreateMemoryTable(LogicalPlan):
+    """CREATE TABLE|VIEW name AS query (src/sql/logical/create_memory_table.rs; consumed by
+    physical/rel/custom/create_memory_table.py:36-76)."""
+    node_type = "CreateMemoryTable"
+
+    def __init__(self, child, name, or_replace, if_not_exists, is_table):
+        super().__init__([child])
+        self.name, self.or_replace, self.if_not_exists, self.is_table_ = name, or_replace, if_not_exists, is_table
+        if not is_table:
+            self.node_type = "CreateView"
+
+    def create_memory_table(self):
+        return self
+
+    def getQualifiedName(self):
+        return self.name
+
+    def getOrReplace(self):
+        return self.or_replace
+
+    def getIfNotExists(self):
+        return self.if_not_exists
+
+    def getInput(self):
+        return self.inputs[0]
+
+    def isTable(self):
+        return self.is_table_
+
+    def describe(self):
+        return f"{self.node_type}: {self.name}"
+
+
+class CreateTable(LogicalPlan):
+    """CREATE TABLE name WITH (...) (src/sql/logical/create_table.rs; custom/create_table.py:40-88)."""
+    node_type = "CreateTable"
+
+    def __init__(self, name, kwargs, or_replace, if_not_exists):
+        super().__init__([])
+        *schema, self.table_name = name.split(".")
+        self.schema_name = schema[0] if schema else None
+        self.kwargs, self.or_replace, self.if_not_exists = dict(kwargs), or_replace, if_not_exists
+
+    def create_table(self):
+        return self
+
+    def getSchemaName(self):
+        return self.schema_name
+
+    def getTableName(self):
+        return self.table_name
+
+    def getOrReplace(self):
+        return self.or_replace
+
+    def getIfNotExists(self):
+        return self.if_not_exists
+
+    def getSQLWithOptions(self):
+        return dict(self.kwargs)
+
+    def describe(self):
+        return f"CreateTable: {self.table_name}"
+
+
+class DropTable(LogicalPlan):
+    """DROP TABLE [IF EXISTS] name (src/sql/logical/drop_table.rs; custom/drop_table.py)."""
+    node_type = "DropTable"
+
+    def __init__(self, name, if_exists):
+        super().__init__([])
+        self.name, self.if_exists = name, if_exists
+
+    def drop_table(self):
+        return self
+
+    def getQualifiedName(self):
+        return self.name
+
+    def getIfExists(self):
+        return self.if_exists
+
+    def describe(self):
+        return f"DropTable: {self.name}"
+
+
 def walk(plan: LogicalPlan):
     yield plan
     for i in plan.inputs:

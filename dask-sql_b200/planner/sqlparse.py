@@ -13,6 +13,12 @@ that crate cannot be built here (no rustc/cargo), so this is a small recursive-d
 Expressions: literals, [qualifier.]column, + - * / %, comparisons, AND OR NOT, IS [NOT] NULL,
 [NOT] BETWEEN, [NOT] IN (list), CAST(e AS type), CASE WHEN, function calls incl. aggregates with
 DISTINCT and FILTER (WHERE ...).
+
+Statements around the path (custom statements of the reference's parser, src/parser.rs):
+  CREATE [OR REPLACE] TABLE|VIEW [IF NOT EXISTS] [schema.]name AS [(] query [)]
+  CREATE [OR REPLACE] TABLE [IF NOT EXISTS] [schema.]name WITH (key = literal [, ...])
+  DROP TABLE [IF EXISTS] [schema.]name
+CREATE / DROP / TABLE / VIEW / IF / EXISTS / REPLACE are contextual words, not reserved.
 """
 import re
 from typing import List, Optional
@@ -125,8 +131,85 @@ class Parser:
             return self.toks[self.i - 1].val.lower()
         self.error("Expected identifier")
 
+    def at_word(self, *words):
+        return self.cur.kind == "id" and self.cur.val.upper() in words
+
+    def eat_word(self, *words):
+        if self.at_word(*words):
+            self.i += 1
+            return self.toks[self.i - 1].val.upper()
+        return None
+
+    def expect_word(self, word):
+        if not self.eat_word(word):
+            self.error(f"Expected {word}")
+
+    def qualified_name(self) -> str:
+        parts = [self.ident()]
+        while self.eat_op("."):
+            parts.append(self.ident())
+        return ".".join(parts)
+
     # -- statements
+    def parse_ddl(self) -> Optional[Node]:
+        if self.at_word("DROP") and self.toks[self.i + 1].kind == "id":
+            self.i += 1
+            self.expect_word("TABLE")
+            if_exists = False
+            if self.at_word("IF"):
+                self.i += 1
+                self.expect_word("EXISTS")
+                if_exists = True
+            return Node("drop_table", name=self.qualified_name(), if_exists=if_exists)
+        if not (self.at_word("CREATE") and self.toks[self.i + 1].kind in ("id", "kw")):
+            return None
+        self.i += 1
+        or_replace = False
+        if self.eat_kw("OR"):
+            self.expect_word("REPLACE")
+            or_replace = True
+        what = self.eat_word("TABLE", "VIEW")
+        if what is None:
+            self.error("Expected TABLE or VIEW")
+        if_not_exists = False
+        if self.at_word("IF"):
+            self.i += 1
+            self.expect_kw("NOT")
+            self.expect_word("EXISTS")
+            if_not_exists = True
+        name = self.qualified_name()
+        if self.eat_kw("AS"):
+            paren = bool(self.at_op("(") and self.toks[self.i + 1].kind == "kw"
+                         and self.toks[self.i + 1].val in ("SELECT", "WITH") and self.eat_op("("))
+            q = self.parse_query()
+            if paren:
+                self.expect_op(")")
+            return Node("create_memory_table", name=name, query=q, or_replace=or_replace,
+                        if_not_exists=if_not_exists, is_table=(what == "TABLE"))
+        if what == "TABLE" and self.eat_kw("WITH"):
+            self.expect_op("(")
+            kwargs = {}
+            while True:
+                key = self.ident()
+                self.expect_op("=")
+                lit = self.parse_primary()
+                neg = False
+                if lit.kind != "lit":
+                    self.error("Expected a literal value")
+                kwargs[key] = lit.value
+                if not self.eat_op(","):
+                    break
+            self.expect_op(")")
+            return Node("create_table", name=name, kwargs=kwargs, or_replace=or_replace, if_not_exists=if_not_exists)
+        self.error("Expected AS or WITH")
+
     def parse_statement(self) -> Node:
+        ddl = self.parse_ddl()
+        if ddl is not None:
+            self.eat_op(";")
+            if self.cur.kind != "eof":
+                self.error("Unexpected trailing input")
+            return ddl
         explain = bool(self.eat_kw("EXPLAIN"))
         q = self.parse_query()
         self.eat_op(";")

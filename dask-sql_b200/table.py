@@ -35,12 +35,131 @@ class HostColumn:
         return self.data.numel() * self.data.element_size() + (0 if self.valid is None else self.valid.numel() * 4)
 
 
+class ArrowColumn:
+    """One column of a pyarrow.Table as plain buffers: widened values + Arrow validity bytes.
+
+    Arrow's validity bitmap is LSB-ordered, one bit per row -- exactly the device layout -- so the
+    bytes are used as they are (no unpack / repack, no pandas object in between); slices at
+    multiples of 8 rows (partitions start at multiples of 32) are views."""
+
+    __slots__ = ("values", "valid_bytes", "logical")
+
+    def __init__(self, values: np.ndarray, valid_bytes: Optional[np.ndarray], logical: str):
+        self.values, self.valid_bytes, self.logical = values, valid_bytes, logical
+
+    def __len__(self):
+        return int(self.values.shape[0])
+
+    def __getitem__(self, sl: slice):
+        lo, hi, _ = sl.indices(len(self))
+        vb = None
+        if self.valid_bytes is not None:
+            assert lo % 8 == 0
+            vb = self.valid_bytes[lo // 8: (hi + 7) // 8]
+        return ArrowColumn(self.values[lo:hi], vb, self.logical)
+
+    def valid_words(self) -> Optional[np.ndarray]:
+        """int32 validity words of this slice, or None when nothing is NULL."""
+        if self.valid_bytes is None:
+            return None
+        n = len(self)
+        nbytes = (n + 7) // 8
+        out = np.zeros(((n + 31) // 32) * 4, dtype=np.uint8)
+        out[:nbytes] = self.valid_bytes[:nbytes]
+        if n % 8:
+            out[nbytes - 1] &= (1 << (n % 8)) - 1          # bits past the end belong to nobody
+        bits_set = int(np.unpackbits(out[:nbytes], bitorder="little")[:n].sum()) if n else 0
+        return None if bits_set == n else out.view(np.int32)
+
+
+def _arrow_array_to_column(arr) -> ArrowColumn:
+    import pyarrow as pa
+
+    t = arr.type
+    n = len(arr)
+    if pa.types.is_dictionary(t) or pa.types.is_string(t) or pa.types.is_large_string(t) or pa.types.is_temporal(t) \
+            or pa.types.is_decimal(t) or pa.types.is_nested(t) or pa.types.is_uint64(t):
+        raise NotImplementedError(
+            f"column type {t} is outside the int64/float64/bool hot path of the B200 layer")
+    bufs = arr.buffers()
+    off = arr.offset
+    has_nulls = arr.null_count > 0
+    valid_bytes = None
+    if has_nulls:
+        vb = np.frombuffer(bufs[0], dtype=np.uint8)
+        if off % 8 == 0:
+            valid_bytes = vb[off // 8: off // 8 + (n + 7) // 8]
+        else:   # a slice that does not start on a byte boundary: realign once
+            bits = np.unpackbits(vb, bitorder="little")[off: off + n]
+            valid_bytes = np.packbits(bits, bitorder="little")
+    if pa.types.is_boolean(t):
+        bits = np.unpackbits(np.frombuffer(bufs[1], dtype=np.uint8), bitorder="little")[off: off + n]
+        return ArrowColumn(np.ascontiguousarray(bits, dtype=np.uint8).view(np.bool_), valid_bytes,
+                           "boolean" if has_nulls else "bool")
+    if pa.types.is_integer(t):
+        np_dt = np.dtype(t.to_pandas_dtype())
+        vals = np.frombuffer(bufs[1], dtype=np_dt)[off: off + n]
+        name = np_dt.name
+        return ArrowColumn(vals.astype(np.int64, copy=False), valid_bytes,
+                           (name[0].upper() + name[1:]).replace("Uint", "UInt") if has_nulls else name)
+    if pa.types.is_floating(t):
+        np_dt = np.dtype(t.to_pandas_dtype())
+        vals = np.frombuffer(bufs[1], dtype=np_dt)[off: off + n].astype(np.float64, copy=False)
+        if has_nulls:   # NULL float = NaN, the reference's (pandas') convention
+            vals = vals.copy()
+            vals[np.unpackbits(valid_bytes, bitorder="little")[:n] == 0] = np.nan
+        return ArrowColumn(vals, None, np_dt.name)
+    raise NotImplementedError(f"column type {t} is outside the int64/float64/bool hot path of the B200 layer")
+
+
+def arrow_columns(table) -> Dict[str, ArrowColumn]:
+    """pyarrow.Table -> {name: ArrowColumn}.  Multi-chunk columns are concatenated once (Arrow
+    does that in C++); single-chunk columns are zero-copy views of the Arrow buffers."""
+    import pyarrow as pa
+
+    out = {}
+    for name in table.column_names:
+        col = table.column(name)
+        arr = col.chunk(0) if col.num_chunks == 1 else (col.combine_chunks() if col.num_chunks else
+                                                       pa.array([], type=col.type))
+        if isinstance(arr, pa.ChunkedArray):
+            arr = arr.chunk(0) if arr.num_chunks == 1 else pa.concat_arrays(arr.chunks)
+        out[str(name)] = _arrow_array_to_column(arr)
+    return out
+
+
+def read_location(location: str, format: Optional[str] = None, **kwargs):
+    """Parquet / CSV file (or directory of Parquet files) -> pyarrow.Table
+    (the reference: input_utils/location.py:27-54, dd.read_<format>(location, **kwargs))."""
+    import os
+
+    if format is None:
+        ext = os.path.splitext(location.rstrip("/"))[1].lstrip(".").lower()
+        format = ext or "parquet"
+    format = format.lower()
+    columns = kwargs.pop("columns", None)
+    kwargs.pop("gpu", None)
+    if kwargs:
+        raise TypeError(f"unsupported options for reading {location!r}: {sorted(kwargs)}")
+    if format == "parquet":
+        import pyarrow.parquet as pq
+        return pq.read_table(location, columns=list(columns) if columns is not None else None)
+    if format == "csv":
+        import pyarrow.csv as pcsv
+        t = pcsv.read_csv(location)
+        return t.select(list(columns)) if columns is not None else t
+    raise AttributeError(f"Do not understand the input format {format!r} (supported here: parquet, csv)")
+
+
 def _host_column(values, pin=True) -> HostColumn:
     import pandas as pd
 
     logical = str(getattr(values, "dtype", "float64"))
     mask = None
-    if isinstance(values, pd.Series):
+    words = None
+    if isinstance(values, ArrowColumn):
+        vals, logical, words = values.values, values.logical, values.valid_words()
+    elif isinstance(values, pd.Series):
         arr = values.array
         if isinstance(arr, pd.arrays.BooleanArray):
             mask, vals = np.asarray(arr._mask), np.asarray(arr._data).astype(np.uint8)
@@ -78,10 +197,12 @@ def _host_column(values, pin=True) -> HostColumn:
     if pin and torch.cuda.is_available() and not t.is_pinned():
         t = t.pin_memory()
     v = None
-    if mask is not None and mask.any():
+    if words is not None:
+        v = torch.from_numpy(np.ascontiguousarray(words))
+    elif mask is not None and mask.any():
         v = torch.from_numpy(_pack_valid(mask))
-        if pin and torch.cuda.is_available():
-            v = v.pin_memory()
+    if v is not None and pin and torch.cuda.is_available():
+        v = v.pin_memory()
     return HostColumn(t, v, dt, logical)
 
 

@@ -233,3 +233,67 @@ def test_host_column_roundtrip_keeps_logical_dtypes():
     assert b.dtype == 2 and b.data.dtype == torch.uint8
     with pytest.raises(NotImplementedError):
         _host_column(pd.Series(["a", "b"]), pin=False)
+
+
+def test_ddl_statements_plan_like_the_reference():
+    """CREATE TABLE AS / CREATE VIEW / CREATE TABLE WITH / DROP TABLE produce plan nodes with the
+    accessor surface the reference's custom plugins call (physical/rel/custom/*.py)."""
+    from dask_sql_b200.planner import plan_sql
+
+    catalog = lambda schema, table: ("root", [("a", "BIGINT"), ("b", "DOUBLE")]) if table == "x" else None
+    p = plan_sql("CREATE OR REPLACE TABLE s.t AS (SELECT a FROM x WHERE a > 1)", catalog)
+    assert p.get_current_node_type() == "CreateMemoryTable"
+    cmt = p.create_memory_table()
+    assert (cmt.getQualifiedName(), cmt.getOrReplace(), cmt.getIfNotExists(), cmt.isTable()) == ("s.t", True, False, True)
+    assert cmt.getInput().get_current_node_type() in ("Projection", "TableScan")
+    v = plan_sql("create view v as select b from x", catalog)
+    assert v.get_current_node_type() == "CreateView" and not v.create_memory_table().isTable()
+    ct = plan_sql("CREATE TABLE IF NOT EXISTS t WITH (location = '/d/a.parquet', format = 'parquet', persist = True, "
+                  "npartitions = 4)", catalog).create_table()
+    assert ct.getTableName() == "t" and ct.getSchemaName() is None and ct.getIfNotExists()
+    assert ct.getSQLWithOptions() == {"location": "/d/a.parquet", "format": "parquet", "persist": True, "npartitions": 4}
+    dt = plan_sql("DROP TABLE IF EXISTS s.t;", catalog).drop_table()
+    assert dt.getQualifiedName() == "s.t" and dt.getIfExists()
+    # the words stay usable as identifiers
+    assert plan_sql("SELECT a AS view, b AS replace FROM x", catalog).getRowType().getFieldNames() == ["view", "replace"]
+
+
+def test_arrow_buffers_become_host_columns_without_pandas(tmp_path):
+    import pyarrow as pa
+    import pyarrow.parquet as pq
+    from dask_sql_b200.table import arrow_columns, read_location, _host_column, DeviceTable, ArrowColumn
+
+    n = 203
+    vals = np.arange(n)
+    t = pa.table({"i": pa.array([None if v % 7 == 0 else int(v) for v in vals], type=pa.int16()),
+                  "f": pa.array([None if v % 5 == 0 else v / 2 for v in vals], type=pa.float32()),
+                  "b": pa.array([None if v % 11 == 0 else bool(v & 1) for v in vals]),
+                  "d": pa.array(vals, type=pa.int64())})
+    path = str(tmp_path / "x.parquet")
+    pq.write_table(t, path, row_group_size=64)
+    back = read_location(path, None, columns=["i", "f", "b", "d"])
+    assert back.column("i").num_chunks > 1
+    for tab in (t, back, back.slice(5, 150)):
+        cols = arrow_columns(tab)
+        ref = tab.to_pandas()
+        m = len(ref)
+        assert isinstance(cols["d"], ArrowColumn) and cols["i"].logical == "Int16" and cols["d"].logical == "int64"
+        table = DeviceTable.from_columns(cols, npartitions=3, device=None, persist=False)
+        assert table.nrows == m and len(table.partitions) == 3
+        got_i, got_valid = [], []
+        for part in table.partitions:
+            hc = part["i"]
+            got_i.append(hc.data.numpy())
+            words = hc.valid.numpy().view(np.uint8) if hc.valid is not None else np.full((hc.n + 7) // 8, 255, np.uint8)
+            got_valid.append(np.unpackbits(words, bitorder="little")[: hc.n].astype(bool))
+        got_i, got_valid = np.concatenate(got_i), np.concatenate(got_valid)
+        exp_valid = ~ref["i"].isna().to_numpy()
+        np.testing.assert_array_equal(got_valid, exp_valid)
+        np.testing.assert_array_equal(got_i[exp_valid], ref["i"].to_numpy(dtype=float)[exp_valid].astype(np.int64))
+        f = np.concatenate([p["f"].data.numpy() for p in table.partitions])
+        np.testing.assert_array_equal(np.isnan(f), ref["f"].isna().to_numpy())
+        assert all(p["f"].valid is None and p["d"].valid is None for p in table.partitions)
+    with pytest.raises(NotImplementedError):
+        arrow_columns(pa.table({"s": ["a", "b"]}))
+    with pytest.raises(AttributeError):
+        read_location(path, "orc")

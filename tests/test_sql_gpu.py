@@ -259,3 +259,90 @@ def test_no_cpu_fallback_errors_are_loud(c):
     df = pd.DataFrame({"a": [1, 2, 3], "s": ["x", "y", "z"]})
     with pytest.raises(NotImplementedError):
         c.create_table("t", df)          # strings are outside the int64/float64 hot path
+
+
+def _ingest_frame(n=10_007, seed=3):
+    rng = np.random.default_rng(seed)
+    return pd.DataFrame({
+        "k": rng.integers(0, 50, n).astype(np.int32),
+        "v": rng.random(n),
+        "ni": pd.array(np.where(rng.random(n) < 0.1, None, rng.integers(-5, 5, n)), dtype="Int64"),
+        "nf": np.where(rng.random(n) < 0.1, np.nan, rng.random(n)),
+        "b": rng.integers(0, 2, n).astype(bool),
+    })
+
+
+@pytest.mark.parametrize("persist", [True, False])
+def test_create_table_from_arrow_buffers(c, persist):
+    """pyarrow.Table -> device columns without a pandas detour: int32 widened, Arrow validity
+    bitmaps used as they are (nullable ints stay ints instead of turning into float64 + NaN),
+    NULL floats = NaN, multi-chunk and offset (sliced) inputs."""
+    import pyarrow as pa
+    df = _ingest_frame()
+    t = pa.Table.from_pandas(df, preserve_index=False)
+    chunked = pa.concat_tables([t.slice(0, 4001), t.slice(4001, 3), t.slice(4004)])      # 3 chunks per column
+    c.create_table("t", chunked, persist=persist, npartitions=3)
+    got = c.sql("SELECT k, SUM(v) AS sv, SUM(ni) AS sn, COUNT(ni) AS cn, AVG(nf) AS af, COUNT(*) AS n FROM t "
+                "WHERE b GROUP BY k", return_futures=False)
+    d = df[df["b"]]
+    exp = d.groupby("k").agg(sv=("v", "sum"), sn=("ni", lambda s: s.sum(min_count=1)), cn=("ni", "count"),
+                             af=("nf", "mean"), n=("k", "size")).reset_index()
+    assert_same(got, exp, float_cols=("sv", "af"))
+    # a slice with a non-byte-aligned offset
+    c.create_table("s", t.slice(13, 5000), persist=persist)
+    got = c.sql("SELECT SUM(ni) AS sn, COUNT(ni) AS cn, COUNT(*) AS n FROM s", return_futures=False)
+    sl = df.iloc[13:5013]
+    assert got["sn"].iloc[0] == sl["ni"].sum() and got["cn"].iloc[0] == sl["ni"].count() and got["n"].iloc[0] == 5000
+    out = c.sql("SELECT ni, k FROM s WHERE ni IS NULL OR ni > 3", return_futures=False)
+    assert str(out["ni"].dtype) == "Int64" and str(out["k"].dtype) == "int32"
+    assert int(out["ni"].isna().sum()) == int(sl["ni"].isna().sum())
+
+
+def test_parquet_and_csv_locations_and_ddl(c, tmp_path):
+    """CREATE TABLE ... WITH (location=...), CREATE TABLE|VIEW ... AS, DROP TABLE
+    (physical/rel/custom/create_table.py, create_memory_table.py, drop_table.py)."""
+    import pyarrow as pa
+    import pyarrow.parquet as pq
+    df = _ingest_frame(5_003, seed=4)
+    pq_path, csv_path = str(tmp_path / "t.parquet"), str(tmp_path / "t.csv")
+    pq.write_table(pa.Table.from_pandas(df, preserve_index=False), pq_path, row_group_size=1000)
+    df[["k", "v"]].to_csv(csv_path, index=False)
+
+    c.create_table("p", pq_path, persist=True, npartitions=2, columns=["k", "v", "ni"])
+    assert c.sql("SELECT * FROM p").columns == ["k", "v", "ni"]
+    c.sql(f"CREATE TABLE q WITH (location = '{pq_path}', format = 'parquet', persist = True)")
+    c.sql(f"CREATE TABLE cs WITH (location = '{csv_path}')")
+    exp = df.groupby("k").agg(s=("v", "sum")).reset_index()
+    for name in ("p", "q", "cs"):
+        got = c.sql(f"SELECT k, SUM(v) AS s FROM {name} GROUP BY k", return_futures=False)
+        assert_same(got, exp, float_cols=("s",))
+
+    with pytest.raises(RuntimeError):
+        c.sql(f"CREATE TABLE q WITH (location = '{pq_path}')")                 # already present
+    c.sql(f"CREATE TABLE IF NOT EXISTS q WITH (location = '{csv_path}')")       # silently kept
+    assert "ni" in c.sql("SELECT * FROM q").columns
+
+    # CREATE TABLE AS persists the result on the device; CREATE VIEW keeps the lazy frame
+    c.sql("CREATE TABLE agg AS (SELECT k, SUM(v) AS s, COUNT(*) AS n FROM q WHERE v > 0.25 GROUP BY k)")
+    c.sql("CREATE VIEW big AS SELECT k, v FROM q WHERE v > 0.25")
+    from dask_sql_b200.frame import TableSource
+    assert isinstance(c.schema["root"].tables["agg"].df.source, TableSource)
+    assert not isinstance(c.schema["root"].tables["big"].df.source, TableSource) or c.schema["root"].tables["big"].df.pred
+    d = df[df["v"] > 0.25]
+    exp = d.groupby("k").agg(s=("v", "sum"), n=("k", "size")).reset_index()
+    assert_same(c.sql("SELECT * FROM agg", return_futures=False), exp, float_cols=("s",))
+    got = c.sql("SELECT a.k, a.n, SUM(b.v) AS s2 FROM agg a JOIN big b ON a.k = b.k GROUP BY a.k, a.n",
+                return_futures=False)
+    exp2 = exp.merge(d, on="k").groupby(["k", "n"]).agg(s2=("v", "sum")).reset_index()
+    assert_same(got, exp2, float_cols=("s2",))
+    c.sql("CREATE OR REPLACE TABLE agg AS SELECT k FROM q WHERE k < 3 GROUP BY k")
+    assert sorted(c.sql("SELECT k FROM agg", return_futures=False)["k"].tolist()) == [0, 1, 2]
+
+    c.sql("DROP TABLE agg")
+    with pytest.raises(RuntimeError):
+        c.sql("DROP TABLE agg")
+    c.sql("DROP TABLE IF EXISTS agg")
+    with pytest.raises(Exception):
+        c.sql("SELECT * FROM agg")
+    with pytest.raises(AttributeError):
+        c.sql("CREATE TABLE nope WITH (format = 'parquet')")                    # location is mandatory
