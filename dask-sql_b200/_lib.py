@@ -94,6 +94,8 @@ _lib.b2_stats_ws_bytes.restype = C.c_int64
 _lib.b2_scan_agg_ws_bytes.restype = C.c_int64
 _lib.b2_join_onepass_ws_bytes.restype = C.c_int64
 _lib.b2_join_onepass_ws_bytes.argtypes = [C.c_int64]
+_lib.b2_range_partition_ws_bytes.restype = C.c_int64
+_lib.b2_range_partition_ws_bytes.argtypes = [C.c_int32]
 _lib.b2_f64_to_ordered.restype = C.c_int64
 _lib.b2_f64_to_ordered.argtypes = [C.c_double]
 _lib.b2_ordered_to_f64.restype = C.c_double
@@ -136,6 +138,8 @@ _SIGS = {
     "b2_join_onepass": [C.POINTER(Scan), C.POINTER(C.c_int32), C.POINTER(JoinTable), C.c_int32, C.c_int32, _P, C.c_int32,
                         C.POINTER(C.c_int32), C.POINTER(_P), C.POINTER(_P), C.c_int32, C.POINTER(Col),
                         C.POINTER(C.c_int64), C.POINTER(_P), C.POINTER(_P), _P],
+    "b2_range_partition": [C.POINTER(Scan), C.c_int32, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
+                           C.POINTER(C.c_int32), _P, C.POINTER(_P), _P, _P],
     "b2_iota": [_P, C.c_int64, _P],
     "b2_bitmap_or": [_P, _P, C.c_int64, _P],
     "b2_sort_by": [C.POINTER(Col), C.c_int64, C.c_int32, C.c_int32, _P, _P, _P],
@@ -149,7 +153,7 @@ _SIGS = {
 }
 
 EXPORTS = sorted(list(_SIGS) + ["b2_last_error", "b2_num_tiles", "b2_stats_ws_bytes", "b2_scan_agg_ws_bytes",
-                                "b2_sort_ws_bytes", "b2_join_onepass_ws_bytes",
+                                "b2_sort_ws_bytes", "b2_join_onepass_ws_bytes", "b2_range_partition_ws_bytes",
                                 "b2_f64_to_ordered", "b2_ordered_to_f64"])
 
 
@@ -191,6 +195,8 @@ join_write_gather_keyed = _wrap("b2_join_write_gather_keyed")
 join_key_layout = _wrap("b2_join_key_layout")
 join_onepass = _wrap("b2_join_onepass")
 join_onepass_ws_bytes = _lib.b2_join_onepass_ws_bytes
+range_partition = _wrap("b2_range_partition")
+range_partition_ws_bytes = _lib.b2_range_partition_ws_bytes
 iota = _wrap("b2_iota")
 bitmap_or = _wrap("b2_bitmap_or")
 sort_by = _wrap("b2_sort_by")

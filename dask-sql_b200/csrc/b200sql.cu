@@ -36,6 +36,7 @@ int b2_sm_count() {
 #include "groupby.cuh"
 #include "join.cuh"
 #include "sort.cuh"
+#include "partition.cuh"
 
 extern "C" {
 

@@ -1,0 +1,176 @@
+// partition.cuh — range partitioning of (group key, aggregate inputs) for group tables far beyond L2.
+//
+// A direct-address group table of 100M slots (C5) is 0.8 GB per accumulator array: every atomic of
+// b2_groupby_dense is then a random DRAM read-modify-write (measured 52 ms for 500M rows).  Rows are
+// therefore first reordered by key range so that all rows of one bucket -- whose slice of the table
+// is a few tens of MB -- are contiguous; b2_groupby_dense over the reordered arrays then walks the
+// buckets in order and its atomics stay L2-resident.  Three launches, no host round trip:
+//   b2_part_hist_kernel    rows per bucket (key + predicate columns only)
+//   b2_part_scan_kernel    bucket starts, write cursors
+//   b2_part_scatter_kernel per 2048-row tile: shared-memory ranks, one global reservation per
+//                          (tile, bucket), then key' = kmin + slot and the carried columns are
+//                          written to their bucket's region
+// Rows that fail the scan's terms are dropped; a NULL key goes to slot nslots-1 (encoded as the key
+// value kmin + nslots - 1, so the consumer runs with one slot more and no bitmap).
+#pragma once
+#include "common.cuh"
+
+#define B2_PART_R 8
+#define B2_PART_TILE (B2_BLOCK * B2_PART_R)
+#define B2_PART_MAX_BUCKETS 1024
+
+struct b2_partcarry_arg {
+  int32_t n;
+  int32_t cols[B2_MAX_GATHER];
+  void* out[B2_MAX_GATHER];
+};
+
+// slots of the batch (-1 = row does not take part)
+template <int R>
+__device__ __forceinline__ void b2_part_slots(const b2_scan_t& s, int key_col, int64_t kmin, int64_t nslots,
+                                              int64_t row0, int64_t (&slot)[R]) {
+  const b2_col_t& kc = s.cols[key_col];
+  bool full;
+  const uint32_t bits = b2_eval_terms<R>(s, row0, full);
+  int64_t key[R];
+  b2_load_batch<R>(kc, row0, bits, full, key);
+  uint32_t kvalid = bits;
+  if (kc.valid) kvalid = b2_valid_bits<R>(kc.valid, row0, bits);
+#pragma unroll
+  for (int j = 0; j < R; ++j) {
+    slot[j] = -1;
+    if ((bits >> j) & 1) {
+      if (!((kvalid >> j) & 1)) slot[j] = nslots - 1;
+      else {
+        const uint64_t d = (uint64_t)key[j] - (uint64_t)kmin;
+        slot[j] = d < (uint64_t)(nslots - 1) ? (int64_t)d : -1;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(B2_BLOCK)
+b2_part_hist_kernel(const __grid_constant__ b2_scan_t s, int key_col, int64_t kmin, int64_t nslots, int shift,
+                    int nbuckets, int64_t ntiles, unsigned long long* __restrict__ counts) {
+  __shared__ int hist[B2_PART_MAX_BUCKETS];
+  for (int b = threadIdx.x; b < nbuckets; b += B2_BLOCK) hist[b] = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t row0 = tile * B2_PART_TILE + (int64_t)warp * (32 * B2_PART_R) + lane;
+    int64_t slot[B2_PART_R];
+    b2_part_slots<B2_PART_R>(s, key_col, kmin, nslots, row0, slot);
+#pragma unroll
+    for (int j = 0; j < B2_PART_R; ++j)
+      if (slot[j] >= 0) atomicAdd(&hist[(int)(slot[j] >> shift)], 1);
+  }
+  __syncthreads();
+  for (int b = threadIdx.x; b < nbuckets; b += B2_BLOCK)
+    if (hist[b]) atomicAdd(counts + b, (unsigned long long)hist[b]);
+}
+
+// ws: [0, nb] bucket starts (in: counts), [nb+1, 2nb] write cursors
+__global__ void b2_part_scan_kernel(int64_t* __restrict__ ws, int nbuckets) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  int64_t run = 0;
+  for (int b = 0; b < nbuckets; ++b) {
+    const int64_t c = ws[b];
+    ws[b] = run;
+    ws[nbuckets + 1 + b] = run;
+    run += c;
+  }
+  ws[nbuckets] = run;
+}
+
+__global__ void __launch_bounds__(B2_BLOCK)
+b2_part_scatter_kernel(const __grid_constant__ b2_scan_t s, int key_col, int64_t kmin, int64_t nslots, int shift,
+                       int nbuckets, int64_t ntiles, unsigned long long* __restrict__ cursor,
+                       int64_t* __restrict__ out_key, const __grid_constant__ b2_partcarry_arg carry) {
+  __shared__ int hist[B2_PART_MAX_BUCKETS];
+  __shared__ long long base[B2_PART_MAX_BUCKETS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    for (int b = threadIdx.x; b < nbuckets; b += B2_BLOCK) hist[b] = 0;
+    __syncthreads();
+    const int64_t row0 = tile * B2_PART_TILE + (int64_t)warp * (32 * B2_PART_R) + lane;
+    int64_t slot[B2_PART_R];
+    int rank[B2_PART_R];
+    b2_part_slots<B2_PART_R>(s, key_col, kmin, nslots, row0, slot);
+    uint32_t live = 0;
+#pragma unroll
+    for (int j = 0; j < B2_PART_R; ++j) {
+      rank[j] = 0;
+      if (slot[j] >= 0) {
+        rank[j] = atomicAdd(&hist[(int)(slot[j] >> shift)], 1);
+        live |= 1u << j;
+      }
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < nbuckets; b += B2_BLOCK)
+      base[b] = hist[b] ? (long long)atomicAdd(cursor + b, (unsigned long long)hist[b]) : 0;
+    __syncthreads();
+    int64_t dst[B2_PART_R];
+#pragma unroll
+    for (int j = 0; j < B2_PART_R; ++j) {
+      dst[j] = 0;
+      if ((live >> j) & 1) {
+        dst[j] = base[(int)(slot[j] >> shift)] + rank[j];
+        b2_st_stream(out_key + dst[j], kmin + slot[j]);
+      }
+    }
+    for (int c = 0; c < carry.n; ++c) {
+      int64_t raw[B2_PART_R];
+      b2_load_batch64<B2_PART_R>(s.cols[carry.cols[c]].data, row0, live, false, raw);
+#pragma unroll
+      for (int j = 0; j < B2_PART_R; ++j)
+        if ((live >> j) & 1) b2_st_stream(reinterpret_cast<int64_t*>(carry.out[c]) + dst[j], raw[j]);
+    }
+    __syncthreads();   // hist / base are reused by the next tile
+  }
+}
+
+extern "C" {
+
+int64_t b2_range_partition_ws_bytes(int32_t nbuckets) { return 8 * (2 * (int64_t)nbuckets + 2); }
+
+int32_t b2_range_partition(const b2_scan_t* scan, int32_t key_col, int64_t kmin, int64_t nslots, int32_t shift,
+                           int32_t nbuckets, int32_t ncarry, const int32_t* carry_cols, int64_t* out_key,
+                           void* const* out_cols, void* d_ws, void* stream) {
+  int32_t rc = b2_check_scan(scan);
+  if (rc) return rc;
+  B2_REQUIRE(key_col >= 0 && key_col < scan->ncols && scan->cols[key_col].dtype == B2_I64, "range partition needs an int64 key");
+  B2_REQUIRE(nslots >= 2 && shift >= 0 && shift < 62, "bad slot range");
+  B2_REQUIRE(nbuckets >= 1 && nbuckets <= B2_PART_MAX_BUCKETS && ((nslots - 1) >> shift) < nbuckets, "bad bucket count");
+  B2_REQUIRE(ncarry >= 0 && ncarry <= B2_MAX_GATHER && out_key && d_ws, "bad arguments");
+  b2_partcarry_arg carry;
+  memset(&carry, 0, sizeof(carry));
+  carry.n = ncarry;
+  for (int c = 0; c < ncarry; ++c) {
+    B2_REQUIRE(carry_cols[c] >= 0 && carry_cols[c] < scan->ncols && out_cols[c], "bad carried column");
+    const b2_col_t& col = scan->cols[carry_cols[c]];
+    B2_REQUIRE(col.dtype != B2_U8 && !col.valid, "carried columns must be 8-byte columns without a validity bitmap");
+    carry.cols[c] = carry_cols[c];
+    carry.out[c] = out_cols[c];
+  }
+  const int64_t ntiles = (scan->n + B2_PART_TILE - 1) / B2_PART_TILE;
+  cudaStream_t st = (cudaStream_t)stream;
+  int64_t* ws = reinterpret_cast<int64_t*>(d_ws);
+  if (ntiles > 0) {
+    int grid = b2_wave_grid(b2_part_hist_kernel, B2_BLOCK, ntiles);
+    b2_part_hist_kernel<<<grid, B2_BLOCK, 0, st>>>(*scan, key_col, kmin, nslots, shift, nbuckets, ntiles,
+                                                   reinterpret_cast<unsigned long long*>(ws));
+    B2_CHECK_LAUNCH("b2_part_hist_kernel");
+  }
+  b2_part_scan_kernel<<<1, 32, 0, st>>>(ws, nbuckets);
+  B2_CHECK_LAUNCH("b2_part_scan_kernel");
+  if (ntiles > 0) {
+    int grid = b2_wave_grid(b2_part_scatter_kernel, B2_BLOCK, ntiles);
+    b2_part_scatter_kernel<<<grid, B2_BLOCK, 0, st>>>(*scan, key_col, kmin, nslots, shift, nbuckets, ntiles,
+                                                      reinterpret_cast<unsigned long long*>(ws + nbuckets + 1), out_key,
+                                                      carry);
+    B2_CHECK_LAUNCH("b2_part_scatter_kernel");
+  }
+  return B2_OK;
+}
+
+}  // extern "C"

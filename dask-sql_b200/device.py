@@ -315,12 +315,11 @@ def select(scan: L.Scan, device, gather_cols: Sequence[int] = (), want_idx=True,
         outs.append(torch.empty(total, dtype=_TORCH_DTYPE[c.dtype], device=device))
         ovalid.append(torch.zeros(bitmap_words(total), dtype=torch.int32, device=device) if c.valid is not None else None)
     k = len(gather_cols)
-    if total > 0 or True:
+    if total > 0:
         gc = (C.c_int32 * max(1, k))(*gather_cols)
-        od = (C.c_void_p * max(1, k))(*[o.data_ptr() if o.numel() else 0 for o in outs])
-        ov = (C.c_void_p * max(1, k))(*[(v.data_ptr() if v is not None and v.numel() else 0) for v in ovalid])
-        if total > 0:
-            L.select_write(C.byref(scan), ptr(tile_off), ptr(idx), k, gc, od, ov, stream_ptr())
+        od = (C.c_void_p * max(1, k))(*[o.data_ptr() for o in outs])
+        ov = (C.c_void_p * max(1, k))(*[(v.data_ptr() if v is not None else 0) for v in ovalid])
+        L.select_write(C.byref(scan), ptr(tile_off), ptr(idx), k, gc, od, ov, stream_ptr())
     res = [DeviceColumn(o, v, cols[g].dtype, cols[g].logical) for o, v, g in zip(outs, ovalid, gather_cols)]
     return idx, res, total
 

@@ -34,7 +34,7 @@ _LOGICAL = {I64: "int64", F64: "float64", U8: "bool"}
 
 # counters the bench / tests read to prove which kernels ran
 stats = {"launches": 0, "star_fused": 0, "dense_groupby": 0, "hash_groupby": 0, "dense_join": 0,
-         "chain_join": 0, "keyed_join": 0, "h2d_bytes": 0, "d2h_bytes": 0}
+         "chain_join": 0, "keyed_join": 0, "partitioned_groupby": 0, "h2d_bytes": 0, "d2h_bytes": 0}
 
 
 # Optional per-launch timing of the dominant kernels (bench.py sets this to a list): each entry
@@ -754,15 +754,43 @@ def grouped_aggregate(parts, pred, gexprs, gnames, plan: AggPlan, child, sharded
     if mode == "dense":
         stats["dense_groupby"] += 1
         nslots = rng + 1
-        gs = GroupState(dev, nslots, plan, need_present=True)
+        work = []
         for part in parts:
             if part.n == 0:
                 continue
             ctx = ScanCtx(part, pred)
             kslot = ctx.slot(gexprs[0])
-            gs.bind(ctx)
-            stats["launches"] += 1
-            D.groupby_dense(ctx.scan(), kslot, kmin, gs.table)
+            work.append((part, ctx, kslot, [ctx.slot(ka.expr) for ka in plan.kaggs]))
+        buckets = _partition_plan(nslots, plan, work, total_rows)
+        if buckets is not None:
+            # table far beyond L2: reorder (key, inputs) by key range first so the atomics of the
+            # aggregation pass stay inside one L2-sized slice of the table at a time
+            stats["partitioned_groupby"] += 1
+            shift, nbuckets = buckets
+            gs = GroupState(dev, nslots + 1, plan, need_present=True)      # +1: see b2_range_partition
+            for part, ctx, kslot, vslots in work:
+                carried = sorted(set(vslots))
+                n = part.n
+                out_key = torch.full((n,), kmin + nslots + 1, dtype=torch.int64, device=dev)
+                outs = [torch.empty(n, dtype=_TORCH_DT[ctx.cols[c].dtype], device=dev) for c in carried]
+                ws = torch.zeros(L.range_partition_ws_bytes(nbuckets) // 8, dtype=torch.int64, device=dev)
+                cc = (C.c_int32 * max(1, len(carried)))(*carried)
+                oc = (C.c_void_p * max(1, len(carried)))(*[o.data_ptr() for o in outs])
+                stats["launches"] += 3
+                L.range_partition(C.byref(ctx.scan()), kslot, kmin, nslots, shift, nbuckets, len(carried), cc,
+                                  D.ptr(out_key), oc, D.ptr(ws), D.stream_ptr())
+                cols2 = [DeviceColumn(out_key, None, I64)] + \
+                        [DeviceColumn(o, None, ctx.cols[c].dtype) for o, c in zip(outs, carried)]
+                specs = [(1 + carried.index(v), ka.op) for v, ka in zip(vslots, plan.kaggs)]
+                gs.table.specs, gs.table.aggs = specs, D.make_aggs(specs)
+                stats["launches"] += 1
+                D.groupby_dense(D.make_scan(cols2, [], n), 0, kmin, gs.table)
+        else:
+            gs = GroupState(dev, nslots, plan, need_present=True)
+            for part, ctx, kslot, _ in work:
+                gs.bind(ctx)
+                stats["launches"] += 1
+                D.groupby_dense(ctx.scan(), kslot, kmin, gs.table)
         if sharded:
             _allreduce_table(gs.table, plan)
         key_nullable = E.may_be_null(gexprs[0], lambda n: any(n in p and p[n].valid is not None for p in parts))
@@ -806,6 +834,35 @@ def grouped_aggregate(parts, pred, gexprs, gnames, plan: AggPlan, child, sharded
         from .merge import tree_merge_raw
         raw = tree_merge_raw(raw, plan, options, dev)
     return finish(raw, plan)
+
+
+PARTITION_MIN_TABLE_BYTES = 256 << 20     # below this the table (mostly) lives in the 126 MB L2 anyway
+PARTITION_BUCKET_BYTES = 24 << 20         # slice of the group table touched by one bucket
+
+
+def _partition_plan(nslots, plan: AggPlan, work, total_rows):
+    """(shift, nbuckets) for b2_range_partition, or None when the dense table is small enough for
+    L2, the inputs are not plain 8-byte columns, or there are too few rows to pay for the extra pass."""
+    if os.environ.get("B200SQL_NO_PARTITION") == "1" or not work:
+        return None
+    per_slot = 8 * (sum(1 for k in plan.kaggs if k.op != L.AGG_COUNT) + sum(1 for k in plan.kaggs if k.need_cnt)
+                    + (1 if plan.need_rows else 0))
+    min_bytes = int(os.environ.get("B200SQL_PARTITION_MIN_BYTES", PARTITION_MIN_TABLE_BYTES))
+    if per_slot == 0 or nslots * per_slot < min_bytes or total_rows * 4 < nslots:
+        return None
+    if len({v for _, _, _, vs in work for v in vs}) > L.MAX_GATHER:
+        return None
+    for part, ctx, kslot, vslots in work:
+        if ctx.cols[kslot].dtype != I64:
+            return None
+        for v in vslots:
+            if ctx.cols[v].dtype == U8 or ctx.cols[v].valid is not None:
+                return None
+    bucket_bytes = int(os.environ.get("B200SQL_PARTITION_BUCKET_BYTES", PARTITION_BUCKET_BYTES))
+    shift = max(0, (max(1, bucket_bytes // per_slot)).bit_length() - 1)
+    while ((nslots - 1) >> shift) + 1 > 1024:
+        shift += 1
+    return shift, ((nslots - 1) >> shift) + 1
 
 
 def _allreduce_table(table: D.GroupTable, plan: AggPlan):

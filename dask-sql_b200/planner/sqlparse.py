@@ -390,8 +390,10 @@ class Parser:
                     e = Node("istrue", e=e, negated=neg, value=True)
                 elif self.eat_kw("FALSE"):
                     e = Node("istrue", e=e, negated=neg, value=False)
+                elif self.eat_word("UNKNOWN"):      # a boolean is UNKNOWN iff it is NULL (call.py:1123-1124)
+                    e = Node("isnull", e=e, negated=neg)
                 else:
-                    self.error("Expected NULL, TRUE or FALSE after IS")
+                    self.error("Expected NULL, TRUE, FALSE or UNKNOWN after IS")
             elif self.at_kw("NOT") and self.toks[self.i + 1].kind == "kw" and self.toks[self.i + 1].val in ("BETWEEN", "IN"):
                 self.i += 1
                 e = self._between_or_in(e, True)

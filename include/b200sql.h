@@ -350,6 +350,24 @@ int32_t b2_join_onepass(const b2_scan_t* scan, const int32_t* probe_keys, const 
                         const b2_col_t* build_cols, const int64_t* build_base, void* const* build_out,
                         uint32_t* const* build_valid, void* stream);
 
+/* ---- group tables far beyond L2 (C5: 100M keys) ----------------------------------------------- */
+/* Reorder the rows of `scan` that pass its terms by key RANGE, so that b2_groupby_dense over the
+ * reordered arrays touches one L2-sized slice of the group table after the other (instead of a random
+ * DRAM read-modify-write per row).  bucket = slot >> shift with slot = key - kmin (NULL key ->
+ * nslots-1, the NULL slot of b2_groupby_dense), nbuckets <= 1024 and > (nslots-1) >> shift.
+ *   out_key[i]      = kmin + slot   (int64, no bitmap: run the consumer with nslots+1 slots)
+ *   out_cols[c][i]  = scan.cols[carry_cols[c]] of the same row (8-byte columns without bitmap)
+ * All outputs are caller-allocated with scan.n rows; rows past the number of passing rows are left
+ * untouched (pre-fill out_key with an out-of-range key, e.g. kmin + nslots + 1, so the consumer
+ * ignores them).  d_ws: b2_range_partition_ws_bytes(nbuckets) bytes, ZEROED; afterwards
+ * ws[0..nbuckets] are the bucket starts (ws[nbuckets] = rows written).  No host round trip.
+ * Replaces nothing in the reference (pandas' groupby hashes in place); it is what makes
+ * aggregate.py:522-589 on 100M groups stream instead of thrash. */
+int64_t b2_range_partition_ws_bytes(int32_t nbuckets);
+int32_t b2_range_partition(const b2_scan_t* scan, int32_t key_col, int64_t kmin, int64_t nslots, int32_t shift,
+                           int32_t nbuckets, int32_t ncarry, const int32_t* carry_cols, int64_t* out_key,
+                           void* const* out_cols, void* d_ws, void* stream);
+
 /* ---- ORDER BY ("next" row of the scope: the tail of TPC-H Q3) ------------------------------- */
 /* Stable LSD radix sort of row ids by one key column.  idx = int32[n] permutation (b2_iota for the
  * identity) reordered in place so that col[idx[i]] is sorted (descending != 0: DESC; nulls_first

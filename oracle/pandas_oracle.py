@@ -29,6 +29,48 @@ import pandas as pd
 
 
 # ---------------------------------------------------------------------------------------------
+# expressions — dask_sql/physical/rex/core/call.py (the operator table OPERATION_MAPPING :1047-1216)
+# ---------------------------------------------------------------------------------------------
+def rex_reduce(op: Callable, *operands):
+    """ReduceOperation.reduce (call.py:140-162): n-ary operators fold left over their operands."""
+    return reduce(op, operands) if len(operands) > 1 else op(*operands)
+
+
+def rex_sql_div(lhs, rhs, output_is_float: bool):
+    """SQLDivisionOperator.div (call.py:165-189): true division, truncated (NOT floored) when the
+    SQL result type is an integer type."""
+    result = lhs / rhs
+    return result if output_is_float else np.trunc(result)
+
+
+def rex_not(x):
+    """NotOperation (call.py:348-364)."""
+    return ~(x.astype("boolean")) if isinstance(x, pd.Series) else (not x)
+
+
+def rex_is_null(x):
+    """IsNullOperation (call.py:367-383)."""
+    return x.isna() if isinstance(x, pd.Series) else bool(pd.isna(x))
+
+
+def rex_is_true(x):
+    """IsTrueOperation (call.py:315-332): NULL -> False."""
+    return x.astype("boolean").fillna(False)
+
+
+def rex_is_false(x):
+    """IsFalseOperation (call.py:295-312): NULL -> False."""
+    return ~x.astype("boolean").fillna(True)
+
+
+REX_BINARY = {  # call.py:1050-1062
+    "and": operator.and_, "or": operator.or_, ">": operator.gt, ">=": operator.ge, "<": operator.lt,
+    "<=": operator.le, "=": operator.eq, "<>": operator.ne, "+": operator.add, "-": operator.sub,
+    "*": operator.mul,
+}
+
+
+# ---------------------------------------------------------------------------------------------
 # filter  — dask_sql/physical/rel/logical/filter.py:20-45, table_scan.py:80-119
 # ---------------------------------------------------------------------------------------------
 def filter_or_scalar(df: pd.DataFrame, cond) -> pd.DataFrame:

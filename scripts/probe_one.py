@@ -1,4 +1,4 @@
-"""Run one BASELINE config repeatedly (for launch lists / event timing).  usage: probe_one.py c1|c2|c2i|c3|c4|c5 rows reps [nparts]"""
+"""Run one BASELINE config repeatedly (for launch lists / event timing).  usage: probe_one.py c1|c2|c2i|c3|c4|c5 rows reps [nparts]  (env knobs apply)"""
 import sys, os, time, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch

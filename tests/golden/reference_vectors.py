@@ -143,6 +143,43 @@ CASES = [
 ]
 
 
+def _bool_table():          # tests/integration/test_rex.py:457-461
+    return pd.DataFrame({"b": pd.array([True, False, pd.NA], dtype="boolean")})
+
+
+def _operators_expected(t):  # tests/integration/test_rex.py:223-235
+    d = t["df"]
+    e = pd.DataFrame(index=d.index)
+    e["m"], e["u"], e["q"], e["s"], e["d"] = d["a"] * d["b"], -d["a"], d["a"] / d["b"], d["a"] + d["b"], d["a"] - d["b"]
+    e["e"], e["g"], e["ge"] = d["a"] == d["b"], d["a"] > d["b"], d["a"] >= d["b"]
+    e["l"], e["le"], e["n"] = d["a"] < d["b"], d["a"] <= d["b"], d["a"] != d["b"]
+    return e
+
+
+CASES += [
+    # ---- expressions (predicate / pre-projection arithmetic of the path) --------------------
+    dict(name="rex_operators", cite="tests/integration/test_rex.py:205-236", tables=["df"],
+         sql="SELECT a * b AS m, -a AS u, a / b AS q, a + b AS s, a - b AS d, a = b AS e, a > b AS g, "
+             "a >= b AS ge, a < b AS l, a <= b AS le, a <> b AS n FROM df",
+         expected=_operators_expected, float_cols=["m", "u", "q", "s", "d"]),
+    dict(name="rex_null", cite="tests/integration/test_rex.py:363-377", tables=["user_table_nan"],
+         sql="SELECT c IS NOT NULL AS nn, c IS NULL AS n FROM user_table_nan",
+         expected=pd.DataFrame({"nn": [True, False, True], "n": [False, True, False]})),
+    dict(name="rex_integer_div", cite="tests/integration/test_rex.py:548-568", tables=["df_simple"],
+         sql="SELECT 1 / a AS a, a / 2 AS b, 1.0 / a AS c FROM df_simple",
+         expected=lambda t: pd.DataFrame({"a": (1 // t["df_simple"].a).astype("Int64"),
+                                          "b": (t["df_simple"].a // 2).astype("Int64"),
+                                          "c": 1 / t["df_simple"].a}), float_cols=["c"]),
+    dict(name="rex_boolean_operations", cite="tests/integration/test_rex.py:456-485",
+         inline_tables={"df": _bool_table()},
+         sql="SELECT b IS TRUE AS t, b IS FALSE AS f, b IS NOT TRUE AS nt, b IS NOT FALSE AS nf, "
+             "b IS UNKNOWN AS u, b IS NOT UNKNOWN AS nu FROM df",
+         expected=lambda t: pd.DataFrame({"t": t["df"].b.fillna(False), "f": ~t["df"].b.fillna(True),
+                                          "nt": ~t["df"].b.fillna(False), "nf": t["df"].b.fillna(True),
+                                          "u": t["df"].b.isna(), "nu": ~t["df"].b.isna()})),
+]
+
+
 def tables_of(case):
     t = {n: FIXTURES[n]() for n in case.get("tables", [])}
     t.update(case.get("inline_tables", {}))

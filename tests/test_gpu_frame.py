@@ -409,3 +409,41 @@ def test_join_single_pass_lookback_equals_two_pass(how, match, monkeypatch):
     exp = O.join_on_columns(fact[fact["x"] > -3], dim, ["fk"], ["pk"], how)
     assert len(got) == len(exp)
     assert_frames(got[list(exp.columns)], exp, sort_by=["fk", "v"])
+
+
+@pytest.mark.parametrize("nullable_key", [False, True])
+def test_groupby_range_partitioned_matches_direct(nullable_key, monkeypatch):
+    """Group tables far beyond L2 are fed by b2_range_partition (rows reordered by key range, then the
+    same dense kernel).  Forced here on a small table: many buckets, a pushed-down predicate, NULL
+    keys, several aggregates sharing inputs, float NaNs as NULL inputs."""
+    from dask_sql_b200 import executor
+    rng = np.random.default_rng(51)
+    n, nkeys = 300_007, 5_000
+    key = rng.integers(100, 100 + nkeys, n)
+    df = pd.DataFrame({
+        "key": pd.array(np.where(rng.random(n) < 0.02, None, key), dtype="Int64") if nullable_key else key,
+        "v": rng.random(n),
+        "w": rng.integers(-100, 100, n),
+        "g": np.where(rng.random(n) < 0.1, np.nan, rng.random(n)),
+        "x": rng.integers(0, 10, n),
+    })
+    spec = [("v", "sv", "sum"), ("w", "sw", "sum"), ("v", "av", "mean"), ("g", "cg", "count"), ("g", "sg", "sum"),
+            ("w", "mn", "min"), ("v", "mx", "max"), (None, "n", "size")]
+
+    def run():
+        f = _table(df, 3)
+        return agg(f[f["x"] > 2], ["key"], spec)
+
+    direct = run()
+    monkeypatch.setenv("B200SQL_PARTITION_MIN_BYTES", "1")
+    monkeypatch.setenv("B200SQL_PARTITION_BUCKET_BYTES", "8192")
+    before = executor.stats["partitioned_groupby"]
+    parted = run()
+    assert executor.stats["partitioned_groupby"] == before + 1
+    fl = ("sv", "av", "sg")
+    assert_frames(parted, direct, float_cols=fl, sort_by=["key"])
+    d = df[df["x"] > 2]
+    exp = d.groupby("key", dropna=False).agg(sv=("v", "sum"), sw=("w", "sum"), av=("v", "mean"), cg=("g", "count"),
+                                             sg=("g", lambda s: s.sum(min_count=1)), mn=("w", "min"),
+                                             mx=("v", "max"), n=("v", "size")).reset_index()
+    assert_frames(parted, exp, float_cols=fl, sort_by=["key"])

@@ -152,3 +152,41 @@ def test_q3_restatement_matches_sqlite():
     exp = pd.read_sql("SELECT SUM(x) FROM fact WHERE x > 0", con)
     got = O.c1_filter_sum(O.split(fact[["x"]], 3))
     assert int(got.iloc[0, 0]) == int(exp.iloc[0, 0])
+
+
+def test_rex_operator_cases():
+    """The operator restatement (oracle rex_*; call.py:140-189, 295-383, 1047-1062) against the
+    reference's expression tests."""
+    c = CASE["rex_operators"]
+    t = G.tables_of(c)
+    d = t["df"]
+    B = O.REX_BINARY
+    got = pd.DataFrame({
+        "m": O.rex_reduce(B["*"], d.a, d.b), "u": -d.a, "q": O.rex_sql_div(d.a, d.b, True),
+        "s": O.rex_reduce(B["+"], d.a, d.b), "d": O.rex_reduce(B["-"], d.a, d.b),
+        "e": O.rex_reduce(B["="], d.a, d.b), "g": O.rex_reduce(B[">"], d.a, d.b),
+        "ge": O.rex_reduce(B[">="], d.a, d.b), "l": O.rex_reduce(B["<"], d.a, d.b),
+        "le": O.rex_reduce(B["<="], d.a, d.b), "n": O.rex_reduce(B["<>"], d.a, d.b)})
+    _cmp(got, G.expected_of(c, t), c["float_cols"])
+
+    nan = G.user_table_nan()
+    _cmp(pd.DataFrame({"nn": O.rex_not(O.rex_is_null(nan.c)), "n": O.rex_is_null(nan.c)}), CASE["rex_null"]["expected"])
+
+    c = CASE["rex_integer_div"]
+    t = G.tables_of(c)
+    a = t["df_simple"].a
+    got = pd.DataFrame({"a": O.rex_sql_div(1, a, False), "b": O.rex_sql_div(a, 2, False), "c": O.rex_sql_div(1.0, a, True)})
+    _cmp(got, G.expected_of(c, t), ["c"])
+    # truncation, not floor (the docstring example of SQLDivisionOperator: -1 / 2 = 0)
+    assert O.rex_sql_div(pd.Series([-1, -7, 7]), 2, False).tolist() == [-0.0, -3.0, 3.0]
+
+    c = CASE["rex_boolean_operations"]
+    t = G.tables_of(c)
+    b = t["df"].b
+    got = pd.DataFrame({"t": O.rex_is_true(b), "f": O.rex_is_false(b), "nt": O.rex_not(O.rex_is_true(b)),
+                        "nf": O.rex_not(O.rex_is_false(b)), "u": O.rex_is_null(b), "nu": O.rex_not(O.rex_is_null(b))})
+    _cmp(got, G.expected_of(c, t))
+    # n-ary reduce (tests/unit/test_call.py:130-153: and / or / >= / + over several operands)
+    s1, s2, s3 = pd.Series([1, 2, 3]), pd.Series([3, 2, 1]), pd.Series([1, 1, 1])
+    assert O.rex_reduce(O.REX_BINARY["+"], s1, s2, s3).tolist() == [5, 5, 5]
+    assert O.rex_reduce(O.REX_BINARY["and"], s1 > 1, s2 > 1, s3 > 0).tolist() == [False, True, False]
