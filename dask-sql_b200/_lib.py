@@ -138,6 +138,10 @@ _SIGS = {
     "b2_join_onepass": [C.POINTER(Scan), C.POINTER(C.c_int32), C.POINTER(JoinTable), C.c_int32, C.c_int32, _P, C.c_int32,
                         C.POINTER(C.c_int32), C.POINTER(_P), C.POINTER(_P), C.c_int32, C.POINTER(Col),
                         C.POINTER(C.c_int64), C.POINTER(_P), C.POINTER(_P), _P],
+    "b2_range_partition_hist": [C.POINTER(Scan), C.c_int32, C.c_int64, C.c_int64, C.c_int32, C.c_int32, _P, _P],
+    "b2_range_partition_scan": [C.c_int32, _P, _P],
+    "b2_range_partition_scatter": [C.POINTER(Scan), C.c_int32, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
+                                   C.POINTER(C.c_int32), _P, C.POINTER(_P), _P, _P],
     "b2_range_partition": [C.POINTER(Scan), C.c_int32, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
                            C.POINTER(C.c_int32), _P, C.POINTER(_P), _P, _P],
     "b2_iota": [_P, C.c_int64, _P],
@@ -196,6 +200,9 @@ join_key_layout = _wrap("b2_join_key_layout")
 join_onepass = _wrap("b2_join_onepass")
 join_onepass_ws_bytes = _lib.b2_join_onepass_ws_bytes
 range_partition = _wrap("b2_range_partition")
+range_partition_hist = _wrap("b2_range_partition_hist")
+range_partition_scan = _wrap("b2_range_partition_scan")
+range_partition_scatter = _wrap("b2_range_partition_scatter")
 range_partition_ws_bytes = _lib.b2_range_partition_ws_bytes
 iota = _wrap("b2_iota")
 bitmap_or = _wrap("b2_bitmap_or")

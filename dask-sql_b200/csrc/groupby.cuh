@@ -12,9 +12,14 @@
 #define B2_MAX_PROBE 1024
 
 // ---- dense ------------------------------------------------------------------------------
+__device__ __forceinline__ void b2_prefetch_l2_keep(const void* p) {
+  asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(p));
+}
+
 template <class LD>
 __device__ __forceinline__ void b2_dense_body(const b2_scan_t& s, const LD& ld, int key_col, int64_t kmin,
-                                              int64_t nslots, const b2_aggs_arg& aggs, const b2_aggstate_t& st) {
+                                              int64_t nslots, const b2_aggs_arg& aggs, const b2_aggstate_t& st,
+                                              int touch = 0) {
   const b2_col_t& kc = s.cols[key_col];
   bool full;
   const uint32_t bits = b2_eval_terms<B2_GB_R>(s, ld, full);
@@ -34,6 +39,20 @@ __device__ __forceinline__ void b2_dense_body(const b2_scan_t& s, const LD& ld, 
       }
     }
   }
+  if (touch) {
+    // tables far beyond L2: an atomic that misses L2 is executed as a DRAM read-modify-write without
+    // leaving the line behind, so even range-ordered input (partition.cuh) would pay DRAM for every
+    // row.  A prefetch allocates the sector first; the rows that follow in the same slice then hit.
+#pragma unroll
+    for (int j = 0; j < B2_GB_R; ++j) {
+      if (slot[j] < 0) continue;
+      if (st.rows) b2_prefetch_l2_keep(st.rows + slot[j]);
+      for (int a = 0; a < aggs.n; ++a) {
+        if (st.acc[a]) b2_prefetch_l2_keep(reinterpret_cast<const int64_t*>(st.acc[a]) + slot[j]);
+        if (st.cnt[a]) b2_prefetch_l2_keep(st.cnt[a] + slot[j]);
+      }
+    }
+  }
   b2_apply_aggs<B2_GB_R>(s, ld, aggs.a, aggs.n, st, slot);
 }
 
@@ -41,8 +60,8 @@ template <bool PIPE>
 __global__ void __launch_bounds__(PIPE ? B2_PIPE_THREADS : B2_BLOCK)
 b2_groupby_dense_kernel(const __grid_constant__ b2_scan_t s, const __grid_constant__ b2_pipe_t pp, int key_col,
                         int64_t kmin, int64_t nslots, const __grid_constant__ b2_aggs_arg aggs,
-                        const __grid_constant__ b2_aggstate_t st) {
-  auto body = [&](const auto& ld) { b2_dense_body(s, ld, key_col, kmin, nslots, aggs, st); };
+                        const __grid_constant__ b2_aggstate_t st, int touch) {
+  auto body = [&](const auto& ld) { b2_dense_body(s, ld, key_col, kmin, nslots, aggs, st, touch); };
   if (PIPE) b2_tile_pipeline(s, pp, body);
   else b2_tile_direct<B2_GB_R>(s, body);
 }
@@ -370,15 +389,19 @@ int32_t b2_groupby_dense(const b2_scan_t* scan, int32_t key_col, int64_t kmin, i
   B2_REQUIRE(scan->cols[key_col].dtype == B2_I64 || scan->cols[key_col].dtype == B2_U8, "dense keys must be integers");
   B2_REQUIRE(nslots >= 2, "nslots must cover the key range plus the NULL slot");
   if (scan->n == 0) return B2_OK;
+  // pre-touch accumulator sectors when the table cannot live in L2 (see b2_dense_body);
+  // B200SQL_DENSE_TOUCH=0/1 overrides the size rule
+  int touch = nslots * 8 > (64LL << 20);
+  if (const char* e = getenv("B200SQL_DENSE_TOUCH")) touch = atoi(e) != 0;
   b2_pipe_t pp;
   b2_make_pipe(*scan, &pp);
   if (pp.enabled) {
     int grid = b2_pipe_grid(b2_groupby_dense_kernel<true>, pp, scan->n);
-    b2_groupby_dense_kernel<true><<<grid, B2_PIPE_THREADS, pp.smem_bytes, (cudaStream_t)stream>>>(*scan, pp, key_col, kmin, nslots, aa, *st);
+    b2_groupby_dense_kernel<true><<<grid, B2_PIPE_THREADS, pp.smem_bytes, (cudaStream_t)stream>>>(*scan, pp, key_col, kmin, nslots, aa, *st, touch);
   } else {
     int64_t nblk = (scan->n + B2_GB_ROWS_PER_BLOCK - 1) / B2_GB_ROWS_PER_BLOCK;
     int grid = b2_wave_grid(b2_groupby_dense_kernel<false>, B2_BLOCK, nblk);
-    b2_groupby_dense_kernel<false><<<grid, B2_BLOCK, 0, (cudaStream_t)stream>>>(*scan, pp, key_col, kmin, nslots, aa, *st);
+    b2_groupby_dense_kernel<false><<<grid, B2_BLOCK, 0, (cudaStream_t)stream>>>(*scan, pp, key_col, kmin, nslots, aa, *st, touch);
   }
   B2_CHECK_LAUNCH("b2_groupby_dense_kernel");
   return B2_OK;

@@ -82,50 +82,94 @@ __global__ void b2_part_scan_kernel(int64_t* __restrict__ ws, int nbuckets) {
   ws[nbuckets] = run;
 }
 
+// Scatter one 2048-row tile: ranks by shared-memory atomics, then the tile's rows are ordered by
+// bucket in shared memory (key' + source row + bucket id: 24 KB) so that consecutive threads write
+// consecutive output rows -- coalesced stores instead of 32 different sectors per store instruction.
+// The carried columns are gathered from the tile (16 KB per column, just read: L1/L2 hits).
 __global__ void __launch_bounds__(B2_BLOCK)
 b2_part_scatter_kernel(const __grid_constant__ b2_scan_t s, int key_col, int64_t kmin, int64_t nslots, int shift,
                        int nbuckets, int64_t ntiles, unsigned long long* __restrict__ cursor,
                        int64_t* __restrict__ out_key, const __grid_constant__ b2_partcarry_arg carry) {
-  __shared__ int hist[B2_PART_MAX_BUCKETS];
-  __shared__ long long base[B2_PART_MAX_BUCKETS];
+  __shared__ int hist[B2_PART_MAX_BUCKETS];          // rows of this tile per bucket
+  __shared__ int prefix[B2_PART_MAX_BUCKETS];        // exclusive scan of hist
+  __shared__ long long base[B2_PART_MAX_BUCKETS];    // first output row of this tile in each bucket
+  __shared__ int64_t st_key[B2_PART_TILE];
+  __shared__ uint16_t st_src[B2_PART_TILE];
+  __shared__ uint16_t st_bkt[B2_PART_TILE];
+  __shared__ int warp_tot[B2_WARPS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int PER = B2_PART_MAX_BUCKETS / B2_BLOCK;  // buckets per thread in the scan (4)
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     for (int b = threadIdx.x; b < nbuckets; b += B2_BLOCK) hist[b] = 0;
     __syncthreads();
-    const int64_t row0 = tile * B2_PART_TILE + (int64_t)warp * (32 * B2_PART_R) + lane;
+    const int local0 = warp * (32 * B2_PART_R) + lane;                 // row within the tile of batch row 0
+    const int64_t row0 = tile * B2_PART_TILE + local0;
     int64_t slot[B2_PART_R];
     int rank[B2_PART_R];
     b2_part_slots<B2_PART_R>(s, key_col, kmin, nslots, row0, slot);
-    uint32_t live = 0;
 #pragma unroll
     for (int j = 0; j < B2_PART_R; ++j) {
       rank[j] = 0;
-      if (slot[j] >= 0) {
-        rank[j] = atomicAdd(&hist[(int)(slot[j] >> shift)], 1);
-        live |= 1u << j;
+      if (slot[j] >= 0) rank[j] = atomicAdd(&hist[(int)(slot[j] >> shift)], 1);
+    }
+    __syncthreads();
+    // exclusive scan of hist[0..nbuckets) + one global reservation per non-empty bucket
+    {
+      int v[PER], tsum = 0;
+#pragma unroll
+      for (int k = 0; k < PER; ++k) {
+        const int b = threadIdx.x * PER + k;
+        v[k] = b < nbuckets ? hist[b] : 0;
+        tsum += v[k];
+      }
+      int incl = tsum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(FULL_MASK, incl, o);
+        if (lane >= o) incl += t;
+      }
+      if (lane == 31) warp_tot[warp] = incl;
+      __syncthreads();
+      int woff = 0;
+      for (int w = 0; w < warp; ++w) woff += warp_tot[w];
+      int run = woff + incl - tsum;
+#pragma unroll
+      for (int k = 0; k < PER; ++k) {
+        const int b = threadIdx.x * PER + k;
+        if (b < nbuckets) {
+          prefix[b] = run;
+          base[b] = v[k] ? (long long)atomicAdd(cursor + b, (unsigned long long)v[k]) : 0;
+          run += v[k];
+        }
       }
     }
     __syncthreads();
-    for (int b = threadIdx.x; b < nbuckets; b += B2_BLOCK)
-      base[b] = hist[b] ? (long long)atomicAdd(cursor + b, (unsigned long long)hist[b]) : 0;
-    __syncthreads();
-    int64_t dst[B2_PART_R];
+    int total = 0;
+    for (int w = 0; w < B2_WARPS; ++w) total += warp_tot[w];
+    // stage the tile in bucket order
 #pragma unroll
     for (int j = 0; j < B2_PART_R; ++j) {
-      dst[j] = 0;
-      if ((live >> j) & 1) {
-        dst[j] = base[(int)(slot[j] >> shift)] + rank[j];
-        b2_st_stream(out_key + dst[j], kmin + slot[j]);
+      if (slot[j] >= 0) {
+        const int b = (int)(slot[j] >> shift);
+        const int p = prefix[b] + rank[j];
+        st_key[p] = kmin + slot[j];
+        st_src[p] = (uint16_t)(local0 + j * 32);
+        st_bkt[p] = (uint16_t)b;
       }
     }
-    for (int c = 0; c < carry.n; ++c) {
-      int64_t raw[B2_PART_R];
-      b2_load_batch64<B2_PART_R>(s.cols[carry.cols[c]].data, row0, live, false, raw);
-#pragma unroll
-      for (int j = 0; j < B2_PART_R; ++j)
-        if ((live >> j) & 1) b2_st_stream(reinterpret_cast<int64_t*>(carry.out[c]) + dst[j], raw[j]);
+    __syncthreads();
+    const int64_t tile_row0 = tile * B2_PART_TILE;
+    for (int p = threadIdx.x; p < total; p += B2_BLOCK) {
+      const int b = st_bkt[p];
+      const int64_t dst = base[b] + (p - prefix[b]);
+      b2_st_stream(out_key + dst, st_key[p]);
+      const int64_t src = tile_row0 + st_src[p];
+      for (int c = 0; c < carry.n; ++c) {
+        const int64_t v = __ldg(reinterpret_cast<const long long*>(s.cols[carry.cols[c]].data) + src);
+        b2_st_stream(reinterpret_cast<int64_t*>(carry.out[c]) + dst, v);
+      }
     }
-    __syncthreads();   // hist / base are reused by the next tile
+    __syncthreads();   // shared arrays are reused by the next tile
   }
 }
 
@@ -133,15 +177,43 @@ extern "C" {
 
 int64_t b2_range_partition_ws_bytes(int32_t nbuckets) { return 8 * (2 * (int64_t)nbuckets + 2); }
 
-int32_t b2_range_partition(const b2_scan_t* scan, int32_t key_col, int64_t kmin, int64_t nslots, int32_t shift,
-                           int32_t nbuckets, int32_t ncarry, const int32_t* carry_cols, int64_t* out_key,
-                           void* const* out_cols, void* d_ws, void* stream) {
+static int32_t b2_part_check(const b2_scan_t* scan, int32_t key_col, int64_t nslots, int32_t shift, int32_t nbuckets,
+                             const void* d_ws) {
   int32_t rc = b2_check_scan(scan);
   if (rc) return rc;
   B2_REQUIRE(key_col >= 0 && key_col < scan->ncols && scan->cols[key_col].dtype == B2_I64, "range partition needs an int64 key");
   B2_REQUIRE(nslots >= 2 && shift >= 0 && shift < 62, "bad slot range");
   B2_REQUIRE(nbuckets >= 1 && nbuckets <= B2_PART_MAX_BUCKETS && ((nslots - 1) >> shift) < nbuckets, "bad bucket count");
-  B2_REQUIRE(ncarry >= 0 && ncarry <= B2_MAX_GATHER && out_key && d_ws, "bad arguments");
+  B2_REQUIRE(d_ws, "null workspace");
+  return B2_OK;
+}
+
+int32_t b2_range_partition_hist(const b2_scan_t* scan, int32_t key_col, int64_t kmin, int64_t nslots, int32_t shift,
+                                int32_t nbuckets, void* d_ws, void* stream) {
+  int32_t rc = b2_part_check(scan, key_col, nslots, shift, nbuckets, d_ws);
+  if (rc) return rc;
+  const int64_t ntiles = (scan->n + B2_PART_TILE - 1) / B2_PART_TILE;
+  if (ntiles <= 0) return B2_OK;
+  int grid = b2_wave_grid(b2_part_hist_kernel, B2_BLOCK, ntiles);
+  b2_part_hist_kernel<<<grid, B2_BLOCK, 0, (cudaStream_t)stream>>>(*scan, key_col, kmin, nslots, shift, nbuckets, ntiles,
+                                                                  reinterpret_cast<unsigned long long*>(d_ws));
+  B2_CHECK_LAUNCH("b2_part_hist_kernel");
+  return B2_OK;
+}
+
+int32_t b2_range_partition_scan(int32_t nbuckets, void* d_ws, void* stream) {
+  B2_REQUIRE(nbuckets >= 1 && nbuckets <= B2_PART_MAX_BUCKETS && d_ws, "bad arguments");
+  b2_part_scan_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(reinterpret_cast<int64_t*>(d_ws), nbuckets);
+  B2_CHECK_LAUNCH("b2_part_scan_kernel");
+  return B2_OK;
+}
+
+int32_t b2_range_partition_scatter(const b2_scan_t* scan, int32_t key_col, int64_t kmin, int64_t nslots, int32_t shift,
+                                   int32_t nbuckets, int32_t ncarry, const int32_t* carry_cols, int64_t* out_key,
+                                   void* const* out_cols, void* d_ws, void* stream) {
+  int32_t rc = b2_part_check(scan, key_col, nslots, shift, nbuckets, d_ws);
+  if (rc) return rc;
+  B2_REQUIRE(ncarry >= 0 && ncarry <= B2_MAX_GATHER && out_key, "bad arguments");
   b2_partcarry_arg carry;
   memset(&carry, 0, sizeof(carry));
   carry.n = ncarry;
@@ -153,24 +225,25 @@ int32_t b2_range_partition(const b2_scan_t* scan, int32_t key_col, int64_t kmin,
     carry.out[c] = out_cols[c];
   }
   const int64_t ntiles = (scan->n + B2_PART_TILE - 1) / B2_PART_TILE;
-  cudaStream_t st = (cudaStream_t)stream;
+  if (ntiles <= 0) return B2_OK;
   int64_t* ws = reinterpret_cast<int64_t*>(d_ws);
-  if (ntiles > 0) {
-    int grid = b2_wave_grid(b2_part_hist_kernel, B2_BLOCK, ntiles);
-    b2_part_hist_kernel<<<grid, B2_BLOCK, 0, st>>>(*scan, key_col, kmin, nslots, shift, nbuckets, ntiles,
-                                                   reinterpret_cast<unsigned long long*>(ws));
-    B2_CHECK_LAUNCH("b2_part_hist_kernel");
-  }
-  b2_part_scan_kernel<<<1, 32, 0, st>>>(ws, nbuckets);
-  B2_CHECK_LAUNCH("b2_part_scan_kernel");
-  if (ntiles > 0) {
-    int grid = b2_wave_grid(b2_part_scatter_kernel, B2_BLOCK, ntiles);
-    b2_part_scatter_kernel<<<grid, B2_BLOCK, 0, st>>>(*scan, key_col, kmin, nslots, shift, nbuckets, ntiles,
-                                                      reinterpret_cast<unsigned long long*>(ws + nbuckets + 1), out_key,
-                                                      carry);
-    B2_CHECK_LAUNCH("b2_part_scatter_kernel");
-  }
+  int grid = b2_wave_grid(b2_part_scatter_kernel, B2_BLOCK, ntiles);
+  b2_part_scatter_kernel<<<grid, B2_BLOCK, 0, (cudaStream_t)stream>>>(
+      *scan, key_col, kmin, nslots, shift, nbuckets, ntiles, reinterpret_cast<unsigned long long*>(ws + nbuckets + 1),
+      out_key, carry);
+  B2_CHECK_LAUNCH("b2_part_scatter_kernel");
   return B2_OK;
+}
+
+int32_t b2_range_partition(const b2_scan_t* scan, int32_t key_col, int64_t kmin, int64_t nslots, int32_t shift,
+                           int32_t nbuckets, int32_t ncarry, const int32_t* carry_cols, int64_t* out_key,
+                           void* const* out_cols, void* d_ws, void* stream) {
+  int32_t rc = b2_range_partition_hist(scan, key_col, kmin, nslots, shift, nbuckets, d_ws, stream);
+  if (rc) return rc;
+  rc = b2_range_partition_scan(nbuckets, d_ws, stream);
+  if (rc) return rc;
+  return b2_range_partition_scatter(scan, key_col, kmin, nslots, shift, nbuckets, ncarry, carry_cols, out_key,
+                                    out_cols, d_ws, stream);
 }
 
 }  // extern "C"

@@ -768,23 +768,33 @@ def grouped_aggregate(parts, pred, gexprs, gnames, plan: AggPlan, child, sharded
             stats["partitioned_groupby"] += 1
             shift, nbuckets = buckets
             gs = GroupState(dev, nslots + 1, plan, need_present=True)      # +1: see b2_range_partition
+            # all input partitions are reordered into ONE bucket-ordered array: the aggregation pass
+            # then meets every slice of the table exactly once (per-partition passes would reload it
+            # once per partition)
+            carried = sorted({v for _, _, _, vs in work for v in vs})
+            n_all = sum(part.n for part, _, _, _ in work)
+            ws = torch.zeros(L.range_partition_ws_bytes(nbuckets) // 8, dtype=torch.int64, device=dev)
             for part, ctx, kslot, vslots in work:
-                carried = sorted(set(vslots))
-                n = part.n
-                out_key = torch.full((n,), kmin + nslots + 1, dtype=torch.int64, device=dev)
-                outs = [torch.empty(n, dtype=_TORCH_DT[ctx.cols[c].dtype], device=dev) for c in carried]
-                ws = torch.zeros(L.range_partition_ws_bytes(nbuckets) // 8, dtype=torch.int64, device=dev)
-                cc = (C.c_int32 * max(1, len(carried)))(*carried)
-                oc = (C.c_void_p * max(1, len(carried)))(*[o.data_ptr() for o in outs])
-                stats["launches"] += 3
-                L.range_partition(C.byref(ctx.scan()), kslot, kmin, nslots, shift, nbuckets, len(carried), cc,
-                                  D.ptr(out_key), oc, D.ptr(ws), D.stream_ptr())
-                cols2 = [DeviceColumn(out_key, None, I64)] + \
-                        [DeviceColumn(o, None, ctx.cols[c].dtype) for o, c in zip(outs, carried)]
-                specs = [(1 + carried.index(v), ka.op) for v, ka in zip(vslots, plan.kaggs)]
-                gs.table.specs, gs.table.aggs = specs, D.make_aggs(specs)
                 stats["launches"] += 1
-                D.groupby_dense(D.make_scan(cols2, [], n), 0, kmin, gs.table)
+                L.range_partition_hist(C.byref(ctx.scan()), kslot, kmin, nslots, shift, nbuckets, D.ptr(ws),
+                                       D.stream_ptr())
+            stats["launches"] += 1
+            L.range_partition_scan(nbuckets, D.ptr(ws), D.stream_ptr())
+            ctx0 = work[0][1]
+            out_key = torch.full((n_all,), kmin + nslots + 1, dtype=torch.int64, device=dev)
+            outs = [torch.empty(n_all, dtype=_TORCH_DT[ctx0.cols[c].dtype], device=dev) for c in carried]
+            cc = (C.c_int32 * max(1, len(carried)))(*carried)
+            oc = (C.c_void_p * max(1, len(carried)))(*[o.data_ptr() for o in outs])
+            for part, ctx, kslot, vslots in work:
+                stats["launches"] += 1
+                L.range_partition_scatter(C.byref(ctx.scan()), kslot, kmin, nslots, shift, nbuckets, len(carried), cc,
+                                          D.ptr(out_key), oc, D.ptr(ws), D.stream_ptr())
+            cols2 = [DeviceColumn(out_key, None, I64)] + \
+                    [DeviceColumn(o, None, ctx0.cols[c].dtype) for o, c in zip(outs, carried)]
+            specs = [(1 + carried.index(v), ka.op) for v, ka in zip(work[0][3], plan.kaggs)]
+            gs.table.specs, gs.table.aggs = specs, D.make_aggs(specs)
+            stats["launches"] += 1
+            D.groupby_dense(D.make_scan(cols2, [], n_all), 0, kmin, gs.table)
         else:
             gs = GroupState(dev, nslots, plan, need_present=True)
             for part, ctx, kslot, _ in work:

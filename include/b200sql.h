@@ -364,6 +364,16 @@ int32_t b2_join_onepass(const b2_scan_t* scan, const int32_t* probe_keys, const 
  * Replaces nothing in the reference (pandas' groupby hashes in place); it is what makes
  * aggregate.py:522-589 on 100M groups stream instead of thrash. */
 int64_t b2_range_partition_ws_bytes(int32_t nbuckets);
+/* The three phases separately, so that SEVERAL input partitions can be reordered into ONE output (the
+ * dask-style partitions of a table would otherwise each revisit every slice of the group table):
+ * _hist per input (accumulates into ws), _scan once, _scatter per input into the shared outputs (sized
+ * for the sum of the inputs' rows).  b2_range_partition = the three on one input. */
+int32_t b2_range_partition_hist(const b2_scan_t* scan, int32_t key_col, int64_t kmin, int64_t nslots, int32_t shift,
+                                int32_t nbuckets, void* d_ws, void* stream);
+int32_t b2_range_partition_scan(int32_t nbuckets, void* d_ws, void* stream);
+int32_t b2_range_partition_scatter(const b2_scan_t* scan, int32_t key_col, int64_t kmin, int64_t nslots, int32_t shift,
+                                   int32_t nbuckets, int32_t ncarry, const int32_t* carry_cols, int64_t* out_key,
+                                   void* const* out_cols, void* d_ws, void* stream);
 int32_t b2_range_partition(const b2_scan_t* scan, int32_t key_col, int64_t kmin, int64_t nslots, int32_t shift,
                            int32_t nbuckets, int32_t ncarry, const int32_t* carry_cols, int64_t* out_key,
                            void* const* out_cols, void* d_ws, void* stream);

@@ -297,3 +297,25 @@ def test_arrow_buffers_become_host_columns_without_pandas(tmp_path):
         arrow_columns(pa.table({"s": ["a", "b"]}))
     with pytest.raises(AttributeError):
         read_location(path, "orc")
+
+
+def test_pending_part_resolves_on_first_use_only():
+    """executor.PendingPart: a partition whose row count is still on the device behaves like a Part
+    once anybody looks at it, and not before (host logic only; the kernels are covered by -m gpu)."""
+    from dask_sql_b200 import executor as X
+
+    calls = []
+
+    def thunk():
+        calls.append(1)
+        return X.Part({"a": "col-a", "b": "col-b"}, 7)
+
+    p = X.PendingPart(thunk)
+    assert not p.resolved and calls == []
+    q = X.PendingPart(lambda: X.Part({"x": p.resolve()["a"]}, p.n))       # chained (execute()'s projection)
+    assert not q.resolved and calls == []
+    assert q.n == 7 and q.resolved and p.resolved and calls == [1]
+    assert q["x"] == "col-a" and list(q) == ["x"] and "x" in q and len(q) == 1 and q.get("y") is None
+    assert p.n == 7 and dict(p) == {"a": "col-a", "b": "col-b"} and list(p.items())[0] == ("a", "col-a")
+    assert calls == [1]                                                     # resolved exactly once
+    assert X.Part({"k": 1}, 3).resolve().n == 3
