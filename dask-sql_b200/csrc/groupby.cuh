@@ -12,14 +12,9 @@
 #define B2_MAX_PROBE 1024
 
 // ---- dense ------------------------------------------------------------------------------
-__device__ __forceinline__ void b2_prefetch_l2_keep(const void* p) {
-  asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(p));
-}
-
 template <class LD>
 __device__ __forceinline__ void b2_dense_body(const b2_scan_t& s, const LD& ld, int key_col, int64_t kmin,
-                                              int64_t nslots, const b2_aggs_arg& aggs, const b2_aggstate_t& st,
-                                              int touch = 0) {
+                                              int64_t nslots, const b2_aggs_arg& aggs, const b2_aggstate_t& st) {
   const b2_col_t& kc = s.cols[key_col];
   bool full;
   const uint32_t bits = b2_eval_terms<B2_GB_R>(s, ld, full);
@@ -39,20 +34,6 @@ __device__ __forceinline__ void b2_dense_body(const b2_scan_t& s, const LD& ld, 
       }
     }
   }
-  if (touch) {
-    // tables far beyond L2: an atomic that misses L2 is executed as a DRAM read-modify-write without
-    // leaving the line behind, so even range-ordered input (partition.cuh) would pay DRAM for every
-    // row.  A prefetch allocates the sector first; the rows that follow in the same slice then hit.
-#pragma unroll
-    for (int j = 0; j < B2_GB_R; ++j) {
-      if (slot[j] < 0) continue;
-      if (st.rows) b2_prefetch_l2_keep(st.rows + slot[j]);
-      for (int a = 0; a < aggs.n; ++a) {
-        if (st.acc[a]) b2_prefetch_l2_keep(reinterpret_cast<const int64_t*>(st.acc[a]) + slot[j]);
-        if (st.cnt[a]) b2_prefetch_l2_keep(st.cnt[a] + slot[j]);
-      }
-    }
-  }
   b2_apply_aggs<B2_GB_R>(s, ld, aggs.a, aggs.n, st, slot);
 }
 
@@ -60,9 +41,10 @@ template <bool PIPE>
 __global__ void __launch_bounds__(PIPE ? B2_PIPE_THREADS : B2_BLOCK)
 b2_groupby_dense_kernel(const __grid_constant__ b2_scan_t s, const __grid_constant__ b2_pipe_t pp, int key_col,
                         int64_t kmin, int64_t nslots, const __grid_constant__ b2_aggs_arg aggs,
-                        const __grid_constant__ b2_aggstate_t st, int touch) {
-  auto body = [&](const auto& ld) { b2_dense_body(s, ld, key_col, kmin, nslots, aggs, st, touch); };
+                        const __grid_constant__ b2_aggstate_t st, unsigned long long* ticket) {
+  auto body = [&](const auto& ld) { b2_dense_body(s, ld, key_col, kmin, nslots, aggs, st); };
   if (PIPE) b2_tile_pipeline(s, pp, body);
+  else if (ticket) b2_tile_ticket<B2_GB_R>(s, ticket, body);
   else b2_tile_direct<B2_GB_R>(s, body);
 }
 
@@ -378,8 +360,9 @@ static int32_t b2_check_state(const b2_aggs_arg& aa, const b2_aggstate_t* st) {
 }
 static inline bool b2_pow2(int64_t x) { return x > 0 && (x & (x - 1)) == 0; }
 
-int32_t b2_groupby_dense(const b2_scan_t* scan, int32_t key_col, int64_t kmin, int64_t nslots,
-                         const b2_agg_t* aggs, int32_t naggs, const b2_aggstate_t* st, void* stream) {
+static int32_t b2_groupby_dense_impl(const b2_scan_t* scan, int32_t key_col, int64_t kmin, int64_t nslots,
+                                     const b2_agg_t* aggs, int32_t naggs, const b2_aggstate_t* st,
+                                     unsigned long long* ticket, void* stream) {
   int32_t rc = b2_check_scan(scan);
   if (rc) return rc;
   b2_aggs_arg aa;
@@ -389,22 +372,32 @@ int32_t b2_groupby_dense(const b2_scan_t* scan, int32_t key_col, int64_t kmin, i
   B2_REQUIRE(scan->cols[key_col].dtype == B2_I64 || scan->cols[key_col].dtype == B2_U8, "dense keys must be integers");
   B2_REQUIRE(nslots >= 2, "nslots must cover the key range plus the NULL slot");
   if (scan->n == 0) return B2_OK;
-  // pre-touch accumulator sectors when the table cannot live in L2 (see b2_dense_body);
-  // B200SQL_DENSE_TOUCH=0/1 overrides the size rule
-  int touch = nslots * 8 > (64LL << 20);
-  if (const char* e = getenv("B200SQL_DENSE_TOUCH")) touch = atoi(e) != 0;
   b2_pipe_t pp;
   b2_make_pipe(*scan, &pp);
+  if (ticket) pp.enabled = 0;
   if (pp.enabled) {
     int grid = b2_pipe_grid(b2_groupby_dense_kernel<true>, pp, scan->n);
-    b2_groupby_dense_kernel<true><<<grid, B2_PIPE_THREADS, pp.smem_bytes, (cudaStream_t)stream>>>(*scan, pp, key_col, kmin, nslots, aa, *st, touch);
+    b2_groupby_dense_kernel<true><<<grid, B2_PIPE_THREADS, pp.smem_bytes, (cudaStream_t)stream>>>(*scan, pp, key_col, kmin, nslots, aa, *st, nullptr);
   } else {
     int64_t nblk = (scan->n + B2_GB_ROWS_PER_BLOCK - 1) / B2_GB_ROWS_PER_BLOCK;
     int grid = b2_wave_grid(b2_groupby_dense_kernel<false>, B2_BLOCK, nblk);
-    b2_groupby_dense_kernel<false><<<grid, B2_BLOCK, 0, (cudaStream_t)stream>>>(*scan, pp, key_col, kmin, nslots, aa, *st, touch);
+    b2_groupby_dense_kernel<false><<<grid, B2_BLOCK, 0, (cudaStream_t)stream>>>(*scan, pp, key_col, kmin, nslots, aa, *st, ticket);
   }
   B2_CHECK_LAUNCH("b2_groupby_dense_kernel");
   return B2_OK;
+}
+
+int32_t b2_groupby_dense(const b2_scan_t* scan, int32_t key_col, int64_t kmin, int64_t nslots,
+                         const b2_agg_t* aggs, int32_t naggs, const b2_aggstate_t* st, void* stream) {
+  return b2_groupby_dense_impl(scan, key_col, kmin, nslots, aggs, naggs, st, nullptr, stream);
+}
+
+int32_t b2_groupby_dense_ordered(const b2_scan_t* scan, int32_t key_col, int64_t kmin, int64_t nslots,
+                                 const b2_agg_t* aggs, int32_t naggs, const b2_aggstate_t* st, uint64_t* d_ticket,
+                                 void* stream) {
+  B2_REQUIRE(d_ticket, "null ticket");
+  return b2_groupby_dense_impl(scan, key_col, kmin, nslots, aggs, naggs, st,
+                               reinterpret_cast<unsigned long long*>(d_ticket), stream);
 }
 
 int32_t b2_groupby_hash1(const b2_scan_t* scan, int32_t key_col, int64_t* table_keys, int64_t cap,

@@ -167,6 +167,28 @@ __device__ __forceinline__ void b2_tile_direct(const b2_scan_t& s, Body&& body) 
   }
 }
 
+// Tiles handed out IN ORDER by a global ticket instead of a fixed stride per CTA: the rows being
+// processed at any moment then form one contiguous window of (resident CTAs x tile) rows no matter how
+// unevenly the CTAs progress.  With a fixed stride a CTA that runs 10 % faster is 10 % of the input
+// ahead by the end -- fatal when the input is ordered so that a window should touch one L2-sized slice
+// of a table (partition.cuh).  *ticket must be 0 at launch.
+template <int R, class Body>
+__device__ __forceinline__ void b2_tile_ticket(const b2_scan_t& s, unsigned long long* __restrict__ ticket, Body&& body) {
+  __shared__ long long sh_tile;
+  const int tile_off = (threadIdx.x >> 5) * (32 * R) + (threadIdx.x & 31);
+  const int64_t tile = (int64_t)B2_BLOCK * R;
+  const int64_t ntiles = (s.n + tile - 1) / tile;
+  for (;;) {
+    if (threadIdx.x == 0) sh_tile = (long long)atomicAdd(ticket, 1ULL);
+    __syncthreads();
+    const int64_t t = sh_tile;
+    __syncthreads();
+    if (t >= ntiles) break;
+    const b2_gld ld{&s, t * tile + tile_off};
+    body(ld);
+  }
+}
+
 // host: launch geometry of a pipelined kernel.  Occupancy is limited by shared memory.
 template <class K>
 static inline int b2_pipe_grid(K kernel, const b2_pipe_t& pp, int64_t n) {

@@ -794,7 +794,10 @@ def grouped_aggregate(parts, pred, gexprs, gnames, plan: AggPlan, child, sharded
             specs = [(1 + carried.index(v), ka.op) for v, ka in zip(work[0][3], plan.kaggs)]
             gs.table.specs, gs.table.aggs = specs, D.make_aggs(specs)
             stats["launches"] += 1
-            D.groupby_dense(D.make_scan(cols2, [], n_all), 0, kmin, gs.table)
+            ticket = torch.zeros(1, dtype=torch.int64, device=dev)
+            scan2 = D.make_scan(cols2, [], n_all)
+            L.groupby_dense_ordered(C.byref(scan2), 0, int(kmin), gs.table.nslots, gs.table.aggs, len(gs.table.specs),
+                                    C.byref(gs.table.state), D.ptr(ticket), D.stream_ptr())
         else:
             gs = GroupState(dev, nslots, plan, need_present=True)
             for part, ctx, kslot, _ in work:

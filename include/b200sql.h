@@ -363,6 +363,12 @@ int32_t b2_join_onepass(const b2_scan_t* scan, const int32_t* probe_keys, const 
  * ws[0..nbuckets] are the bucket starts (ws[nbuckets] = rows written).  No host round trip.
  * Replaces nothing in the reference (pandas' groupby hashes in place); it is what makes
  * aggregate.py:522-589 on 100M groups stream instead of thrash. */
+/* b2_groupby_dense for input that b2_range_partition has ordered by key range: 2048-row tiles are
+ * handed to the CTAs in order through *d_ticket (device uint64, ZEROED by the caller), so the rows in
+ * flight always form one contiguous window and touch one slice of the table at a time. */
+int32_t b2_groupby_dense_ordered(const b2_scan_t* scan, int32_t key_col, int64_t kmin, int64_t nslots,
+                                 const b2_agg_t* aggs, int32_t naggs, const b2_aggstate_t* st, uint64_t* d_ticket,
+                                 void* stream);
 int64_t b2_range_partition_ws_bytes(int32_t nbuckets);
 /* The three phases separately, so that SEVERAL input partitions can be reordered into ONE output (the
  * dask-style partitions of a table would otherwise each revisit every slice of the group table):
