@@ -34,7 +34,7 @@ struct b2_pipe_t {  // computed on the host per launch
 static inline void b2_make_pipe(const b2_scan_t& s, b2_pipe_t* pp) {
   memset(pp, 0, sizeof(*pp));
   int off = 0;
-  // Opt-in (B200SQL_PIPELINE=1): measured on B200 (profiles/r01_pipeline_vs_direct.md) the staged
+  // Opt-in (B200SQL_PIPELINE=1): measured on B200 (profiles/r01_ncu_notes.md, capture C) the staged
   // path currently loses to the direct path because shared memory caps it at 2 CTAs/SM while the
   // consumers are still issue-bound; the direct path runs 5 CTAs/SM.
   static const bool want = [] { const char* e = getenv("B200SQL_PIPELINE"); return e && e[0] == '1'; }();
