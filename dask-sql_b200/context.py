@@ -48,24 +48,13 @@ class Context:
         self._plan_cache = {}
         logger.setLevel(logging_level)
 
-        RelConverter.add_plugin_class(logical.DaskAggregatePlugin, replace=False)
-        RelConverter.add_plugin_class(logical.DaskCrossJoinPlugin, replace=False)
-        RelConverter.add_plugin_class(logical.ExplainPlugin, replace=False)
-        RelConverter.add_plugin_class(logical.DaskFilterPlugin, replace=False)
-        RelConverter.add_plugin_class(logical.DaskJoinPlugin, replace=False)
-        RelConverter.add_plugin_class(logical.DaskProjectPlugin, replace=False)
-        RelConverter.add_plugin_class(logical.DaskSortPlugin, replace=False)
-        RelConverter.add_plugin_class(logical.DaskLimitPlugin, replace=False)
-        RelConverter.add_plugin_class(logical.SubqueryAlias, replace=False)
-        RelConverter.add_plugin_class(logical.DaskTableScanPlugin, replace=False)
-        RelConverter.add_plugin_class(custom.CreateMemoryTablePlugin, replace=False)
-        RelConverter.add_plugin_class(custom.CreateTablePlugin, replace=False)
-        RelConverter.add_plugin_class(custom.DropTablePlugin, replace=False)
-
-        RexConverter.add_plugin_class(core.RexAliasPlugin, replace=False)
-        RexConverter.add_plugin_class(core.RexCallPlugin, replace=False)
-        RexConverter.add_plugin_class(core.RexInputRefPlugin, replace=False)
-        RexConverter.add_plugin_class(core.RexLiteralPlugin, replace=False)
+        # replace=False: whoever registered a plugin for a node type before us -- or registers one
+        # later with replace=True -- wins (context.py:118-158); that is the drop-in seam
+        for plugin in (*logical.ALL_PLUGINS, custom.CreateMemoryTablePlugin, custom.CreateTablePlugin,
+                       custom.DropTablePlugin):
+            RelConverter.add_plugin_class(plugin, replace=False)
+        for plugin in core.ALL_PLUGINS:
+            RexConverter.add_plugin_class(plugin, replace=False)
 
     # -- catalog ------------------------------------------------------------------------------
     def _torch_device(self):

@@ -1,3 +1,2 @@
-from .convert import RelConverter
-
-__all__ = ["RelConverter"]
+"""Relational side of the plugin boundary."""
+from .convert import RelConverter  # noqa: F401  (re-exported)

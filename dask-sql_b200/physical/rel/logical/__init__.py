@@ -1,13 +1,17 @@
-from .aggregate import DaskAggregatePlugin
-from .cross_join import DaskCrossJoinPlugin
-from .explain import ExplainPlugin
-from .filter import DaskFilterPlugin
-from .join import DaskJoinPlugin
-from .limit import DaskLimitPlugin
-from .project import DaskProjectPlugin
-from .sort import DaskSortPlugin
-from .subquery_alias import SubqueryAlias
-from .table_scan import DaskTableScanPlugin
+"""Plan-node plugins of the filter -> join -> group-by path and the operators either side of it."""
+from . import (aggregate, cross_join, explain, filter, join, limit, project, sort, subquery_alias,  # noqa: A004
+               table_scan)
 
-__all__ = [DaskAggregatePlugin, DaskCrossJoinPlugin, ExplainPlugin, DaskFilterPlugin, DaskJoinPlugin,
-           DaskProjectPlugin, SubqueryAlias, DaskTableScanPlugin, DaskSortPlugin, DaskLimitPlugin]
+DaskTableScanPlugin = table_scan.DaskTableScanPlugin
+DaskFilterPlugin = filter.DaskFilterPlugin
+DaskProjectPlugin = project.DaskProjectPlugin
+DaskJoinPlugin = join.DaskJoinPlugin
+DaskCrossJoinPlugin = cross_join.DaskCrossJoinPlugin
+DaskAggregatePlugin = aggregate.DaskAggregatePlugin
+DaskSortPlugin = sort.DaskSortPlugin
+DaskLimitPlugin = limit.DaskLimitPlugin
+SubqueryAlias = subquery_alias.SubqueryAlias
+ExplainPlugin = explain.ExplainPlugin
+
+ALL_PLUGINS = (DaskTableScanPlugin, DaskFilterPlugin, DaskProjectPlugin, DaskJoinPlugin, DaskCrossJoinPlugin,
+               DaskAggregatePlugin, DaskSortPlugin, DaskLimitPlugin, SubqueryAlias, ExplainPlugin)

@@ -1,4 +1,4 @@
-"""WHERE / HAVING not pushed into a scan (dask_sql/physical/rel/logical/filter.py:20-74)."""
+"""WHERE / HAVING that was not pushed into a scan (dask_sql/physical/rel/logical/filter.py:20-74)."""
 import logging
 
 import numpy as np
@@ -7,33 +7,30 @@ from ....datacontainer import DataContainer
 from ...rex import RexConverter
 from ..base import BaseRelPlugin
 
-logger = logging.getLogger(__name__)
+log = logging.getLogger(__name__)
 
 
 def filter_or_scalar(df, filter_condition, add_filters=None):
-    """A scalar condition keeps everything or nothing; NULL in a boolean condition is False
-    (filter.py:20-45).  The lazy frame records the conjuncts; they are evaluated inside the
-    consuming kernel (b2_scan_t terms), never as a separate mask pass unless they are not
-    `column <cmp> literal` shaped."""
-    if filter_condition is None:
+    """Rows of `df` for which the condition holds (filter.py:20-45).
+
+    A literal condition keeps everything (truthy) or nothing (falsy / NULL); in a column condition
+    NULL counts as False.  On a lazy frame `df[cond]` only records the conjuncts: they run inside the
+    consuming kernel as b2_scan_t terms, and only what is not `column <cmp> literal` shaped is
+    evaluated as a mask first."""
+    if filter_condition is None or (np.isscalar(filter_condition) and not filter_condition):
+        if filter_condition is not None:
+            log.warning("Join condition is always false - returning empty dataset")
         return df.head(0, compute=False)
     if np.isscalar(filter_condition):
-        if not filter_condition:
-            logger.warning("Join condition is always false - returning empty dataset")
-            return df.head(0, compute=False)
         return df
-    filter_condition = filter_condition.fillna(False)
-    return df[filter_condition]
+    return df[filter_condition.fillna(False)]
 
 
 class DaskFilterPlugin(BaseRelPlugin):
     class_name = "Filter"
 
     def convert(self, rel, context) -> DataContainer:
-        (dc,) = self.assert_inputs(rel, 1, context)
-        df, cc = dc.df, dc.column_container
-        condition = rel.filter().getCondition()
-        df_condition = RexConverter.convert(rel, condition, dc, context=context)
-        df = filter_or_scalar(df, df_condition)
-        cc = self.fix_column_to_row_type(cc, rel.getRowType())
-        return DataContainer(df, cc)
+        (child,) = self.assert_inputs(rel, 1, context)
+        keep = RexConverter.convert(rel, rel.filter().getCondition(), child, context=context)
+        names = self.fix_column_to_row_type(child.column_container, rel.getRowType())
+        return DataContainer(filter_or_scalar(child.df, keep), names)

@@ -1,42 +1,35 @@
-"""Projection: re-map references for free, add computed columns lazily
-(dask_sql/physical/rel/logical/project.py:17-78)."""
-import logging
+"""Projection (dask_sql/physical/rel/logical/project.py:17-78).
 
+A projected plain column reference costs nothing: the output name is mapped onto the backend
+column it already is.  Every other item becomes one lazy expression column under a temporary
+backend name; nothing is evaluated here -- the executor fuses the expression into whichever
+kernel consumes it."""
 from ....datacontainer import DataContainer
 from ....planner import RexType
-from ....utils import is_frame, new_temporary_column
+from ....utils import new_temporary_column
 from ...rex import RexConverter
 from ..base import BaseRelPlugin
 
-logger = logging.getLogger(__name__)
+_REFERENCE = str(RexType.Reference)
 
 
 class DaskProjectPlugin(BaseRelPlugin):
     class_name = "Projection"
 
     def convert(self, rel, context) -> DataContainer:
-        (dc,) = self.assert_inputs(rel, 1, context)
-        df, cc = dc.df, dc.column_container
-        named_projects = rel.projection().getNamedProjects()
-        column_names, new_columns, new_mappings = [], {}, {}
-        for key, expr in named_projects:
-            key = str(key)
-            column_names.append(key)
-            if str(expr.getRexType()) == str(RexType.Reference):
-                backend_column_name = cc.get_backend_by_frontend_index(expr.getIndex())
-                logger.debug(f"Not re-adding the same column {key} (but just referencing it)")
-                new_mappings[key] = backend_column_name
+        (child,) = self.assert_inputs(rel, 1, context)
+        frame, names = child.df, child.column_container
+        computed, backend_of = {}, {}
+        for out_name, expr in rel.projection().getNamedProjects():
+            if str(expr.getRexType()) == _REFERENCE:
+                backend_of[str(out_name)] = names.get_backend_by_frontend_index(expr.getIndex())
             else:
-                random_name = new_temporary_column(df)
-                value = RexConverter.convert(rel, expr, dc, context=context)
-                new_columns[random_name] = value
-                logger.debug(f"Adding a new column {key} out of {expr}")
-                new_mappings[key] = random_name
-        if new_columns:
-            df = df.assign(**new_columns)
-        for key, backend_column_name in new_mappings.items():
-            cc = cc.add(key, backend_column_name)
-        cc = cc.limit_to(column_names)
-        cc = self.fix_column_to_row_type(cc, rel.getRowType())
-        dc = DataContainer(df, cc)
-        return self.fix_dtype_to_row_type(dc, rel.getRowType())
+                tmp = new_temporary_column(frame)
+                computed[tmp] = RexConverter.convert(rel, expr, child, context=context)
+                backend_of[str(out_name)] = tmp
+        if computed:
+            frame = frame.assign(**computed)
+        for out_name, backend in backend_of.items():
+            names = names.add(out_name, backend)
+        names = self.fix_column_to_row_type(names.limit_to(list(backend_of)), rel.getRowType())
+        return self.fix_dtype_to_row_type(DataContainer(frame, names), rel.getRowType())

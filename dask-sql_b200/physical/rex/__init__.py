@@ -1,3 +1,2 @@
-from .convert import RexConverter
-
-__all__ = ["RexConverter"]
+"""Expression side of the plugin boundary."""
+from .convert import RexConverter  # noqa: F401  (re-exported)

@@ -1,6 +1,10 @@
-from .alias import RexAliasPlugin
-from .call import RexCallPlugin
-from .input_ref import RexInputRefPlugin
-from .literal import RexLiteralPlugin
+"""Expression plugins of the hot path: calls (operators), column references, literals, aliases."""
+from . import alias, call, input_ref, literal
 
-__all__ = [RexAliasPlugin, RexCallPlugin, RexInputRefPlugin, RexLiteralPlugin]
+RexAliasPlugin = alias.RexAliasPlugin
+RexCallPlugin = call.RexCallPlugin
+RexInputRefPlugin = input_ref.RexInputRefPlugin
+RexLiteralPlugin = literal.RexLiteralPlugin
+
+ALL_PLUGINS = (RexCallPlugin, RexInputRefPlugin, RexLiteralPlugin, RexAliasPlugin)
+__all__ = ["RexAliasPlugin", "RexCallPlugin", "RexInputRefPlugin", "RexLiteralPlugin", "ALL_PLUGINS"]

@@ -36,6 +36,27 @@ class Pluggable:
         return list(Pluggable.__plugins[cls].values())
 
 
+class PluginDispatch:
+    """What RelConverter and RexConverter have in common: register a plugin class under its
+    class_name(s), look the plugin up by a key derived from the plan object, fail with
+    NotImplementedError when nobody registered for it (physical/rel/convert.py:32-63,
+    physical/rex/convert.py:42-76).  Mixed into two separate Pluggable subclasses because the
+    registry is keyed by subclass."""
+
+    kind = "?"
+
+    @classmethod
+    def add_plugin_class(cls, plugin_class, replace=True):
+        cls.add_plugin(plugin_class.class_name, plugin_class(), replace=replace)
+
+    @classmethod
+    def plugin_for(cls, key):
+        try:
+            return cls.get_plugin(key)
+        except KeyError:
+            raise NotImplementedError(f"no {cls.kind} plugin is registered for {key!r}") from None
+
+
 class ParsingException(Exception):
     """SQL could not be parsed / validated (utils.py:94-105)."""
 

@@ -319,3 +319,39 @@ def test_pending_part_resolves_on_first_use_only():
     assert p.n == 7 and dict(p) == {"a": "col-a", "b": "col-b"} and list(p.items())[0] == ("a", "col-a")
     assert calls == [1]                                                     # resolved exactly once
     assert X.Part({"k": 1}, 3).resolve().n == 3
+
+
+def test_sql_to_lazy_frames_without_a_gpu():
+    """Planning + plugin conversion is host-only: with host-resident tables (persist=False, the
+    reference's default) every statement reaches a LazyFrame / catalog change without touching CUDA."""
+    import pandas as pd
+    from dask_sql_b200 import Context
+    from dask_sql_b200.frame import LazyFrame
+    from dask_sql_b200.physical.rel import RelConverter
+
+    c = Context()
+    c.create_table("t", pd.DataFrame({"a": [1, 2, 3, 4], "b": [1.5, 2.5, 3.5, 4.5], "k": [1, 1, 2, 2]}))
+    for q, cols in [("SELECT a, a + b AS s, b * 2 AS d FROM t WHERE a > 1", ["a", "s", "d"]),
+                    ("SELECT k, SUM(b) AS sb FROM t GROUP BY k HAVING SUM(b) > 3", ["k", "sb"]),
+                    ("SELECT x.k, y.a FROM t x JOIN t y ON x.a = y.a WHERE x.b + y.b > 3", ["k", "a"]),
+                    ("SELECT a, b FROM t ORDER BY b DESC LIMIT 2", ["a", "b"]),
+                    ("SELECT COUNT(*) AS n, AVG(b) AS m FROM t WHERE NOT (a = 2)", ["n", "m"])]:
+        lf = c.sql(q)
+        assert isinstance(lf, LazyFrame) and lf.columns == cols
+    assert c.sql("CREATE VIEW v AS SELECT a, b FROM t WHERE a > 2") is None
+    assert c.sql("SELECT * FROM v").columns == ["a", "b"]
+    c.sql("DROP TABLE v")
+    with pytest.raises(RuntimeError, match="not present"):
+        c.sql("DROP TABLE v")
+    c.sql("DROP TABLE IF EXISTS v")
+    with pytest.raises(RuntimeError, match="already present"):
+        c.sql("CREATE VIEW t AS SELECT a FROM t")
+    c.sql("CREATE VIEW IF NOT EXISTS t AS SELECT a FROM t")
+    assert c.sql("SELECT * FROM t").columns == ["a", "b", "k"]          # kept
+
+    class Unknown:
+        def get_current_node_type(self):
+            return "WindowAggr"
+
+    with pytest.raises(NotImplementedError):
+        RelConverter.convert(Unknown(), c)
