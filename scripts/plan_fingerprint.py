@@ -1,4 +1,12 @@
-import sys, re, json
+"""Host-only fingerprint of what the planner + plugins turn a set of queries into (lazy-frame trees,
+temporary names normalised).  Run before and after touching planner/ or physical/ and `cmp` the two
+JSON files: identical output means the executor sees exactly the same work.
+usage: plan_fingerprint.py out.json"""
+import json
+import os
+import re
+import sys
+
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import pandas as pd, numpy as np
 from dask_sql_b200 import Context
