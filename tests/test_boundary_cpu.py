@@ -355,3 +355,25 @@ def test_sql_to_lazy_frames_without_a_gpu():
 
     with pytest.raises(NotImplementedError):
         RelConverter.convert(Unknown(), c)
+
+
+def test_header_is_plain_c():
+    """include/b200sql.h must be consumable by a C compiler on its own (cgo / JNI / ctypes bind it):
+    C99, no C++ or torch types in any signature."""
+    import shutil
+    import subprocess
+    import tempfile
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with tempfile.TemporaryDirectory() as d:
+        src = os.path.join(d, "h.c")
+        with open(src, "w") as f:
+            f.write('#include "b200sql.h"\nint main(void) { return (int)sizeof(b2_scan_t) * 0; }\n')
+        r = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only",
+                            "-I", os.path.join(root, "include"), src], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    text = open(os.path.join(root, "include", "b200sql.h")).read()
+    assert "at::" not in text and "std::" not in text and "template" not in text
