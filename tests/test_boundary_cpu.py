@@ -377,3 +377,30 @@ def test_header_is_plain_c():
     assert r.returncode == 0, r.stderr
     text = open(os.path.join(root, "include", "b200sql.h")).read()
     assert "at::" not in text and "std::" not in text and "template" not in text
+
+
+def test_partition_plan_heuristics(monkeypatch):
+    """executor._partition_plan (host logic): range-partition only group tables far beyond L2 whose
+    inputs are plain 8-byte columns; buckets of ~24 MB of table, at most 1024 of them."""
+    from types import SimpleNamespace as NS
+    from dask_sql_b200 import executor as X, _lib as L
+
+    col = lambda dtype, valid=None: NS(dtype=dtype, valid=valid)
+    plan = NS(kaggs=[NS(op=L.AGG_SUM, need_cnt=False)], need_rows=True)          # SUM + AVG of a non-null column
+    ctx = NS(cols=[col(L.I64), col(L.F64)])
+    work = [(NS(n=10), ctx, 0, [1])]
+    monkeypatch.delenv("B200SQL_NO_PARTITION", raising=False)
+    monkeypatch.delenv("B200SQL_PARTITION_MIN_BYTES", raising=False)
+    monkeypatch.delenv("B200SQL_PARTITION_BUCKET_BYTES", raising=False)
+    assert X._partition_plan(1_000_001, plan, work, 200_000_000) is None         # 16 MB of table: stays in L2
+    shift, nb = X._partition_plan(100_000_001, plan, work, 500_000_000)          # C5: 1.6 GB of table
+    assert (shift, nb) == (20, 96) and ((100_000_001 - 1) >> shift) < nb
+    assert X._partition_plan(100_000_001, plan, work, 1_000_000) is None         # too few rows to pay for a pass
+    shift, nb = X._partition_plan(1 << 31, plan, work, 1 << 33)
+    assert nb <= 1024 and (((1 << 31) - 1) >> shift) < nb                        # bucket count is capped
+    nullable = [(NS(n=10), NS(cols=[col(L.I64), col(L.F64, valid=object())]), 0, [1])]
+    assert X._partition_plan(100_000_001, plan, nullable, 500_000_000) is None   # bitmap inputs: direct path
+    boolean = [(NS(n=10), NS(cols=[col(L.I64), col(L.U8)]), 0, [1])]
+    assert X._partition_plan(100_000_001, plan, boolean, 500_000_000) is None
+    monkeypatch.setenv("B200SQL_NO_PARTITION", "1")
+    assert X._partition_plan(100_000_001, plan, work, 500_000_000) is None
