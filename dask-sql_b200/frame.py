@@ -14,7 +14,7 @@ so chains of Filter / Projection / TableScan nodes collapse into ONE fused kerne
 """
 import itertools
 from collections import OrderedDict
-from typing import Dict, List, Optional, Sequence
+from typing import Dict, List, Sequence
 
 import numpy as np
 

@@ -9,7 +9,6 @@ Dense group tables never come here: their accumulator arrays are all-reduced in 
 from collections import OrderedDict
 from typing import List
 
-import numpy as np
 import torch
 import torch.distributed as dist
 

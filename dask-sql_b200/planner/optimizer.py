@@ -2,7 +2,7 @@
 hot-path plans: predicate pushdown down to TableScan.filters (the Rust TableSource answers
 `Exact` to every pushdown, src/sql/table.rs:70-91), IS NOT NULL on inner-join keys
 (FilterNullJoinKeys, optimizer.rs:76) and projection pruning into the scans."""
-from typing import Dict, List, Optional, Set
+from typing import List, Optional, Set
 
 from . import plan as P
 from .plan import PyExpr

@@ -22,7 +22,7 @@ Each function cites the reference lines it follows (paths relative to /root/refe
 import operator
 from concurrent.futures import ThreadPoolExecutor
 from functools import reduce
-from typing import Callable, Dict, List, Optional, Sequence, Tuple
+from typing import Callable, List, Optional, Sequence, Tuple
 
 import numpy as np
 import pandas as pd
