@@ -63,6 +63,14 @@ class JoinTable(C.Structure):
                 ("range", C.c_int64)]
 
 
+JA_P, JA_B, JA_MUL, JA_ADD, JA_SUB, JA_RSUB, JA_ROWS = range(7)
+JA_MAX_BUILD = 4
+
+
+class JoinAgg(C.Structure):
+    _fields_ = [("pcol", C.c_int32), ("bcol", C.c_int32), ("combine", C.c_int32), ("op", C.c_int32)]
+
+
 class StarLookup(C.Structure):
     _fields_ = [("dense", C.c_int32), ("pad_", C.c_int32), ("lookup", C.c_void_p), ("kmin", C.c_int64),
                 ("range", C.c_int64), ("table_keys", C.c_void_p), ("table_slots", C.c_void_p),
@@ -140,6 +148,8 @@ _SIGS = {
     "b2_join_onepass": [C.POINTER(Scan), C.POINTER(C.c_int32), C.POINTER(JoinTable), C.c_int32, C.c_int32, _P, C.c_int32,
                         C.POINTER(C.c_int32), C.POINTER(_P), C.POINTER(_P), C.c_int32, C.POINTER(Col),
                         C.POINTER(C.c_int64), C.POINTER(_P), C.POINTER(_P), _P],
+    "b2_join_agg": [C.POINTER(Scan), C.c_int32, C.POINTER(JoinTable), C.c_int32, C.POINTER(Col), C.POINTER(C.c_int64),
+                    C.POINTER(JoinAgg), C.c_int32, _P, _P, C.c_int32, _P, _P],
     "b2_range_partition_hist": [C.POINTER(Scan), C.c_int32, C.c_int64, C.c_int64, C.c_int32, C.c_int32, _P, _P],
     "b2_range_partition_scan": [C.c_int32, _P, _P],
     "b2_range_partition_scatter": [C.POINTER(Scan), C.c_int32, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
@@ -202,6 +212,7 @@ join_write_gather_keyed = _wrap("b2_join_write_gather_keyed")
 join_key_layout = _wrap("b2_join_key_layout")
 join_onepass = _wrap("b2_join_onepass")
 join_onepass_ws_bytes = _lib.b2_join_onepass_ws_bytes
+join_agg = _wrap("b2_join_agg")
 range_partition = _wrap("b2_range_partition")
 range_partition_hist = _wrap("b2_range_partition_hist")
 range_partition_scan = _wrap("b2_range_partition_scan")

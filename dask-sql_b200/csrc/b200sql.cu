@@ -35,6 +35,7 @@ int b2_sm_count() {
 #include "filter.cuh"
 #include "groupby.cuh"
 #include "join.cuh"
+#include "joinagg.cuh"
 #include "sort.cuh"
 #include "partition.cuh"
 

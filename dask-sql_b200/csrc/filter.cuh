@@ -126,8 +126,12 @@ b2_scan_agg_kernel(const __grid_constant__ b2_scan_t s, const __grid_constant__ 
 }
 
 // deterministic final reduce over the per-block partials (fixed order)
-__global__ void b2_scan_agg_final_kernel(const __grid_constant__ b2_scan_t s,
-                                         const __grid_constant__ b2_aggs_arg aggs,
+struct b2_final_arg {   // what the final reduce needs to know about each aggregate
+  int32_t op[B2_MAX_AGGS];
+  int32_t dtype[B2_MAX_AGGS];   // type the accumulator is combined in (B2_I64 / B2_F64)
+  int32_t n;
+};
+__global__ void b2_scan_agg_final_kernel(const __grid_constant__ b2_final_arg fa,
                                          const b2_partial* __restrict__ partials, int nblocks,
                                          int64_t* __restrict__ out_acc, int64_t* __restrict__ out_cnt,
                                          int accumulate) {
@@ -136,8 +140,8 @@ __global__ void b2_scan_agg_final_kernel(const __grid_constant__ b2_scan_t s,
   __shared__ int64_t sh_r[B2_BLOCK];
   __shared__ int64_t sh_c[B2_BLOCK];
   const int a = blockIdx.x, t = threadIdx.x;
-  const int op = aggs.a[a].op;
-  const int dt = aggs.a[a].col >= 0 ? s.cols[aggs.a[a].col].dtype : B2_I64;
+  const int op = fa.op[a];
+  const int dt = fa.dtype[a];
   int64_t r = b2_identity(op), c = 0;
   for (int b = t; b < nblocks; b += B2_BLOCK) {
     r = b2_combine(op, dt, r, partials[b].acc[a]);
@@ -387,8 +391,16 @@ int32_t b2_scan_agg(const b2_scan_t* scan, const b2_agg_t* aggs, int32_t naggs, 
     b2_scan_agg_kernel<false><<<grid, B2_BLOCK, 0, st>>>(*scan, pp, aa, partials);
   }
   B2_CHECK_LAUNCH("b2_scan_agg_kernel");
-  if (naggs > 0)
-    b2_scan_agg_final_kernel<<<naggs, B2_BLOCK, 0, st>>>(*scan, aa, partials, grid, d_out_acc, d_out_cnt, accumulate);
+  if (naggs > 0) {
+    b2_final_arg fa;
+    memset(&fa, 0, sizeof(fa));
+    fa.n = naggs;
+    for (int a = 0; a < naggs; ++a) {
+      fa.op[a] = aa.a[a].op;
+      fa.dtype[a] = aa.a[a].col >= 0 ? scan->cols[aa.a[a].col].dtype : B2_I64;
+    }
+    b2_scan_agg_final_kernel<<<naggs, B2_BLOCK, 0, st>>>(fa, partials, grid, d_out_acc, d_out_cnt, accumulate);
+  }
   B2_CHECK_LAUNCH("b2_scan_agg_final_kernel");
   return B2_OK;
 }

@@ -1,0 +1,253 @@
+// joinagg.cuh — inner join on a unique dense key fused with GLOBAL aggregates over expressions
+// that mix both sides (C3's non-materialising variant: SELECT SUM(f.v * d.w) FROM fact f JOIN dim d
+// ON f.fk = d.pk).  The reference materialises the whole join (join.py:241-246: merge = factorize +
+// two indexers + take on every column) and then reduces it (aggregate.py:305-306,576: constant-key
+// groupby); here one pass over the probe partition does predicate -> presence/payload lookup at the
+// key offset -> combine -> per-thread accumulators, nothing is written but 2 x naggs words.
+//
+// The build side is the key-ordered layout of b2_join_key_layout (jt->dense == 2): `lookup` is the
+// presence bitmap and payload column b holds build value at [key - kmin] (int64 / float64, or uint32
+// offsets from bbase[b]).
+#pragma once
+#include "common.cuh"
+#include "filter.cuh"
+
+#define B2_JA_R 8
+#define B2_JA_ROWS_PER_BLOCK (B2_BLOCK * B2_JA_R)
+
+struct b2_joinagg_arg {
+  b2_joinagg_t a[B2_MAX_AGGS];
+  int32_t n;
+  int32_t nb;
+  b2_col_t bcols[B2_JA_MAX_BUILD];
+  int64_t bbase[B2_JA_MAX_BUILD];
+};
+
+// build value of one matched row as a raw 64-bit word of the payload's LOGICAL type
+__device__ __forceinline__ int64_t b2_ja_payload(const b2_col_t& c, int64_t base, uint64_t d) {
+  if (c.dtype == B2_U32) return base + (int64_t)(uint32_t)b2_ld_keep_i32(reinterpret_cast<const int32_t*>(c.data) + d);
+  return b2_ld_keep_i64(reinterpret_cast<const int64_t*>(c.data) + d);
+}
+
+template <int R>
+__device__ __forceinline__ void b2_join_agg_body(const b2_scan_t& s, const b2_gld& ld, int key_col,
+                                                 const b2_jointable_t& jt, const b2_joinagg_arg& ja,
+                                                 int64_t (*sh_acc)[B2_BLOCK], int32_t (*sh_cnt)[B2_BLOCK], int tid) {
+  const b2_col_t& kc = s.cols[key_col];
+  // trip 1: the join key is requested together with the predicate columns
+  bool full0;
+  const uint32_t inb = b2_bounds_bits<R>(ld.row0, s.n, full0);
+  int64_t key[R];
+  ld.template load<R>(key_col, inb, full0, key);
+  bool full;
+  const uint32_t bits = b2_eval_terms<R>(s, ld, full);
+  uint32_t live = bits;
+  if (kc.valid) live &= b2_valid_bits<R>(kc.valid, ld.row0, bits);
+  const uint64_t range = (uint64_t)jt.range;
+  uint64_t d[R];
+  uint32_t inr = 0;
+#pragma unroll
+  for (int j = 0; j < R; ++j) {
+    d[j] = (uint64_t)key[j] - (uint64_t)jt.kmin;
+    inr |= (uint32_t)(((live >> j) & 1) && d[j] < range) << j;
+  }
+  // trip 2: presence words, and -- speculatively, for every in-range row -- both inputs of the first
+  // aggregate (the payload at an offset without a build row is garbage that nobody reads)
+  uint32_t word[R];
+#pragma unroll
+  for (int j = 0; j < R; ++j) word[j] = (inr >> j) & 1 ? (uint32_t)b2_ld_keep_i32(jt.lookup + (d[j] >> 5)) : 0u;
+  const b2_joinagg_t a0 = ja.a[0];
+  const bool pre_b = ja.n > 0 && a0.bcol >= 0 && ja.bcols[a0.bcol].dtype != B2_U8;
+  const bool pre_p = ja.n > 0 && a0.pcol >= 0 && s.cols[a0.pcol].dtype != B2_U8;
+  int64_t pb[R], pp[R];
+  if (pre_b) {
+#pragma unroll
+    for (int j = 0; j < R; ++j) pb[j] = (inr >> j) & 1 ? b2_ja_payload(ja.bcols[a0.bcol], ja.bbase[a0.bcol], d[j]) : 0;
+  }
+  if (pre_p) ld.template load<R>(a0.pcol, inr, false, pp);
+  uint32_t matched = 0;
+#pragma unroll
+  for (int j = 0; j < R; ++j) matched |= ((word[j] >> (d[j] & 31)) & 1u) << j;
+
+  for (int a = 0; a < ja.n; ++a) {
+    const b2_joinagg_t ag = ja.a[a];
+    if (ag.combine == B2_JA_ROWS) {  // COUNT(*) of the join
+      sh_cnt[a][tid] += __popc(matched);
+      continue;
+    }
+    uint32_t ok = matched;
+    int64_t p[R], b[R];
+    bool pf = false, bf = false;
+    if (ag.pcol >= 0) {
+      const b2_col_t& c = s.cols[ag.pcol];
+      pf = c.dtype == B2_F64;
+      if (a == 0 && pre_p) {
+#pragma unroll
+        for (int j = 0; j < R; ++j) p[j] = pp[j];
+      } else {
+        ld.template load<R>(ag.pcol, matched, false, p);
+      }
+      if (c.valid || pf) ok &= ~b2_null_bits<R>(c, ld.row0, matched, p);
+    }
+    if (ag.bcol >= 0) {
+      const b2_col_t& c = ja.bcols[ag.bcol];
+      bf = c.dtype == B2_F64;
+      if (a == 0 && pre_b) {
+#pragma unroll
+        for (int j = 0; j < R; ++j) b[j] = pb[j];
+      } else if (c.dtype == B2_U8) {
+#pragma unroll
+        for (int j = 0; j < R; ++j) b[j] = (matched >> j) & 1 ? (int64_t) reinterpret_cast<const uint8_t*>(c.data)[d[j]] : 0;
+      } else {
+#pragma unroll
+        for (int j = 0; j < R; ++j) b[j] = (matched >> j) & 1 ? b2_ja_payload(c, ja.bbase[ag.bcol], d[j]) : 0;
+      }
+      if (c.valid) {
+#pragma unroll
+        for (int j = 0; j < R; ++j)
+          if (((ok >> j) & 1) && !b2_bit(c.valid, (int64_t)d[j])) ok &= ~(1u << j);
+      }
+      if (bf) {
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+          const double x = __longlong_as_double(b[j]);
+          if (x != x) ok &= ~(1u << j);
+        }
+      }
+    }
+    // combine into one 64-bit value per row, in float64 as soon as either side is float
+    const bool isf = pf || bf;
+    int64_t v[R];
+    if (ag.combine == B2_JA_P) {
+#pragma unroll
+      for (int j = 0; j < R; ++j) v[j] = p[j];
+    } else if (ag.combine == B2_JA_B) {
+#pragma unroll
+      for (int j = 0; j < R; ++j) v[j] = b[j];
+    } else if (isf) {
+#pragma unroll
+      for (int j = 0; j < R; ++j) {
+        const double x = pf ? __longlong_as_double(p[j]) : (double)p[j];
+        const double y = bf ? __longlong_as_double(b[j]) : (double)b[j];
+        double r;
+        switch (ag.combine) {
+          case B2_JA_MUL: r = x * y; break;
+          case B2_JA_ADD: r = x + y; break;
+          case B2_JA_SUB: r = x - y; break;
+          default: r = y - x; break;  // B2_JA_RSUB
+        }
+        v[j] = __double_as_longlong(r);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < R; ++j) {
+        const uint64_t x = (uint64_t)p[j], y = (uint64_t)b[j];
+        uint64_t r;
+        switch (ag.combine) {
+          case B2_JA_MUL: r = x * y; break;
+          case B2_JA_ADD: r = x + y; break;
+          case B2_JA_SUB: r = x - y; break;
+          default: r = y - x; break;
+        }
+        v[j] = (int64_t)r;
+      }
+    }
+    sh_cnt[a][tid] += __popc(ok);
+    int64_t acc = sh_acc[a][tid];
+    switch (b2_agg_kind(ag.op, isf ? B2_F64 : B2_I64)) {
+      case B2_K_SUM_I: acc = b2_fold_batch<R, B2_K_SUM_I>(acc, v, ok); break;
+      case B2_K_SUM_F: acc = b2_fold_batch<R, B2_K_SUM_F>(acc, v, ok); break;
+      case B2_K_SUMF_I: acc = b2_fold_batch<R, B2_K_SUMF_I>(acc, v, ok); break;
+      case B2_K_MIN_I: acc = b2_fold_batch<R, B2_K_MIN_I>(acc, v, ok); break;
+      case B2_K_MAX_I: acc = b2_fold_batch<R, B2_K_MAX_I>(acc, v, ok); break;
+      case B2_K_MIN_F: acc = b2_fold_batch<R, B2_K_MIN_F>(acc, v, ok); break;
+      case B2_K_MAX_F: acc = b2_fold_batch<R, B2_K_MAX_F>(acc, v, ok); break;
+      default: break;
+    }
+    sh_acc[a][tid] = acc;
+  }
+}
+
+__global__ void __launch_bounds__(B2_BLOCK)
+b2_join_agg_kernel(const __grid_constant__ b2_scan_t s, int key_col, const __grid_constant__ b2_jointable_t jt,
+                   const __grid_constant__ b2_joinagg_arg ja, b2_partial* __restrict__ partials) {
+  __shared__ int64_t sh_acc[B2_MAX_AGGS][B2_BLOCK];
+  __shared__ int32_t sh_cnt[B2_MAX_AGGS][B2_BLOCK];
+  const int tid = threadIdx.x;
+  for (int a = 0; a < ja.n; ++a) {
+    sh_acc[a][tid] = b2_identity(ja.a[a].op);
+    sh_cnt[a][tid] = 0;
+  }
+  b2_tile_direct<B2_JA_R>(s, [&](const b2_gld& ld) { b2_join_agg_body<B2_JA_R>(s, ld, key_col, jt, ja, sh_acc, sh_cnt, tid); });
+  __syncthreads();
+  if (tid < ja.n) {   // fixed-order block reduce, like b2_scan_agg_kernel
+    const int a = tid;
+    const b2_joinagg_t ag = ja.a[a];
+    const bool isf = (ag.pcol >= 0 && s.cols[ag.pcol].dtype == B2_F64) || (ag.bcol >= 0 && ja.bcols[ag.bcol].dtype == B2_F64);
+    const int dt = isf ? B2_F64 : B2_I64;
+    int64_t r = b2_identity(ag.op), c = 0;
+    for (int t = 0; t < B2_BLOCK; ++t) {
+      r = b2_combine(ag.op, dt, r, sh_acc[a][t]);
+      c += sh_cnt[a][t];
+    }
+    partials[blockIdx.x].acc[a] = r;
+    partials[blockIdx.x].cnt[a] = c;
+  }
+}
+
+extern "C" {
+
+int32_t b2_join_agg(const b2_scan_t* scan, int32_t probe_key, const b2_jointable_t* jt, int32_t nbuild,
+                    const b2_col_t* build_cols, const int64_t* build_base, const b2_joinagg_t* aggs, int32_t naggs,
+                    int64_t* d_out_acc, int64_t* d_out_cnt, int32_t accumulate, void* ws, void* stream) {
+  int32_t rc = b2_check_scan(scan);
+  if (rc) return rc;
+  B2_REQUIRE(jt && d_out_acc && d_out_cnt && ws, "null argument");
+  B2_REQUIRE(jt->dense == 2 && jt->nkeys == 1 && jt->lookup && jt->range > 0, "b2_join_agg needs a key-ordered table");
+  B2_REQUIRE(probe_key >= 0 && probe_key < scan->ncols && scan->cols[probe_key].dtype == B2_I64, "probe key must be int64");
+  B2_REQUIRE(naggs >= 1 && naggs <= B2_MAX_AGGS && aggs, "bad aggregate list");
+  B2_REQUIRE(nbuild >= 0 && nbuild <= B2_JA_MAX_BUILD && (nbuild == 0 || build_cols), "bad build column list");
+  b2_joinagg_arg ja;
+  memset(&ja, 0, sizeof(ja));
+  ja.n = naggs;
+  ja.nb = nbuild;
+  for (int b = 0; b < nbuild; ++b) {
+    B2_REQUIRE(build_cols[b].data, "null build column");
+    B2_REQUIRE(build_cols[b].dtype != B2_U32 || build_base, "uint32 payloads need their base");
+    ja.bcols[b] = build_cols[b];
+    ja.bbase[b] = build_base ? build_base[b] : 0;
+  }
+  b2_final_arg fa;
+  memset(&fa, 0, sizeof(fa));
+  fa.n = naggs;
+  for (int a = 0; a < naggs; ++a) {
+    const b2_joinagg_t& ag = aggs[a];
+    B2_REQUIRE(ag.combine >= B2_JA_P && ag.combine <= B2_JA_ROWS, "bad combine");
+    B2_REQUIRE(ag.op >= B2_AGG_SUM && ag.op <= B2_AGG_COUNT, "bad agg op");
+    const bool needp = ag.combine != B2_JA_B && ag.combine != B2_JA_ROWS;
+    const bool needb = ag.combine != B2_JA_P && ag.combine != B2_JA_ROWS;
+    B2_REQUIRE(!needp || (ag.pcol >= 0 && ag.pcol < scan->ncols), "probe column out of range");
+    B2_REQUIRE(!needb || (ag.bcol >= 0 && ag.bcol < nbuild), "build column out of range");
+    B2_REQUIRE(!needp || scan->cols[ag.pcol].dtype != B2_U8, "aggregate inputs must be 8-byte columns");
+    B2_REQUIRE(!needb || build_cols[ag.bcol].dtype != B2_U8, "aggregate inputs must be 8-byte columns");
+    ja.a[a] = ag;
+    if (!needp) ja.a[a].pcol = -1;
+    if (!needb) ja.a[a].bcol = -1;
+    const bool isf = (needp && scan->cols[ag.pcol].dtype == B2_F64) || (needb && build_cols[ag.bcol].dtype == B2_F64);
+    fa.op[a] = ag.combine == B2_JA_ROWS ? B2_AGG_COUNT : ag.op;
+    fa.dtype[a] = isf ? B2_F64 : B2_I64;
+    if (ag.combine == B2_JA_ROWS) ja.a[a].op = B2_AGG_COUNT;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  b2_partial* partials = reinterpret_cast<b2_partial*>(ws);
+  int64_t nblk = (scan->n + B2_JA_ROWS_PER_BLOCK - 1) / B2_JA_ROWS_PER_BLOCK;
+  int grid = b2_wave_grid(b2_join_agg_kernel, B2_BLOCK, nblk);
+  if (grid > 148 * 16) grid = 148 * 16;
+  b2_join_agg_kernel<<<grid, B2_BLOCK, 0, st>>>(*scan, probe_key, *jt, ja, partials);
+  B2_CHECK_LAUNCH("b2_join_agg_kernel");
+  b2_scan_agg_final_kernel<<<naggs, B2_BLOCK, 0, st>>>(fa, partials, grid, d_out_acc, d_out_cnt, accumulate);
+  B2_CHECK_LAUNCH("b2_scan_agg_final_kernel");
+  return B2_OK;
+}
+
+}  // extern "C"

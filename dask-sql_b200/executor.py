@@ -57,6 +57,31 @@ def _kernel_event_end(rec):
         rec[3].record()
 
 
+# Optional per-phase timing of a query's exchange steps (bench.py sets this to a list): entries are
+# [phase name, start event, end event] on the launching stream -- "where does an N>1 step go".
+phase_events = None
+
+
+class _Phase:
+    __slots__ = ("rec",)
+
+    def __init__(self, name):
+        self.rec = None
+        if phase_events is not None:
+            self.rec = [name, torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)]
+
+    def __enter__(self):
+        if self.rec is not None:
+            self.rec[1].record()
+        return self
+
+    def __exit__(self, *exc):
+        if self.rec is not None:
+            self.rec[2].record()
+            phase_events.append(self.rec)
+        return False
+
+
 def _dev():
     D.require_cuda()
     return torch.device("cuda", torch.cuda.current_device())
@@ -64,6 +89,10 @@ def _dev():
 
 class Part(dict):
     """One materialised partition: column name -> DeviceColumn, all of length n."""
+
+    # "replicated": every rank holds these rows (or there is one rank); "keyrange": the rows of a
+    # multi-GPU aggregate, of which every rank holds the groups of its own slice of the key range
+    dist = "replicated"
 
     def __init__(self, cols=(), n=0):
         super().__init__(cols)
@@ -98,6 +127,7 @@ class PendingPart(Part):
             real = thunk().resolve()
             dict.update(self, real)
             self._n = real.n
+            self.dist = real.dist     # a fallback path may have produced a differently distributed result
         return self
 
     @property
@@ -317,9 +347,48 @@ def frame_distribution(frame: LazyFrame) -> str:
     if isinstance(src, TableSource):
         return src.table.distribution
     if isinstance(src, JoinSource):
-        l, r = frame_distribution(src.left), frame_distribution(src.right)
-        return "sharded" if "sharded" in (l, r) else l
+        return join_sides(src)[1]
+    if isinstance(src, (SortSource, LimitSource)):
+        return "replicated" if P.world()[1] > 1 else "local"
     return "replicated" if P.world()[1] > 1 else "local"
+
+
+def _global_rows(frame: LazyFrame) -> int:
+    """Row estimate every rank agrees on (local estimates differ: a 'root' table is empty off rank 0
+    and shards are uneven).  Table counts are gathered once and cached on the immutable table."""
+    src = frame.source
+    world = P.world()[1]
+    if isinstance(src, TableSource):
+        t = src.table
+        if world == 1 or t.distribution not in ("sharded", "root"):
+            return t.nrows
+        if "_global_nrows" not in t.__dict__:
+            t.__dict__["_global_nrows"] = sum(r[0] for r in P.all_gather_ints([t.nrows], _dev()))
+        return t.__dict__["_global_nrows"]
+    if isinstance(src, JoinSource):
+        return max(_global_rows(src.left), _global_rows(src.right))
+    return _global_rows(src.child)
+
+
+def join_sides(js: JoinSource):
+    """(swap, distribution of the result).  swap=True: the LEFT input is hashed (build side) and the
+    right one streams.  Decided only from facts every rank shares -- the join type, the inputs'
+    distributions and globally agreed row counts -- never from rank-local sizes: ranks that disagree
+    on the build side would enter different collectives and hang."""
+    how = js.how
+    ld, rd = frame_distribution(js.left), frame_distribution(js.right)
+    if how == "right":
+        swap = True
+    elif how != "inner":
+        swap = False
+    elif P.world()[1] > 1 and (ld == "sharded") != (rd == "sharded"):
+        swap = rd == "sharded"          # the sharded side streams, the other one is broadcast
+    else:
+        swap = _global_rows(js.left) < _global_rows(js.right)
+    probe_d, build_d = (rd, ld) if swap else (ld, rd)
+    # the build side is made whole on every rank (run_join), so the output rows live where the
+    # probe rows live
+    return swap, probe_d
 
 
 def estimated_rows(frame: LazyFrame) -> int:
@@ -331,7 +400,21 @@ def estimated_rows(frame: LazyFrame) -> int:
     return estimated_rows(src.child)
 
 
-def materialize(src: Source, needed: Set[str]) -> List[Part]:
+def gather_keyrange(part: Part) -> Part:
+    """Key-range-sharded aggregate -> the same rows on every rank (all-gather in rank order)."""
+    part = part.resolve()
+    if part.dist != "keyrange" or P.world()[1] == 1:
+        return part
+    from .merge import allgather_part
+    with _Phase("gather_result"):
+        out = allgather_part(Part(dict(part), part.n), _dev())
+    return out
+
+
+def materialize(src: Source, needed: Set[str], top: bool = False) -> List[Part]:
+    """top: the caller is the outermost frame of a query -- a multi-GPU aggregate may then stay
+    sharded by key range (one slice of the groups per rank, the dask result with split_out = world
+    size); any operator stacked on top of an aggregate needs all groups and gets them gathered."""
     if isinstance(src, TableSource):
         dev = _dev()
         parts = []
@@ -352,7 +435,8 @@ def materialize(src: Source, needed: Set[str]) -> List[Part]:
     if isinstance(src, JoinSource):
         return run_join(src, needed)
     if isinstance(src, AggSource):
-        return [run_aggregate(src)]
+        part = run_aggregate(src)
+        return [part if top else gather_keyrange(part)]
     if isinstance(src, SortSource):
         return [run_sort(src, needed)]
     if isinstance(src, LimitSource):
@@ -413,8 +497,10 @@ def empty_part(exprs: Dict[str, Expr]) -> Part:
     return out
 
 
-def execute(frame: LazyFrame, needed: Optional[Sequence[str]] = None) -> List[Part]:
-    """Materialise `needed` output columns of `frame`, partition by partition."""
+def execute(frame: LazyFrame, needed: Optional[Sequence[str]] = None, top: bool = False) -> List[Part]:
+    """Materialise `needed` output columns of `frame`, partition by partition.  top=True lets the
+    groups of a multi-GPU aggregate stay with the rank that owns their key range (Part.dist ==
+    "keyrange"); compute_frame gathers them on the way to the host."""
     D.reset_stream()
     names = list(needed) if needed is not None else frame.columns
     exprs = {n: frame.exprs[n] for n in names}
@@ -426,13 +512,15 @@ def execute(frame: LazyFrame, needed: Optional[Sequence[str]] = None) -> List[Pa
         e.refs(src_needed)
     for p in pred:
         p.refs(src_needed)
-    parts = materialize(frame.source, src_needed)
+    parts = materialize(frame.source, src_needed, top)
 
     def project(part: Part) -> Part:
+        dist = part.dist
         if pred:
             colrefs = sorted({r for e in exprs.values() for r in e.refs()})
             part = select_part(part, pred, colrefs)
         res = Part({}, part.n)
+        res.dist = dist
         for n, e in exprs.items():
             if isinstance(e, Lit):
                 res[n] = const_column(e.value, e.dtype, part.n, _dev())
@@ -443,7 +531,9 @@ def execute(frame: LazyFrame, needed: Optional[Sequence[str]] = None) -> List[Pa
     out = []
     for part in parts:
         if isinstance(part, PendingPart) and not part.resolved:
-            out.append(PendingPart(lambda part=part: project(part.resolve())))   # stays lazy
+            lazy = PendingPart(lambda part=part: project(part.resolve()))   # stays lazy
+            lazy.dist = part.dist
+            out.append(lazy)
         else:
             out.append(project(part))
     return out
@@ -576,6 +666,10 @@ def run_aggregate(src: AggSource, allow_fast=True) -> Part:
         res = try_star(src, child, gexprs, aggs, pred, sharded, allow_fast)
         if res is not None:
             return res
+    if not gexprs and isinstance(child.source, JoinSource) and not never and allow_fast:
+        res = try_join_agg(src, child, aggs, pred, sharded)
+        if res is not None:
+            return res
     needed: Set[str] = set()
     for e in gexprs:
         e.refs(needed)
@@ -609,7 +703,9 @@ def global_aggregate(parts: List[Part], pred, plan: AggPlan, sharded: bool) -> P
             ga.specs = specs
             ga.aggs = D.make_aggs(specs)
         stats["launches"] += 2
+        ev = _kernel_event_begin("b2_scan_agg_kernel", part.n)
         ga.update(ctx.scan())
+        _kernel_event_end(ev)
     if ga is None:
         acc = np.array([{L.AGG_MIN: (1 << 63) - 1, L.AGG_MAX: -(1 << 63)}.get(ka.op, 0) for ka in plan.kaggs] + [0],
                        dtype=np.int64)
@@ -619,23 +715,32 @@ def global_aggregate(parts: List[Part], pred, plan: AggPlan, sharded: bool) -> P
         stats["d2h_bytes"] += 16 * (k + 1)
     if sharded:
         acc, cnt = _allreduce_global(acc, cnt, plan, dev)
+    return _finish_global(plan, acc, cnt, dev)
+
+
+def _finish_global(plan: AggPlan, acc, cnt, dev, float_acc=None) -> Part:
+    """One-row result of a global aggregate from the raw accumulators (host numpy int64 bit patterns;
+    entry len(plan.kaggs) of `cnt` is the number of rows that took part).  float_acc[i]: accumulator
+    i holds a float64 although its input expression is typed int (never the case for plain scans)."""
+    k = len(plan.kaggs)
     rows = int(cnt[k])
     out = Part({}, 1 if rows > 0 else 0)
     for name, fn, a, c, in_dt, lg in plan.outs:
         n_valid = rows if c == "rows" else (int(cnt[c]) if c is not None else rows)
+        is_f = in_dt == F64 or bool(float_acc and a is not None and float_acc[a])
         if fn in ("size", "count"):
             val, dt, lgo = n_valid, I64, "int64"
         elif fn == "sum":
-            dt, lgo = (F64, lg) if in_dt == F64 else (I64, lg if lg != "bool" else "int64")
-            val = None if n_valid == 0 else (acc[a:a + 1].view(np.float64)[0].item() if in_dt == F64 else int(acc[a]))
+            dt, lgo = (F64, lg if in_dt == F64 else "float64") if is_f else (I64, lg if lg != "bool" else "int64")
+            val = None if n_valid == 0 else (acc[a:a + 1].view(np.float64)[0].item() if is_f else int(acc[a]))
         elif fn == "mean":
             dt, lgo = F64, "float64"
             val = None if n_valid == 0 else acc[a:a + 1].view(np.float64)[0].item() / n_valid
         else:  # min / max
-            dt, lgo = (F64, lg) if in_dt == F64 else (I64, lg)
+            dt, lgo = (F64, lg if in_dt == F64 else "float64") if is_f else (I64, lg)
             if n_valid == 0:
                 val = None
-            elif in_dt == F64:
+            elif is_f:
                 val = L.ordered_to_f64(int(acc[a]))
             else:
                 val = int(acc[a])
@@ -672,16 +777,26 @@ def _allreduce_global(acc, cnt, plan: AggPlan, dev):
 
 
 # -- grouped ----------------------------------------------------------------------------------
+def _padded_slots(nslots: int, sharded: bool) -> int:
+    """Slots to allocate: a table that will be reduce-scattered is padded to a multiple of
+    32 x world size (equal, bitmap-word-aligned slices for every rank)."""
+    size = P.world()[1]
+    if not sharded or size == 1:
+        return nslots
+    q = 32 * size
+    return (nslots + q - 1) // q * q
+
+
 class GroupState:
     """Accumulators + key storage of one GROUP BY, independent of how slots are found."""
 
-    def __init__(self, dev, nslots, plan: AggPlan, need_present, force_rows=False):
+    def __init__(self, dev, nslots, plan: AggPlan, need_present, force_rows=False, alloc=None):
         need_rows = plan.need_rows or force_rows
         specs = [(0, ka.op) for ka in plan.kaggs]
         self.table = D.GroupTable(dev, nslots, specs, [ka.dtype for ka in plan.kaggs],
                                   [ka.need_cnt for ka in plan.kaggs], need_rows,
                                   need_present and not need_rows,
-                                  indicator=None if need_rows else plan.indicator)
+                                  indicator=None if need_rows else plan.indicator, alloc=alloc)
         self.plan = plan
         self.nslots = nslots
 
@@ -767,7 +882,8 @@ def grouped_aggregate(parts, pred, gexprs, gnames, plan: AggPlan, child, sharded
             # aggregation pass stay inside one L2-sized slice of the table at a time
             stats["partitioned_groupby"] += 1
             shift, nbuckets = buckets
-            gs = GroupState(dev, nslots + 1, plan, need_present=True)      # +1: see b2_range_partition
+            gs = GroupState(dev, nslots + 1, plan, need_present=True,      # +1: see b2_range_partition
+                            alloc=_padded_slots(nslots + 1, sharded))
             # all input partitions are reordered into ONE bucket-ordered array: the aggregation pass
             # then meets every slice of the table exactly once (per-partition passes would reload it
             # once per partition)
@@ -787,8 +903,10 @@ def grouped_aggregate(parts, pred, gexprs, gnames, plan: AggPlan, child, sharded
             oc = (C.c_void_p * max(1, len(carried)))(*[o.data_ptr() for o in outs])
             for part, ctx, kslot, vslots in work:
                 stats["launches"] += 1
+                ev = _kernel_event_begin("b2_part_scatter_kernel", part.n)
                 L.range_partition_scatter(C.byref(ctx.scan()), kslot, kmin, nslots, shift, nbuckets, len(carried), cc,
                                           D.ptr(out_key), oc, D.ptr(ws), D.stream_ptr())
+                _kernel_event_end(ev)
             cols2 = [DeviceColumn(out_key, None, I64)] + \
                     [DeviceColumn(o, None, ctx0.cols[c].dtype) for o, c in zip(outs, carried)]
             specs = [(1 + carried.index(v), ka.op) for v, ka in zip(work[0][3], plan.kaggs)]
@@ -796,18 +914,25 @@ def grouped_aggregate(parts, pred, gexprs, gnames, plan: AggPlan, child, sharded
             stats["launches"] += 1
             ticket = torch.zeros(1, dtype=torch.int64, device=dev)
             scan2 = D.make_scan(cols2, [], n_all)
+            ev = _kernel_event_begin("b2_groupby_dense_ordered", n_all)
             L.groupby_dense_ordered(C.byref(scan2), 0, int(kmin), gs.table.nslots, gs.table.aggs, len(gs.table.specs),
                                     C.byref(gs.table.state), D.ptr(ticket), D.stream_ptr())
+            _kernel_event_end(ev)
         else:
-            gs = GroupState(dev, nslots, plan, need_present=True)
+            gs = GroupState(dev, nslots, plan, need_present=True, alloc=_padded_slots(nslots, sharded))
             for part, ctx, kslot, _ in work:
                 gs.bind(ctx)
                 stats["launches"] += 1
+                ev = _kernel_event_begin("b2_groupby_dense_kernel", part.n)
                 D.groupby_dense(ctx.scan(), kslot, kmin, gs.table)
-        if sharded:
-            _allreduce_table(gs.table, plan)
+                _kernel_event_end(ev)
         key_nullable = E.may_be_null(gexprs[0], lambda n: any(n in p and p[n].valid is not None for p in parts))
-        return _finalize_dense(gs, kmin, rng, gnames[0], gexprs[0], glog[0], plan, dev, key_nullable)
+        if sharded:
+            # a rank whose shard has no NULL key must still agree that the NULL slot may be occupied
+            t = torch.tensor([1 if key_nullable else 0], dtype=torch.int64, device=dev)
+            key_nullable = bool(int(P.allreduce_(t, "max").item()))
+        view = _merge_dense(gs.table, plan, sharded, dev)
+        return _finalize_dense(view, kmin, gnames[0], gexprs[0], glog[0], plan, dev, key_nullable)
 
     # ---- hash tables: size from the row count, grow on overflow
     stats["hash_groupby"] += 1
@@ -878,26 +1003,87 @@ def _partition_plan(nslots, plan: AggPlan, work, total_rows):
     return shift, ((nslots - 1) >> shift) + 1
 
 
-def _allreduce_table(table: D.GroupTable, plan: AggPlan):
-    for ka, acc, cnt in zip(plan.kaggs, table.acc, table.cnt):
-        if acc is not None:
-            P.allreduce_(acc, {L.AGG_MIN: "min", L.AGG_MAX: "max"}.get(ka.op, "sum"))
-        if cnt is not None:
-            P.allreduce_(cnt, "sum")
-    if table.rows is not None:
-        P.allreduce_(table.rows, "sum")
-    if table.present is not None:
-        # presence bitmaps are OR-ed: NCCL has no bitwise reduction, so every rank gathers the
-        # (nslots/8-byte) bitmaps and folds them with b2_bitmap_or -- far cheaper than keeping a
-        # row counter per slot (one more atomic per input row) just to be able to sum it
-        import torch.distributed as dist
-        size = P.world()[1]
-        if size > 1:
-            gathered = [torch.empty_like(table.present) for _ in range(size)]
-            dist.all_gather(gathered, table.present)
-            for g in gathered:
-                stats["launches"] += 1
-                L.bitmap_or(D.ptr(table.present), D.ptr(g), table.present.numel(), D.stream_ptr())
+class SlotView:
+    """A window [lo, lo + count) of a dense group table's slots: the accumulator arrays restricted to
+    it and the rule that tells which of its slots hold a group.  Single GPU: the whole table.
+    Multi-GPU: this rank's slice of the reduce-scattered table (executor._merge_dense)."""
+
+    def __init__(self, nslots, lo, count, acc, cnt, rows, occ_kind, occ, dist="replicated"):
+        self.nslots, self.lo, self.count = nslots, lo, count      # nslots: logical table size (NULL slot = nslots-1)
+        self.acc, self.cnt, self.rows = acc, cnt, rows
+        self.occ_kind, self.occ = occ_kind, occ                    # 'rows' | 'indicator' | 'bitmap' | 'bytes'
+        self.dist = dist
+
+    @classmethod
+    def whole(cls, t: D.GroupTable, count=None):
+        n = t.nslots if count is None else count
+        cut = lambda x: None if x is None else x[:n]
+        if t.rows is not None:
+            kind, occ = "rows", cut(t.rows)
+        elif t.indicator is not None:
+            kind, occ = "indicator", cut(t.acc[t.indicator])
+        else:
+            kind, occ = "bitmap", t.present
+        return cls(t.nslots, 0, n, [cut(a) for a in t.acc], [cut(c) for c in t.cnt], cut(t.rows), kind, occ)
+
+    def occupancy(self, keys: torch.Tensor):
+        """(column, predicate term) selecting the slots of the window that received at least one row."""
+        if self.occ_kind == "rows":
+            return DeviceColumn(self.occ, None, I64), TermSpec(0, L.GT, 0)
+        if self.occ_kind == "indicator":
+            # untouched float SUM accumulator = -0.0 = the INT64_MIN bit pattern (single GPU only:
+            # a collective is free to lose the sign of a zero, see _merge_dense)
+            return DeviceColumn(self.occ.view(torch.int64), None, I64), TermSpec(0, L.NE, L.EMPTY_KEY)
+        if self.occ_kind == "bytes":
+            return DeviceColumn(self.occ, None, U8), TermSpec(0, L.IS_TRUE, 0)
+        return DeviceColumn(keys, self.occ, I64), TermSpec(0, L.IS_NOT_NULL, 0)
+
+
+def _presence_bytes(t: D.GroupTable, dev) -> torch.Tensor:
+    """uint8[alloc]: 1 where this rank's partial table holds a group.  Derived from whatever the
+    kernels maintained (row counter, -0.0 indicator accumulator, presence bitmap) in one
+    b2_expr_eval pass, so that existence crosses the ranks as DATA: NCCL may pick an algorithm
+    (in-switch NVLS reduction, zero-initialised scratch) under which -0.0 + -0.0 comes back +0.0."""
+    n = t.alloc
+    if t.rows is not None:
+        e, env = E.binop("gt", ColRef("x", I64), 0), {"x": DeviceColumn(t.rows, None, I64)}
+    elif t.indicator is not None:
+        e = E.binop("ne", ColRef("x", I64), L.EMPTY_KEY)
+        env = {"x": DeviceColumn(t.acc[t.indicator].view(torch.int64), None, I64)}
+    else:
+        e = E.unop("not", Call("isnull", [ColRef("x", I64)], U8))
+        # only the validity bitmap is read; any 8-byte buffer of the right length serves as values
+        vals = next((a for a in list(t.acc) + list(t.cnt) if a is not None), None)
+        if vals is None:
+            vals = torch.zeros(n, dtype=torch.int64, device=dev)
+        env = {"x": DeviceColumn(vals.view(torch.int64), t.present, I64)}
+    return eval_expr(Part(env, n), E.cast(e, U8)).data
+
+
+def _merge_dense(t: D.GroupTable, plan: AggPlan, sharded: bool, dev) -> SlotView:
+    """Combine the ranks' partial dense tables: reduce-scatter by slot range (sum of sums / counts,
+    min of mins, max of maxes, OR of existence), so that every rank ends up owning the merged
+    groups of one contiguous key range -- the reference's tree reduction (aggregate.py:575-581,
+    groupby(...).agg(split_every)) restated for direct-address tables, with split_out = world size.
+    Existence travels explicitly (a uint8 per slot, MAX-reduced); nothing depends on how the
+    collective treats signed zeros."""
+    rank, size = P.world()
+    if not sharded or size == 1:
+        return SlotView.whole(t)
+    assert t.alloc % (32 * size) == 0, "sharded group tables are padded to 32 x world slots"
+    chunk = t.alloc // size
+    with _Phase("presence"):
+        pres = _presence_bytes(t, dev)
+        stats["launches"] += 1
+    with _Phase("reduce_scatter"):
+        accs, cnts = [], []
+        for ka, acc, cnt in zip(plan.kaggs, t.acc, t.cnt):
+            accs.append(None if acc is None else
+                        P.reduce_scatter_(acc, {L.AGG_MIN: "min", L.AGG_MAX: "max"}.get(ka.op, "sum")))
+            cnts.append(None if cnt is None else P.reduce_scatter_(cnt, "sum"))
+        rows = None if t.rows is None else P.reduce_scatter_(t.rows, "sum")
+        pres = P.reduce_scatter_(pres, "max")
+    return SlotView(t.nslots, rank * chunk, chunk, accs, cnts, rows, "bytes", pres, dist="keyrange")
 
 
 class RawGroups:
@@ -943,10 +1129,10 @@ def _finish_outputs(plan: AggPlan, acc_cols, cnt_cols, rows_col, n, out: Part):
         out[name] = col
 
 
-def _gather_state(gs: GroupState, idx, dev):
-    t = gs.table
+def _gather_view(view: SlotView, idx, dev):
+    """Accumulator / count / row-count arrays of `view` gathered at the (window-local) slots `idx`."""
     acc_cols, cnt_cols = [], []
-    for ka, acc, cnt in zip(gs.plan.kaggs, t.acc, t.cnt):
+    for acc, cnt in zip(view.acc, view.cnt):
         if acc is not None:
             dt = F64 if acc.dtype == torch.float64 else I64
             stats["launches"] += 1
@@ -959,53 +1145,44 @@ def _gather_state(gs: GroupState, idx, dev):
         else:
             cnt_cols.append(None)
     rows_col = None
-    if t.rows is not None:
+    if view.rows is not None:
         stats["launches"] += 1
-        rows_col = D.gather(DeviceColumn(t.rows, None, I64), idx, False)
+        rows_col = D.gather(DeviceColumn(view.rows, None, I64), idx, False)
     return acc_cols, cnt_cols, rows_col
 
 
-def _occupancy(t: D.GroupTable, keys: torch.Tensor):
-    """(column, predicate term) selecting the slots that received at least one row."""
-    if t.rows is not None:
-        return DeviceColumn(t.rows, None, I64), TermSpec(0, L.GT, 0)
-    if t.indicator is not None:
-        # untouched float SUM accumulator = -0.0 = the INT64_MIN bit pattern
-        return DeviceColumn(t.acc[t.indicator].view(torch.int64), None, I64), TermSpec(0, L.NE, L.EMPTY_KEY)
-    return DeviceColumn(keys, t.present, I64), TermSpec(0, L.IS_NOT_NULL, 0)
+DEFER_MAX_SLOTS = 1 << 23    # deferred compaction allocates its outputs at one row per slot of the window
 
 
-DEFER_MAX_SLOTS = 1 << 23    # deferred compaction allocates its outputs at nslots rows
-
-
-def _finalize_dense(gs: GroupState, kmin, rng, gname, gexpr, glog, plan, dev, key_nullable=True,
+def _finalize_dense(view: SlotView, kmin, gname, gexpr, glog, plan, dev, key_nullable=True,
                     check=None, fallback=None) -> Part:
-    """Dense table -> result partition.  `check`: optional int32 device flags whose first word must
-    be 0 for the result to stand (star pipeline: duplicate build keys), else `fallback()` is the
-    result.  With a NULL-free int64 key the compaction is enqueued without waiting for its count
-    (PendingPart); the flags ride on the same host copy."""
-    nslots = rng + 1
-    t = gs.table
-    ncols = 1 + sum(a is not None for a in t.acc) + sum(c is not None for c in t.cnt) + (t.rows is not None)
-    if not key_nullable and gexpr.dtype == I64 and nslots <= DEFER_MAX_SLOTS and ncols <= L.MAX_GATHER \
+    """Window of a dense table -> result partition (group key = kmin + slot; the table's last slot
+    is the NULL group).  `check`: optional int32 device flags whose first word must be 0 for the
+    result to stand (star pipeline: duplicate build keys), else `fallback()` is the result.  With a
+    NULL-free int64 key the compaction is enqueued without waiting for its count (PendingPart); the
+    flags ride on the same host copy."""
+    count = view.count
+    ncols = 1 + sum(a is not None for a in view.acc) + sum(c is not None for c in view.cnt) + (view.rows is not None)
+    if not key_nullable and gexpr.dtype == I64 and count <= DEFER_MAX_SLOTS and ncols <= L.MAX_GATHER \
             and os.environ.get("B200SQL_NO_DEFER") != "1":
-        slot_keys = torch.arange(kmin, kmin + nslots, dtype=torch.int64, device=dev)
-        occ, term = _occupancy(t, slot_keys)
-        cols, where = [occ, DeviceColumn(slot_keys, None, I64)], {}
-        for i, (acc, cnt) in enumerate(zip(t.acc, t.cnt)):
-            if acc is not None:
-                where[("a", i)] = len(cols)
-                cols.append(DeviceColumn(acc, None, F64 if acc.dtype == torch.float64 else I64))
-            if cnt is not None:
-                where[("c", i)] = len(cols)
-                cols.append(DeviceColumn(cnt, None, I64))
-        if t.rows is not None:
-            where[("r", 0)] = len(cols)
-            cols.append(DeviceColumn(t.rows, None, I64))
-        gcols = list(range(1, len(cols)))
-        stats["launches"] += 3
-        outs, count = D.select_launch(D.make_scan(cols, [term], nslots), dev, gcols, cols)
-        pending = DeviceCount(count, check) if check is not None else DeviceCount(count)
+        with _Phase("compact"):
+            slot_keys = torch.arange(kmin + view.lo, kmin + view.lo + count, dtype=torch.int64, device=dev)
+            occ, term = view.occupancy(slot_keys)
+            cols, where = [occ, DeviceColumn(slot_keys, None, I64)], {}
+            for i, (acc, cnt) in enumerate(zip(view.acc, view.cnt)):
+                if acc is not None:
+                    where[("a", i)] = len(cols)
+                    cols.append(DeviceColumn(acc, None, F64 if acc.dtype == torch.float64 else I64))
+                if cnt is not None:
+                    where[("c", i)] = len(cols)
+                    cols.append(DeviceColumn(cnt, None, I64))
+            if view.rows is not None:
+                where[("r", 0)] = len(cols)
+                cols.append(DeviceColumn(view.rows, None, I64))
+            gcols = list(range(1, len(cols)))
+            stats["launches"] += 3
+            outs, cnt_dev = D.select_launch(D.make_scan(cols, [term], count), dev, gcols, cols)
+            pending = DeviceCount(cnt_dev, check) if check is not None else DeviceCount(cnt_dev)
 
         def thunk():
             vals = pending.get()
@@ -1014,77 +1191,73 @@ def _finalize_dense(gs: GroupState, kmin, rng, gname, gexpr, glog, plan, dev, ke
                 return fallback()
             got = {g: DeviceColumn(o[:total], None, cols[g].dtype) for g, o in zip(gcols, outs)}
             kcol = DeviceColumn(got[1].data, None, I64, glog)
-            acc_cols = [got.get(where.get(("a", i))) for i in range(len(t.acc))]
-            cnt_cols = [got.get(where.get(("c", i))) for i in range(len(t.cnt))]
-            return finish(RawGroups({gname: kcol}, acc_cols, cnt_cols, got.get(where.get(("r", 0))), total), plan)
+            acc_cols = [got.get(where.get(("a", i))) for i in range(len(view.acc))]
+            cnt_cols = [got.get(where.get(("c", i))) for i in range(len(view.cnt))]
+            res = finish(RawGroups({gname: kcol}, acc_cols, cnt_cols, got.get(where.get(("r", 0))), total), plan)
+            res.dist = view.dist
+            return res
 
-        return PendingPart(thunk)
-    out = finish(_extract_dense(gs, kmin, rng, gname, gexpr, glog, dev, key_nullable), plan)
+        out = PendingPart(thunk)
+        out.dist = view.dist
+        return out
+    out = finish(_extract_dense(view, kmin, gname, gexpr, glog, dev, key_nullable), plan)
+    out.dist = view.dist
     if check is not None and int(check[0].item()):
         return fallback()
     return out
 
 
-def _extract_dense(gs: GroupState, kmin, rng, gname, gexpr, glog, dev, key_nullable=True) -> RawGroups:
-    nslots = rng + 1
-    t = gs.table
-    slot_keys = torch.arange(kmin, kmin + nslots, dtype=torch.int64, device=dev)
+def _extract_dense(view: SlotView, kmin, gname, gexpr, glog, dev, key_nullable=True) -> RawGroups:
+    count = view.count
+    slot_keys = torch.arange(kmin + view.lo, kmin + view.lo + count, dtype=torch.int64, device=dev)
+    occ, term = view.occupancy(slot_keys)
     if not key_nullable and gexpr.dtype == I64:
-        # the key column has no NULLs, so the NULL slot stays empty: no validity work, no host sync
-        occ, term = _occupancy(t, slot_keys)
+        # the key column has no NULLs, so the NULL slot stays empty: no validity work.
         # compaction and gathers in one write pass: keys and every accumulator array ride along as
         # gather columns of b2_select_write (<= 8), instead of one b2_gather launch each
         cols = [occ, DeviceColumn(slot_keys, None, I64)]
         where = {}
-        for i, (acc, cnt) in enumerate(zip(t.acc, t.cnt)):
+        for i, (acc, cnt) in enumerate(zip(view.acc, view.cnt)):
             if acc is not None:
                 where[("a", i)] = len(cols)
                 cols.append(DeviceColumn(acc, None, F64 if acc.dtype == torch.float64 else I64))
             if cnt is not None:
                 where[("c", i)] = len(cols)
                 cols.append(DeviceColumn(cnt, None, I64))
-        if t.rows is not None:
-            where[("r", 0)] = 0
+        if view.rows is not None:
+            where[("r", 0)] = len(cols)
+            cols.append(DeviceColumn(view.rows, None, I64))
         if len(cols) - 1 <= L.MAX_GATHER:
-            scan = D.make_scan(cols, [term], nslots)
-            gcols = list(range(1, len(cols))) if t.rows is None else list(range(0, len(cols)))
-            gcols = gcols[: L.MAX_GATHER] if len(gcols) <= L.MAX_GATHER else None
-        else:
-            gcols = None
-        if gcols is not None:
+            gcols = list(range(1, len(cols)))
             stats["launches"] += 3
-            _, outs, total = D.select(scan, dev, gcols, want_idx=False, cols=cols)
+            _, outs, total = D.select(D.make_scan(cols, [term], count), dev, gcols, want_idx=False, cols=cols)
             got = {g: DeviceColumn(o.data, None, o.dtype) for g, o in zip(gcols, outs)}
             kcol = DeviceColumn(got[1].data, None, I64, glog)
-            acc_cols = [got.get(where.get(("a", i))) for i in range(len(t.acc))]
-            cnt_cols = [got.get(where.get(("c", i))) for i in range(len(t.cnt))]
-            rows_col = got.get(0) if t.rows is not None else None
-            return RawGroups({gname: kcol}, acc_cols, cnt_cols, rows_col, total)
+            acc_cols = [got.get(where.get(("a", i))) for i in range(len(view.acc))]
+            cnt_cols = [got.get(where.get(("c", i))) for i in range(len(view.cnt))]
+            return RawGroups({gname: kcol}, acc_cols, cnt_cols, got.get(where.get(("r", 0))), total)
         stats["launches"] += 4
-        scan = D.make_scan([occ], [term], nslots)
-        idx, _, total = D.select(scan, dev, (), want_idx=True, cols=[occ])
+        idx, _, total = D.select(D.make_scan([occ], [term], count), dev, (), want_idx=True, cols=[occ])
         kcol = D.gather(DeviceColumn(slot_keys, None, I64, glog), idx, False)
         kcol = DeviceColumn(kcol.data, None, I64, glog)
-        acc_cols, cnt_cols, rows_col = _gather_state(gs, idx, dev)
+        acc_cols, cnt_cols, rows_col = _gather_view(view, idx, dev)
         return RawGroups({gname: kcol}, acc_cols, cnt_cols, rows_col, total)
-    # occupied slots
-    occ, term = _occupancy(t, slot_keys)
-    scan = D.make_scan([occ], [term], nslots)
+    # occupied slots of the window
     stats["launches"] += 3
-    idx, _, total = D.select(scan, dev, (), want_idx=True, cols=[occ])
-    # key column: the last slot is the NULL group
-    kvalid = torch.full((D.bitmap_words(nslots),), -1, dtype=torch.int32, device=dev)
-    last = nslots - 1
-    kvalid[last >> 5] = int(np.array([~(1 << (last & 31)) & 0xFFFFFFFF], dtype=np.uint32).view(np.int32)[0])
+    idx, _, total = D.select(D.make_scan([occ], [term], count), dev, (), want_idx=True, cols=[occ])
+    # key column: the table's last slot is the NULL group (it lies in exactly one rank's window)
+    kvalid = torch.full((D.bitmap_words(count),), -1, dtype=torch.int32, device=dev)
+    last = view.nslots - 1 - view.lo
+    if 0 <= last < count:
+        kvalid[last >> 5] = int(np.array([~(1 << (last & 31)) & 0xFFFFFFFF], dtype=np.uint32).view(np.int32)[0])
     stats["launches"] += 1
     kcol = D.gather(DeviceColumn(slot_keys, kvalid, I64), idx, True)
-    out = Part({}, total)
     if gexpr.dtype == U8:
         kc = eval_expr(Part({"k": kcol}, total), E.cast(ColRef("k", I64), U8))
         kcol = DeviceColumn(kc.data, kcol.valid, U8, glog)
     kcol.logical = glog
     kcol = _drop_full_valid(kcol)
-    acc_cols, cnt_cols, rows_col = _gather_state(gs, idx, dev)
+    acc_cols, cnt_cols, rows_col = _gather_view(view, idx, dev)
     return RawGroups({gname: kcol}, acc_cols, cnt_cols, rows_col, total)
 
 
@@ -1125,17 +1298,13 @@ def _extract_hash1(gs, tkeys, cap, fl, gname, gexpr, glog, dev) -> RawGroups:
             valid[null_pos >> 5] = int(np.array([~(1 << (null_pos & 31)) & 0xFFFFFFFF], dtype=np.uint32).view(np.int32)[0])
             kcol = DeviceColumn(kcol.data, valid, kcol.dtype)
     kcol.logical = glog
-    acc_cols, cnt_cols, rows_col = _gather_state(gs, idx, dev)
+    acc_cols, cnt_cols, rows_col = _gather_view(SlotView.whole(gs.table, gs.table.alloc), idx, dev)
     return RawGroups({gname: kcol}, acc_cols, cnt_cols, rows_col, total)
 
 
-def _finalize_hashk(gs, tkeys, tnulls, cap, gnames, gexprs, glogs, plan, dev) -> Part:
-    return finish(_extract_hashk(gs, tkeys, tnulls, cap, gnames, gexprs, glogs, dev), plan)
-
-
 def _extract_hashk(gs, tkeys, tnulls, cap, gnames, gexprs, glogs, dev) -> RawGroups:
-    t = gs.table
-    occ, term = _occupancy(t, tkeys[:cap])
+    view = SlotView.whole(gs.table, cap)
+    occ, term = view.occupancy(tkeys[:cap])
     scan = D.make_scan([occ], [term], cap)
     stats["launches"] += 3
     idx, _, total = D.select(scan, dev, (), want_idx=True, cols=[occ])
@@ -1163,7 +1332,7 @@ def _extract_hashk(gs, tkeys, tnulls, cap, gnames, gexprs, glogs, dev) -> RawGro
         else:
             col = DeviceColumn(kc.data, kc.valid, I64, lg)
         out[g] = col
-    acc_cols, cnt_cols, rows_col = _gather_state(gs, idx, dev)
+    acc_cols, cnt_cols, rows_col = _gather_view(view, idx, dev)
     return RawGroups(out, acc_cols, cnt_cols, rows_col, total)
 
 
@@ -1227,24 +1396,26 @@ def _star_dense_fast(src, fact, dim, fk_e, pk_e, gexprs, aggs, fact_pred, dim_pr
     buf = torch.full((prange + 4,), -1, dtype=torch.int32, device=dev)
     lookup, flags = buf[:prange], buf[prange:]
     flags.zero_()
-    if owner:
-        needed: Set[str] = {pk_e.name, ge.name}
-        for p in dpred:
-            p.refs(needed)
-        for part in materialize(dim.source, needed):
-            if part.n == 0:
-                continue
-            ctx = ScanCtx(part, dpred)
-            pk_slot, g_slot = ctx.slot(pk_e), ctx.slot(ge)     # slots first: scan() snapshots the columns
-            stats["launches"] += 1
-            L.star_build_scan(C.byref(ctx.scan()), pk_slot, g_slot, pmin, prange, gmin, nslots - 1,
-                              D.ptr(lookup), D.ptr(flags), D.stream_ptr())
+    with _Phase("build"):
+        if owner:
+            needed: Set[str] = {pk_e.name, ge.name}
+            for p in dpred:
+                p.refs(needed)
+            for part in materialize(dim.source, needed):
+                if part.n == 0:
+                    continue
+                ctx = ScanCtx(part, dpred)
+                pk_slot, g_slot = ctx.slot(pk_e), ctx.slot(ge)     # slots first: scan() snapshots the columns
+                stats["launches"] += 1
+                L.star_build_scan(C.byref(ctx.scan()), pk_slot, g_slot, pmin, prange, gmin, nslots - 1,
+                                  D.ptr(lookup), D.ptr(flags), D.stream_ptr())
     if world > 1 and dist == "root":
         # the build side crosses NVLink as the finished 4-byte-per-key lookup, not as its columns
-        P.broadcast_(buf, 0)
+        with _Phase("bcast"):
+            P.broadcast_(buf, 0)
     plan = AggPlan([(E.substitute(e, fact.exprs) if e is not None else None, o, f) for e, o, f in aggs],
                    _nullable_fn(fact))
-    gs = GroupState(dev, nslots, plan, need_present=True)
+    gs = GroupState(dev, nslots, plan, need_present=True, alloc=_padded_slots(nslots, sharded))
     lk = L.StarLookup()
     lk.dense, lk.lookup, lk.kmin, lk.range = 1, lookup.data_ptr(), pmin, prange
     needed = set(fk_e.refs())
@@ -1252,19 +1423,19 @@ def _star_dense_fast(src, fact, dim, fk_e, pk_e, gexprs, aggs, fact_pred, dim_pr
         ka.expr.refs(needed)
     for p in fpred:
         p.refs(needed)
-    for part in materialize(fact.source, needed):
-        if part.n == 0:
-            continue
-        ctx = ScanCtx(part, fpred)
-        fk_slot = ctx.slot(fk_e)
-        gs.bind(ctx)
-        stats["launches"] += 1
-        ev = _kernel_event_begin("b2_star_agg_kernel", part.n)
-        L.star_agg(C.byref(ctx.scan()), fk_slot, C.byref(lk), gs.table.aggs, len(gs.table.specs),
-                   C.byref(gs.table.state), D.stream_ptr())
-        _kernel_event_end(ev)
-    if sharded:
-        _allreduce_table(gs.table, plan)
+    with _Phase("scan"):
+        for part in materialize(fact.source, needed):
+            if part.n == 0:
+                continue
+            ctx = ScanCtx(part, fpred)
+            fk_slot = ctx.slot(fk_e)
+            gs.bind(ctx)
+            stats["launches"] += 1
+            ev = _kernel_event_begin("b2_star_agg_kernel", part.n)
+            L.star_agg(C.byref(ctx.scan()), fk_slot, C.byref(lk), gs.table.aggs, len(gs.table.specs),
+                       C.byref(gs.table.state), D.stream_ptr())
+            _kernel_event_end(ev)
+    view = _merge_dense(gs.table, plan, sharded, dev)
     glog = dim.col_type(gexprs[0].name)[1] if isinstance(gexprs[0], ColRef) else "int64"
     stats["star_fused"] += 1
 
@@ -1273,7 +1444,7 @@ def _star_dense_fast(src, fact, dim, fk_e, pk_e, gexprs, aggs, fact_pred, dim_pr
         return run_aggregate(src, allow_fast=False)
 
     # the duplicate-key flags ride on the (deferred) host copy of the group count
-    return _finalize_dense(gs, gmin, grng, src.group_cols[0], gexprs[0], glog, plan, dev, key_nullable=gnull,
+    return _finalize_dense(view, gmin, src.group_cols[0], gexprs[0], glog, plan, dev, key_nullable=gnull,
                            check=flags, fallback=general)
 
 
@@ -1379,7 +1550,8 @@ def try_star(src: AggSource, child: LazyFrame, gexprs, aggs, pred, sharded, allo
         if int(flags[0].item()):
             return None
         nslots = cap
-    gs = GroupState(dev, nslots, plan, need_present=True)
+    gs = GroupState(dev, nslots, plan, need_present=True,
+                    alloc=_padded_slots(nslots, sharded) if dense_groups else None)
 
     # pk -> slot lookup
     lk = L.StarLookup()
@@ -1427,12 +1599,174 @@ def try_star(src: AggSource, child: LazyFrame, gexprs, aggs, pred, sharded, allo
                    C.byref(gs.table.state), D.stream_ptr())
         _kernel_event_end(ev)
     stats["star_fused"] += 1
-    if sharded:
-        _allreduce_table(gs.table, plan)
     if dense_groups:
-        return _finalize_dense(gs, gmin, grng, src.group_cols[0], gexprs[0], glog[0], plan, dev,
+        # dense slots = key - gmin on every rank (gmin comes from the broadcast dim rows): mergeable by slot
+        view = _merge_dense(gs.table, plan, sharded, dev)
+        return _finalize_dense(view, gmin, src.group_cols[0], gexprs[0], glog[0], plan, dev,
                                key_nullable=gkey_cols[0].valid is not None)
-    return _finalize_hashk(gs, tkeys, tnulls, nslots, src.group_cols, gexprs, glog, plan, dev)
+    # hashed slots are assigned by CAS races, i.e. differently on every rank: partial tables are
+    # merged BY KEY along the reduction tree (like any hash GROUP BY), never element-wise by slot
+    raw = _extract_hashk(gs, tkeys, tnulls, nslots, src.group_cols, gexprs, glog, dev)
+    if sharded:
+        from .merge import tree_merge_raw
+        raw = tree_merge_raw(raw, plan, src.options, dev)
+    return finish(raw, plan)
+
+
+# ---------------------------------------------------------------------------------------------
+# fused join + global aggregate: Aggregate(no GROUP BY) <- Inner Join(fk = unique dense pk)
+# ---------------------------------------------------------------------------------------------
+def _strip_f64_cast(e: Expr) -> Expr:
+    """cast(int expr -> float64) -> the int expr: b2_join_agg converts inside the kernel, and an
+    int64 payload can then be stored as 4-byte offsets (half the L2 footprint of the build side)."""
+    if isinstance(e, Call) and e.op == "cast" and e.dtype == F64 and e.args[0].dtype == I64:
+        return e.args[0]
+    return e
+
+
+def _split_two_sided(e: Expr, pnames: Set[str], bnames: Set[str]):
+    """-> (probe-side expr | None, build-side expr | None, B2_JA_* combine), or None when `e` is not
+    of the shape  P,  B,  P*B,  P+B,  P-B,  B-P."""
+    side = _side_of(e, pnames, bnames)
+    if side == "left":
+        return e, None, L.JA_P
+    if side == "right":
+        return None, e, L.JA_B
+    if side != "both" or not isinstance(e, Call) or e.op not in ("mul", "add", "sub"):
+        return None
+    x, y = e.args
+    sx, sy = _side_of(x, pnames, bnames), _side_of(y, pnames, bnames)
+    comb = {"mul": L.JA_MUL, "add": L.JA_ADD, "sub": L.JA_SUB}[e.op]
+    if sx == "left" and sy == "right":
+        return _strip_f64_cast(x), _strip_f64_cast(y), comb
+    if sx == "right" and sy == "left":
+        return _strip_f64_cast(y), _strip_f64_cast(x), (L.JA_RSUB if e.op == "sub" else comb)
+    return None
+
+
+def try_join_agg(src: AggSource, child: LazyFrame, aggs, pred, sharded) -> Optional[Part]:
+    """Global aggregates straight off the probe scan of an inner join on a unique dense key
+    (b2_join_agg): nothing of the join is materialised.  None = shape does not apply."""
+    js: JoinSource = child.source
+    if js.how != "inner" or len(js.left_on) != 1:
+        return None
+    swap, _ = join_sides(js)
+    probe, build = (js.right, js.left) if swap else (js.left, js.right)
+    pkey, bkey = (js.right_on[0], js.left_on[0]) if swap else (js.left_on[0], js.right_on[0])
+    if not isinstance(probe.source, TableSource):
+        return None
+    pk_e, bk_e = probe.exprs[pkey], build.exprs[bkey]
+    if pk_e.dtype != I64 or bk_e.dtype != I64:
+        return None
+    pnames, bnames = set(probe.columns), set(build.columns)
+    probe_pred, build_pred = [], []
+    for p in pred:
+        s_ = _side_of(p, pnames, bnames)
+        if s_ == "left":
+            probe_pred.append(p)
+        elif s_ == "right":
+            build_pred.append(p)
+        else:
+            return None
+    # aggregate inputs in terms of the join's inputs, split into a probe part and a build part
+    plan = AggPlan(aggs, lambda e: True)      # NULLs are tracked per aggregate by the kernel anyway
+    if len(plan.kaggs) + 1 > L.MAX_AGGS:
+        return None
+    split, bexprs = [], []
+    for ka in plan.kaggs:
+        sp = _split_two_sided(ka.expr, pnames, bnames)
+        if sp is None:
+            return None
+        pe, be, comb = sp
+        if pe is not None and pe.dtype == U8 or be is not None and be.dtype == U8:
+            return None
+        bi = -1
+        if be is not None:
+            be = E.substitute(be, build.exprs)
+            for i, x in enumerate(bexprs):
+                if repr(x) == repr(be):
+                    bi = i
+            if bi < 0:
+                bexprs.append(be)
+                bi = len(bexprs) - 1
+        split.append((E.substitute(pe, probe.exprs) if pe is not None else None, bi, comb))
+    if len(bexprs) > L.JA_MAX_BUILD:
+        return None
+    dev = _dev()
+
+    # ---- build side: key + payload expressions of the (filtered) build rows, whole on every rank
+    b_exprs = {"__bk": bk_e}
+    for i, be in enumerate(bexprs):
+        b_exprs[f"__b{i}"] = be
+    bpred = build.pred + [E.substitute(p, build.exprs) for p in build_pred]
+    with _Phase("build"):
+        bpart = concat_parts(execute(LazyFrame(build.source, b_exprs, bpred)), list(b_exprs))
+    if P.world()[1] > 1:
+        bd = frame_distribution(build)
+        if bd in ("root", "sharded") and not (bd == "root" and frame_distribution(probe) == "root"):
+            from .merge import broadcast_part, allgather_part
+            with _Phase("bcast"):
+                bpart = broadcast_part(bpart, dev) if bd == "root" else allgather_part(bpart, dev)
+    if bpart.n == 0:
+        return None
+    jt = D.JoinTable([bpart["__bk"]])
+    stats["launches"] += 1
+    if not jt.dense:
+        return None                      # duplicate or sparse build keys: the general join handles it
+    stats["launches"] += max(1, len(bexprs))
+    jt.key_layout([bpart[f"__b{i}"] for i in range(len(bexprs))])
+
+    # ---- one pass over the probe partitions
+    ppred, never = simplify_pred(probe.pred + [E.substitute(p, probe.exprs) for p in probe_pred])
+    k = len(plan.kaggs)
+    acc_d = torch.zeros(k + 1, dtype=torch.int64, device=dev)
+    cnt_d = torch.zeros(k + 1, dtype=torch.int64, device=dev)
+    ws = D._workspace(dev, L.scan_agg_ws_bytes())
+    nb = len(bexprs)
+    bc = (L.Col * max(1, nb))(*[c.as_struct() for c in jt.keyed_cols])
+    bb = (C.c_int64 * max(1, nb))(*jt.keyed_base)
+    needed: Set[str] = set(pk_e.refs())
+    for pe, _, _ in split:
+        if pe is not None:
+            pe.refs(needed)
+    for p in ppred:
+        p.refs(needed)
+    first = True
+    float_acc = [False] * k
+    for part in ([] if never else materialize(probe.source, needed)):
+        if part.n == 0:
+            continue
+        ctx = ScanCtx(part, ppred)
+        kslot = ctx.slot(pk_e)
+        arr = (L.JoinAgg * (k + 1))()
+        for i, (ka, (pe, bi, comb)) in enumerate(zip(plan.kaggs, split)):
+            arr[i].pcol = ctx.slot(pe) if pe is not None else -1
+            arr[i].bcol, arr[i].combine, arr[i].op = bi, comb, ka.op
+            pf = pe is not None and pe.dtype == F64
+            bf = bi >= 0 and jt.keyed_cols[bi].dtype == F64
+            float_acc[i] = pf or bf or ka.op == L.AGG_SUMF
+        arr[k].pcol, arr[k].bcol, arr[k].combine, arr[k].op = -1, -1, L.JA_ROWS, L.AGG_COUNT
+        stats["launches"] += 2
+        ev = _kernel_event_begin("b2_join_agg_kernel", part.n)
+        L.join_agg(C.byref(ctx.scan()), kslot, C.byref(jt.struct), nb, bc, bb, arr, k + 1, D.ptr(acc_d), D.ptr(cnt_d),
+                   0 if first else 1, D.ptr(ws), D.stream_ptr())
+        _kernel_event_end(ev)
+        first = False
+    if first:
+        acc = np.array([{L.AGG_MIN: (1 << 63) - 1, L.AGG_MAX: -(1 << 63)}.get(ka.op, 0) for ka in plan.kaggs] + [0],
+                       dtype=np.int64)
+        cnt = np.zeros(k + 1, dtype=np.int64)
+    else:
+        acc, cnt = acc_d.cpu().numpy(), cnt_d.cpu().numpy()
+        stats["d2h_bytes"] += 16 * (k + 1)
+    stats["join_agg"] = stats.get("join_agg", 0) + 1
+    if sharded:
+        # the all-reduce folds by the accumulator's arithmetic type: mark float accumulators as such
+        for ka, f in zip(plan.kaggs, float_acc):
+            if f:
+                ka.dtype = F64
+        acc, cnt = _allreduce_global(acc, cnt, plan, dev)
+    return _finish_global(plan, acc, cnt, dev, float_acc)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -1443,12 +1777,8 @@ def run_join(js: JoinSource, needed: Set[str]) -> List[Part]:
     how = js.how
     left, right = js.left, js.right
     lkeys, rkeys = js.left_on, js.right_on
-    # which side is hashed (build) and which streams (probe)
-    swap = False
-    if how == "right":
-        swap = True
-    elif how == "inner" and estimated_rows(left) < estimated_rows(right):
-        swap = True
+    # which side is hashed (build) and which streams (probe): agreed by all ranks
+    swap, _ = join_sides(js)
     probe, build = (right, left) if swap else (left, right)
     pkeys, bkeys = (rkeys, lkeys) if swap else (lkeys, rkeys)
     mode = {"inner": L.JOIN_INNER, "left": L.JOIN_LEFT, "right": L.JOIN_LEFT, "outer": L.JOIN_LEFT,
@@ -1474,11 +1804,16 @@ def run_join(js: JoinSource, needed: Set[str]) -> List[Part]:
         b_exprs[f"__bk{i}"] = e
     bparts = execute(LazyFrame(build.source, b_exprs, build.pred))
     bpart = concat_parts(bparts, list(b_exprs))
+    probe_dist = frame_distribution(probe)
     if P.world()[1] > 1:
         bd = frame_distribution(build)
-        if bd in ("root", "sharded") and frame_distribution(probe) == "sharded":
+        # the build side must be whole wherever probe rows live: broadcast it from its owner, or
+        # all-gather its shards (also for LEFT / SEMI / ANTI / OUTER joins: a probe row is
+        # "unmatched" only if NO rank holds a partner).  Both sides on rank 0 only: nothing to move.
+        if bd in ("root", "sharded") and not (bd == "root" and probe_dist == "root"):
             from .merge import broadcast_part, allgather_part
-            bpart = broadcast_part(bpart, dev) if bd == "root" else allgather_part(bpart, dev)
+            with _Phase("bcast"):
+                bpart = broadcast_part(bpart, dev) if bd == "root" else allgather_part(bpart, dev)
     bkey_cols = [bpart[f"__bk{i}"] for i in range(len(bk_exprs))]
     jt = D.JoinTable(bkey_cols)
     stats["launches"] += 1
@@ -1514,9 +1849,11 @@ def run_join(js: JoinSource, needed: Set[str]) -> List[Part]:
         if fused_gather and jt.dense and build_matched is None and os.environ.get("B200SQL_NO_ONEPASS") != "1":
             # direct-address table: single-pass probe (look-back offsets), row count left on the device
             rslots = [ctx.slot(ColRef(r, part[r].dtype)) for r in refs]
-            stats["launches"] += 1
+            stats["launches"] += 3
+            ev = _kernel_event_begin("b2_join_onepass", part.n)
             trim, count = D.join_probe_onepass(ctx.scan(), kslots, jt, mode, dev, ctx.cols, rslots,
                                                [bpart[n] for n in build_out], mode == L.JOIN_LEFT)
+            _kernel_event_end(ev)
             pending = DeviceCount(count)
 
             def finish_part(trim=trim, pending=pending, keep=(ctx, jt, bpart)):
@@ -1558,7 +1895,13 @@ def run_join(js: JoinSource, needed: Set[str]) -> List[Part]:
             e = probe.exprs[n]
             res[n] = const_column(e.value, e.dtype, total, dev) if isinstance(e, Lit) else eval_expr(g, e)
         outs.append(res)
-    if how == "outer" and bpart.n > 0:
+    emit_unmatched = how == "outer" and bpart.n > 0
+    if emit_unmatched and P.world()[1] > 1 and probe_dist in ("sharded", "root"):
+        # a build row is unmatched only if no rank's probe rows matched it: OR the flags over the
+        # ranks, and let exactly one rank emit the leftovers
+        P.allreduce_(build_matched, "max")
+        emit_unmatched = P.world()[0] == 0
+    if emit_unmatched:
         # build rows nobody matched, with NULL probe columns
         um = DeviceColumn(build_matched[: bpart.n], None, U8)
         scan = D.make_scan([um], [TermSpec(0, L.EQ, 0)], bpart.n)
@@ -1592,7 +1935,7 @@ def compute_frame(frame: LazyFrame):
     """Execute and bring the result to the host as a pandas DataFrame (Context.sql(...).compute())."""
     import pandas as pd
 
-    parts = execute(frame)
+    parts = [gather_keyrange(p) for p in execute(frame, top=True)]
     torch.cuda.current_stream().synchronize()
     frames = []
     for p in parts:

@@ -47,16 +47,31 @@ def broadcast_part(part, dev, src=0):
 
 
 def allgather_part(part, dev):
-    """Concatenation of every rank's `part` on every rank (build side arrives pre-sharded)."""
-    from .executor import Part, concat_parts
+    """Concatenation (in rank order) of every rank's `part` on every rank: the build side arrives
+    pre-sharded, or a key-range-sharded aggregate is needed whole.  One all-gather per column
+    buffer on max-count-padded slices, not one broadcast per rank."""
+    from .executor import Part, concat_columns
     rank, size = P.world()
     if size == 1:
         return part
-    pieces = []
     names = list(part.keys())
-    for r in range(size):
-        pieces.append(broadcast_part(part if r == rank else Part({}, 0), dev, src=r))
-    return concat_parts(pieces, names)
+    hdr = P.all_gather_ints([part.n] + [1 if part[n].valid is not None else 0 for n in names], dev)
+    counts = [h[0] for h in hdr]
+    out = Part({}, sum(counts))
+    for i, name in enumerate(names):
+        c = part[name]
+        pieces = P.all_gather_varlen(c.data.contiguous(), counts, cat=False)
+        if not any(h[1 + i] for h in hdr):
+            out[name] = DeviceColumn(torch.cat(pieces), None, c.dtype, c.logical)
+            continue
+        # some rank carries NULLs: gather the bitmap words too and re-pack row-wise on the device
+        wcounts = [(n + 31) // 32 for n in counts]
+        mine = c.valid if c.valid is not None else torch.full((wcounts[rank],), -1, dtype=torch.int32, device=dev)
+        vpieces = P.all_gather_varlen(mine.contiguous(), wcounts, cat=False)
+        cols = [DeviceColumn(d, v if hdr[r][1 + i] else None, c.dtype, c.logical)
+                for r, (d, v) in enumerate(zip(pieces, vpieces)) if counts[r] > 0]
+        out[name] = concat_columns(cols) if cols else DeviceColumn(torch.cat(pieces), None, c.dtype, c.logical)
+    return out
 
 
 def _send_part(part, names, dst):

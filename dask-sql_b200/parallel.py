@@ -37,6 +37,67 @@ def allreduce_(t: torch.Tensor, op: str = "sum") -> torch.Tensor:
     return t
 
 
+def _backend() -> str:
+    return dist.get_backend() if world()[1] > 1 else "none"
+
+
+def reduce_scatter_(t: torch.Tensor, op: str = "sum") -> torch.Tensor:
+    """Element-wise reduction of `t` over all ranks, of which this rank keeps only its own
+    contiguous 1/size slice (t.numel() must be a multiple of the world size).  NCCL: one
+    ncclReduceScatter -- (size-1)/size of the array crosses NVLink per rank instead of the
+    2(size-1)/size of an all-reduce, and the consumer (compaction of the group table) then
+    touches 1/size of the slots.  gloo (CPU tests) has no reduce-scatter: all-reduce + slice."""
+    rank, size = world()
+    if size == 1:
+        return t
+    n = t.numel()
+    assert n % size == 0, "reduce_scatter_ needs a length that is a multiple of the world size"
+    chunk = n // size
+    rop = {"sum": dist.ReduceOp.SUM, "min": dist.ReduceOp.MIN, "max": dist.ReduceOp.MAX}[op]
+    if _backend() == "nccl":
+        out = torch.empty(chunk, dtype=t.dtype, device=t.device)
+        dist.reduce_scatter_tensor(out, t, op=rop)
+        return out
+    dist.all_reduce(t, op=rop)
+    return t[rank * chunk:(rank + 1) * chunk].clone()
+
+
+def all_gather_varlen(t: torch.Tensor, counts: Sequence[int], cat: bool = True):
+    """Concatenation over ranks of the first counts[r] elements of every rank's 1-D `t`
+    (ONE collective on max(counts)-padded buffers instead of one broadcast per rank).
+    cat=False returns the per-rank pieces (views of the receive buffer) instead."""
+    rank, size = world()
+    if size == 1:
+        return t[: counts[0]] if cat else [t[: counts[0]]]
+    m = max(max(counts), 1)
+    send = t
+    if t.numel() != m:
+        send = torch.zeros(m, dtype=t.dtype, device=t.device)
+        send[: counts[rank]] = t[: counts[rank]]
+    if _backend() == "nccl":
+        recv = torch.empty(size * m, dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(recv, send.contiguous())
+        pieces = [recv[r * m: r * m + counts[r]] for r in range(size)]
+    else:
+        bufs = [torch.empty(m, dtype=t.dtype, device=t.device) for _ in range(size)]
+        dist.all_gather(bufs, send.contiguous())
+        pieces = [bufs[r][: counts[r]] for r in range(size)]
+    if not cat:
+        return pieces
+    return torch.cat(pieces)
+
+
+def all_gather_ints(values: Sequence[int], device) -> List[List[int]]:
+    """Every rank's small list of integers on every rank (one tiny all-gather + one host read)."""
+    rank, size = world()
+    if size == 1:
+        return [list(values)]
+    t = torch.tensor(list(values), dtype=torch.int64, device=device)
+    bufs = [torch.empty_like(t) for _ in range(size)]
+    dist.all_gather(bufs, t)
+    return torch.stack(bufs).cpu().tolist()
+
+
 def broadcast_(t: torch.Tensor, src: int = 0) -> torch.Tensor:
     if world()[1] > 1:
         dist.broadcast(t, src=src)

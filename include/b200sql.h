@@ -350,6 +350,38 @@ int32_t b2_join_onepass(const b2_scan_t* scan, const int32_t* probe_keys, const 
                         const b2_col_t* build_cols, const int64_t* build_base, void* const* build_out,
                         uint32_t* const* build_valid, void* stream);
 
+/* ---- inner join fused with GLOBAL aggregates over both sides (C3, non-materialising) ---------- */
+/* One pass over the probe partition: predicate -> presence + payload lookup at the key offset ->
+ * combine -> aggregate; no join row is materialised.  Replaces, fused, join.py:189-248 (merge:
+ * factorize + indexers + take of every column) followed by the constant-key global aggregate of
+ * aggregate.py:305-306,576 for plans  Aggregate(no GROUP BY) <- Inner Join(fk = unique dense pk)
+ * whose aggregate inputs are  P,  B,  P*B,  P+B,  P-B  or  B-P  with P a probe-side and B a
+ * build-side column (single-sided sub-expressions are evaluated into columns first).
+ * jt must be the key-ordered layout (dense == 2, b2_join_key_layout); build_cols[b] are its payload
+ * columns in key order (B2_I64 / B2_F64, or B2_U32 with build_base[b]).  Arithmetic is float64 as soon
+ * as one side is float64 (the int side is converted, like pandas' upcast), else wrapping int64.
+ * A row contributes to an aggregate iff it finds a build row and neither input is NULL/NaN.
+ * Outputs as for b2_scan_agg (raw 64-bit accumulators + non-null counts, `accumulate` to combine
+ * partitions); an aggregate with combine == B2_JA_ROWS only counts the join's rows.
+ * ws >= b2_scan_agg_ws_bytes(). */
+#define B2_JA_MAX_BUILD 4
+#define B2_JA_P     0   /* value = P                */
+#define B2_JA_B     1   /* value = B                */
+#define B2_JA_MUL   2   /* value = P * B            */
+#define B2_JA_ADD   3   /* value = P + B            */
+#define B2_JA_SUB   4   /* value = P - B            */
+#define B2_JA_RSUB  5   /* value = B - P            */
+#define B2_JA_ROWS  6   /* COUNT(*) of the join     */
+typedef struct b2_joinagg {
+  int32_t pcol;      /* probe input: index into scan.cols, or -1 */
+  int32_t bcol;      /* build input: index into build_cols, or -1 */
+  int32_t combine;   /* B2_JA_* */
+  int32_t op;        /* B2_AGG_* applied to the combined value */
+} b2_joinagg_t;
+int32_t b2_join_agg(const b2_scan_t* scan, int32_t probe_key, const b2_jointable_t* jt, int32_t nbuild,
+                    const b2_col_t* build_cols, const int64_t* build_base, const b2_joinagg_t* aggs, int32_t naggs,
+                    int64_t* d_out_acc, int64_t* d_out_cnt, int32_t accumulate, void* ws, void* stream);
+
 /* ---- group tables far beyond L2 (C5: 100M keys) ----------------------------------------------- */
 /* Reorder the rows of `scan` that pass its terms by key RANGE, so that b2_groupby_dense over the
  * reordered arrays touches one L2-sized slice of the group table after the other (instead of a random

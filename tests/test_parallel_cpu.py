@@ -126,3 +126,97 @@ def test_gloo_broadcast_allgather_and_tree_merge(size, fan_in):
         assert res["k"].tolist() == exp["k"].tolist()
         assert res["c"].tolist() == exp["c"].tolist()
         np.testing.assert_allclose(res["s"].to_numpy(), exp["s"].to_numpy(), rtol=1e-12)
+
+
+def _dense_worker(rank, size, port, out_q):
+    """Dense partial tables -> reduce-scatter by slot range.  The presence derivation is a CUDA
+    pass in the product (b2_expr_eval); here it is restated with torch ops so that the PROTOCOL
+    (who ends up owning which slots, how existence travels) runs on gloo."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=size)
+    try:
+        from dask_sql_b200 import executor as X, parallel as P, merge
+        from dask_sql_b200.device import DeviceColumn, I64
+        from dask_sql_b200.executor import Part
+        dev = torch.device("cpu")
+
+        # --- helpers
+        assert P.all_gather_ints([rank, 10 * rank], dev) == [[r, 10 * r] for r in range(size)]
+        counts = [r + 1 for r in range(size)]
+        mine = torch.arange(counts[rank], dtype=torch.int64) + 100 * rank
+        got = P.all_gather_varlen(mine, counts)
+        assert got.tolist() == [100 * r + i for r in range(size) for i in range(r + 1)]
+        t = torch.arange(4 * size, dtype=torch.float64) * (rank + 1)
+        own = P.reduce_scatter_(t.clone(), "sum")
+        tot = sum(r + 1 for r in range(size))
+        assert own.tolist() == [float(i * tot) for i in range(4 * rank, 4 * rank + 4)]
+
+        # --- uneven all-gather of a partition (rank r contributes r rows; rank 0 none)
+        p = Part({"k": DeviceColumn(torch.arange(rank, dtype=torch.int64) + 1000 * rank, None, I64)}, rank)
+        allp = merge.allgather_part(p, dev)
+        assert allp["k"].data.tolist() == [1000 * r + i for r in range(size) for i in range(r)]
+
+        # --- the dense merge: 1000 logical slots (+ NULL slot), float SUM whose accumulator doubles
+        # as the local presence flag (-0.0 = untouched); 30 % of the slots are hit by NO rank
+        nslots = 1001
+        alloc = X._padded_slots(nslots, True)
+        assert alloc % (32 * size) == 0 and alloc >= nslots
+        rng = np.random.default_rng(5)
+        ever = rng.random(nslots) < 0.7
+        ever[-1] = False                                     # the NULL slot stays empty
+        rng_r = np.random.default_rng(50 + rank)
+        hit = ever & (rng_r.random(nslots) < 0.5)
+        vals = np.where(hit, rng_r.random(nslots), 0.0)
+
+        class T:
+            pass
+
+        tbl = T()
+        tbl.nslots, tbl.alloc, tbl.indicator, tbl.rows, tbl.present = nslots, alloc, 0, None, None
+        acc = torch.full((alloc,), -0.0, dtype=torch.float64)
+        acc[:nslots][torch.from_numpy(hit)] = torch.from_numpy(vals[hit] + 0.0)
+        tbl.acc, tbl.cnt = [acc], [None]
+
+        class KA:
+            op = 0
+
+        class Plan:
+            kaggs = [KA()]
+
+        X._presence_bytes = lambda t, d: (t.acc[0].view(torch.int64) != -(1 << 63)).to(torch.uint8)
+        view = X._merge_dense(tbl, Plan(), True, dev)
+        assert view.dist == "keyrange" and view.count == alloc // size and view.lo == rank * view.count
+        assert view.occ_kind == "bytes"
+        out_q.put((rank, hit, vals, view.lo, view.occ.numpy().copy(), view.acc[0].numpy().copy()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("size", [2, 3])
+def test_gloo_dense_merge_keeps_group_existence(size):
+    """Groups that no rank saw must not appear after the merge (round-1 N=8 failure: existence was
+    inferred from a -0.0 that the collective did not preserve), groups any rank saw must."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_dense_worker, args=(r, size, port, q)) for r in range(size)]
+    for p in procs:
+        p.start()
+    results = sorted([q.get(timeout=120) for _ in range(size)], key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    nslots = 1001
+    any_hit = np.zeros(nslots, bool)
+    total = np.zeros(nslots)
+    for _, hit, vals, _, _, _ in results:
+        any_hit |= hit
+        total += vals
+    pres = np.concatenate([occ for *_, occ, _ in results])[:nslots]
+    sums = np.concatenate([acc for *_, acc in results])[:nslots]
+    los = [lo for _, _, _, lo, _, _ in results]
+    assert los == sorted(los) and los[0] == 0
+    assert (pres.astype(bool) == any_hit).all()
+    assert 0 < any_hit.sum() < nslots - 200            # the test really has never-hit groups
+    np.testing.assert_allclose(sums[any_hit], total[any_hit], rtol=1e-12)
