@@ -344,12 +344,11 @@ int32_t b2_range_partition_scatter(const b2_scan_t* scan, int32_t key_col, int64
   if (ntiles <= 0) return B2_OK;
   int64_t* ws = reinterpret_cast<int64_t*>(d_ws);
   // variant: B200SQL_SCATTER = "block" (round-1 kernel) | "warp8" | "warp16" (default warp8: rows per lane)
-  static const int variant = [] {
-    const char* e = getenv("B200SQL_SCATTER");
-    if (e && !strcmp(e, "block")) return 0;
-    if (e && !strcmp(e, "warp16")) return 16;
-    return 8;
-  }();
+  int variant = 8;   // re-read per call (cheap) so that tests and A/B runs can switch in-process
+  if (const char* e = getenv("B200SQL_SCATTER")) {
+    if (!strcmp(e, "block")) variant = 0;
+    else if (!strcmp(e, "warp16")) variant = 16;
+  }
   if (variant) {
     unsigned long long* cur = reinterpret_cast<unsigned long long*>(ws + nbuckets + 1);
     cudaStream_t st = (cudaStream_t)stream;

@@ -542,6 +542,9 @@ def execute(frame: LazyFrame, needed: Optional[Sequence[str]] = None, top: bool 
 # ---------------------------------------------------------------------------------------------
 # aggregation
 # ---------------------------------------------------------------------------------------------
+MOMENT_FUNCS = ("var_samp", "var_pop", "stddev_samp", "stddev_pop")
+
+
 class KAgg:
     __slots__ = ("expr", "op", "need_cnt", "dtype", "nullable")
 
@@ -555,12 +558,26 @@ class AggPlan:
     Semantics follow aggregate.py:486-495: SUM is sum(min_count=1) (all-NULL group -> NULL),
     AVG = mean (NULLs skipped), COUNT(col) skips NULLs, COUNT(*) counts rows."""
 
-    def __init__(self, aggs, nullable):
+    def __init__(self, aggs, nullable, shifts=None):
         self.kaggs: List[KAgg] = []
         self.need_rows = False
         self.outs = []  # (out_name, fn, acc_idx, cnt_ref, in_dtype, logical)  cnt_ref: int | 'rows' | None
+        self.second = {}   # moment functions: out_name -> accumulator of the sum of squared deviations
         for e, out, fn in aggs:
             fn = fn.lower()
+            if fn in MOMENT_FUNCS:
+                # VAR / STDDEV from (n, sum(x-K), sum((x-K)^2)): the three sums are additive over
+                # partitions and GPUs, and with K near the data (the midpoint of the column's range,
+                # agreed by all ranks) the subtraction S2 - S1^2/n no longer cancels catastrophically
+                # for large-mean data the way sum-of-squares around zero does.  (pandas' groupby var is
+                # Welford's update, aggregate.py:129-231 builds on it.)
+                x = E.cast(e, F64)
+                k_shift = float((shifts or {}).get(repr(e), 0.0))
+                d = E.binop("sub", x, k_shift) if k_shift else x
+                a1 = self._slot(d, L.AGG_SUM, True)
+                self.second[out] = self._slot(E.binop("mul", d, d), L.AGG_SUM, True)
+                self.outs.append((out, fn, a1, self._cnt(d), F64, "float64"))
+                continue
             lg = (e.logical if isinstance(e, ColRef) else _LOGICAL[e.dtype]) if e is not None else "int64"
             if fn == "size" or e is None:
                 self.need_rows = True
@@ -656,6 +673,24 @@ def _one_row(value, dtype, logical, dev) -> DeviceColumn:
     return c
 
 
+def _moment_shifts(aggs, parts, child, sharded):
+    """{repr(input expr): K} for the VAR / STDDEV aggregates: K = midpoint of the input's value range
+    (cached table statistics for plain columns), the same on every rank."""
+    shifts = {}
+    for e, _, fn in aggs:
+        if e is None or fn.lower() not in MOMENT_FUNCS or repr(e) in shifts:
+            continue
+        st = _key_stats(parts, e, child)
+        lo, hi = (float(st.vmin), float(st.vmax)) if st.vmin is not None else (float("inf"), float("-inf"))
+        if sharded:
+            t = torch.tensor([lo, -hi], dtype=torch.float64, device=_dev())
+            P.allreduce_(t, "min")
+            lo, hi = float(t[0].item()), -float(t[1].item())
+        mid = (lo + hi) / 2 if lo <= hi else 0.0
+        shifts[repr(e)] = mid if np.isfinite(mid) else 0.0
+    return shifts
+
+
 def run_aggregate(src: AggSource, allow_fast=True) -> Part:
     child = src.child
     pred, never = simplify_pred(child.pred)
@@ -679,7 +714,7 @@ def run_aggregate(src: AggSource, allow_fast=True) -> Part:
     for p in pred:
         p.refs(needed)
     parts = [] if never else materialize(child.source, needed)
-    plan = AggPlan(aggs, _nullable_fn(child))
+    plan = AggPlan(aggs, _nullable_fn(child), _moment_shifts(aggs, parts, child, sharded))
     if not gexprs:
         return global_aggregate(parts, pred, plan, sharded)
     return grouped_aggregate(parts, pred, gexprs, src.group_cols, plan, child, sharded, src.options)
@@ -730,6 +765,18 @@ def _finish_global(plan: AggPlan, acc, cnt, dev, float_acc=None) -> Part:
         is_f = in_dt == F64 or bool(float_acc and a is not None and float_acc[a])
         if fn in ("size", "count"):
             val, dt, lgo = n_valid, I64, "int64"
+        elif fn in MOMENT_FUNCS:
+            dt, lgo = F64, "float64"
+            ddof = 0 if fn.endswith("pop") else 1
+            if n_valid <= ddof:
+                val = None
+            else:
+                s1 = acc[a:a + 1].view(np.float64)[0].item()
+                a2 = plan.second[name]
+                s2 = acc[a2:a2 + 1].view(np.float64)[0].item()
+                val = max((s2 - s1 * s1 / n_valid) / (n_valid - ddof), 0.0)
+                if fn.startswith("stddev"):
+                    val = val ** 0.5
         elif fn == "sum":
             dt, lgo = (F64, lg if in_dt == F64 else "float64") if is_f else (I64, lg if lg != "bool" else "int64")
             val = None if n_valid == 0 else (acc[a:a + 1].view(np.float64)[0].item() if is_f else int(acc[a]))
@@ -1112,6 +1159,19 @@ def _finish_outputs(plan: AggPlan, acc_cols, cnt_cols, rows_col, n, out: Part):
             continue
         acc = acc_cols[a]
         env["a"] = acc
+        if fn in MOMENT_FUNCS:
+            env["b"] = acc_cols[plan.second[name]]
+            ddof = 0 if fn.endswith("pop") else 1
+            nf = E.cast(ColRef("c", I64), F64)
+            s1, s2 = ColRef("a", F64), ColRef("b", F64)
+            var = E.binop("truediv", E.binop("sub", s2, E.binop("truediv", E.binop("mul", s1, s1), nf)),
+                          E.binop("sub", nf, float(ddof)))
+            var = E.case(E.binop("lt", var, 0.0), Lit(0.0), var)      # a constant group may round to -1e-17
+            val = E.unop("sqrt", var) if fn.startswith("stddev") else var
+            col = eval_expr(env, E.case(E.binop("gt", ColRef("c", I64), ddof), val, Lit(None, F64)))
+            col.logical = "float64"
+            out[name] = col
+            continue
         if fn == "mean":
             e = E.binop("truediv", ColRef("a", F64), ColRef("c", I64))
             e = E.case(E.binop("gt", ColRef("c", I64), 0), e, Lit(None, F64))
@@ -1450,7 +1510,7 @@ def _star_dense_fast(src, fact, dim, fk_e, pk_e, gexprs, aggs, fact_pred, dim_pr
 
 def try_star(src: AggSource, child: LazyFrame, gexprs, aggs, pred, sharded, allow_fast=True) -> Optional[Part]:
     js: JoinSource = child.source
-    if js.how != "inner" or len(js.left_on) != 1:
+    if js.how != "inner" or len(js.left_on) != 1 or any(fn.lower() in MOMENT_FUNCS for _, _, fn in aggs):
         return None
     lnames, rnames = set(js.left.columns), set(js.right.columns)
     gsides = {_side_of(e, lnames, rnames) for e in gexprs}
@@ -1648,7 +1708,7 @@ def try_join_agg(src: AggSource, child: LazyFrame, aggs, pred, sharded) -> Optio
     """Global aggregates straight off the probe scan of an inner join on a unique dense key
     (b2_join_agg): nothing of the join is materialised.  None = shape does not apply."""
     js: JoinSource = child.source
-    if js.how != "inner" or len(js.left_on) != 1:
+    if js.how != "inner" or len(js.left_on) != 1 or any(fn.lower() in MOMENT_FUNCS for _, _, fn in aggs):
         return None
     swap, _ = join_sides(js)
     probe, build = (js.right, js.left) if swap else (js.left, js.right)

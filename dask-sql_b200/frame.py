@@ -59,9 +59,12 @@ class JoinSource(Source):
                 self.schema[n] = right.col_type(n)
 
 
+MOMENT_FUNCS = ("var_samp", "var_pop", "stddev_samp", "stddev_pop")
+
+
 class AggSource(Source):
     """group_cols: child columns; aggs: [(input child column or None, output name, fn)] with
-    fn in sum | count | mean | min | max | size."""
+    fn in sum | count | mean | min | max | size | var_samp | var_pop | stddev_samp | stddev_pop."""
 
     def __init__(self, child: "LazyFrame", group_cols, aggs, options=None):
         self.child, self.group_cols, self.aggs = child, list(group_cols), list(aggs)
@@ -72,7 +75,7 @@ class AggSource(Source):
         for in_col, out, fn in self.aggs:
             if fn in ("count", "size"):
                 self.schema[out] = (I64, "int64")
-            elif fn == "mean":
+            elif fn == "mean" or fn in MOMENT_FUNCS:
                 self.schema[out] = (F64, "float64")
             else:
                 dt, lg = child.col_type(in_col)

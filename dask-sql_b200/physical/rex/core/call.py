@@ -1,13 +1,15 @@
-"""Operator calls (dask_sql/physical/rex/core/call.py:1029-1216), restricted to the operators of
-the int64/float64/bool hot path: comparisons, boolean logic, arithmetic,
-IS [NOT] NULL / TRUE / FALSE, BETWEEN, IN (list), CAST, CASE, negative, abs.
+"""RexCall: SQL operator calls of the int64/float64/bool hot path (the reference's operator table is
+dask_sql/physical/rex/core/call.py:1047-1156; SURVEY 2 row 6 lists the rows in scope): comparisons,
+boolean logic, arithmetic, IS [NOT] NULL / TRUE / FALSE / UNKNOWN, BETWEEN, IN (list), CAST, CASE,
+unary minus, ABS.
 
-Operands are LazySeries (device expressions) or python scalars; every operation only BUILDS the
-expression tree — evaluation happens fused inside the consuming kernel at compute time.
+A value is either a LazySeries -- a device expression that has not run yet -- or a Python scalar
+(None is SQL NULL).  An operator here is a plain function  (operands, rex) -> value  that only
+BUILDS expression nodes (dask-sql_b200/expr.py); the arithmetic happens later, fused into whichever
+kernel consumes the expression.  Scalars are folded on the host with SQL's three-valued logic.
 """
 import logging
 import operator
-from functools import partial, reduce
 
 import numpy as np
 
@@ -19,299 +21,206 @@ from ..convert import RexConverter
 logger = logging.getLogger(__name__)
 
 
-class Operation:
-    """Wrapper around a callable used as SQL operator (call.py:59-103)."""
-
-    needs_dc = False
-    needs_rex = False
-    needs_context = False
-    needs_rel = False
-
-    @staticmethod
-    def op_needs_dc(op):
-        return getattr(op, "needs_dc", False)
-
-    @staticmethod
-    def op_needs_rex(op):
-        return getattr(op, "needs_rex", False)
-
-    @staticmethod
-    def op_needs_context(op):
-        return getattr(op, "needs_context", False)
-
-    @staticmethod
-    def op_needs_rel(op):
-        return getattr(op, "needs_rel", False)
-
-    def __init__(self, f):
-        self.f = f
-
-    def __call__(self, *operands, **kwargs):
-        return self.f(*operands, **kwargs)
-
-    def of(self, op: "Operation") -> "Operation":
-        new_op = Operation(lambda *x, **kwargs: self(op(*x, **kwargs)))
-        new_op.needs_dc = Operation.op_needs_dc(op)
-        new_op.needs_rex = Operation.op_needs_rex(op)
-        new_op.needs_context = Operation.op_needs_context(op)
-        new_op.needs_rel = Operation.op_needs_rel(op)
-        return new_op
+# ---------------------------------------------------------------------------------------------
+# building blocks
+# ---------------------------------------------------------------------------------------------
+def _left_fold(step, alone=None):
+    """n-ary operator: ((a op b) op c) ...  (the planner hands `a + b + c` over as one call).
+    `alone` is what a single operand means (unary plus / minus)."""
+    def run(args, rex):
+        if len(args) == 1 and alone is not None:
+            return alone(args[0])
+        acc = args[0]
+        for nxt in args[1:]:
+            acc = step(acc, nxt, rex)
+        return acc
+    return run
 
 
-class ReduceOperation(Operation):
-    """n-ary operator applied by reduction over the operands (call.py:140-162)."""
-
-    def __init__(self, operation, unary_operation=None):
-        self.operation = operation
-        self.unary_operation = unary_operation or operation
-        self.needs_dc = Operation.op_needs_dc(self.operation)
-        self.needs_rex = Operation.op_needs_rex(self.operation)
-        super().__init__(self.reduce)
-
-    def reduce(self, *operands, **kwargs):
-        if len(operands) > 1:
-            return reduce(partial(self.operation, **kwargs), operands)
-        return self.unary_operation(*operands, **kwargs)
-
-
-def _null_safe(f):
-    """SQL: any NULL scalar operand makes a scalar comparison / arithmetic NULL."""
-    def g(a, b):
-        if a is None and not is_frame(b):
+def _strict(fn):
+    """Binary operator that is NULL as soon as a scalar operand is NULL.  (A NULL scalar next to a
+    column becomes a NULL literal in the expression tree and the kernel propagates it.)"""
+    def step(a, b, rex):
+        if (a is None and not is_frame(b)) or (b is None and not is_frame(a)):
             return None
-        if b is None and not is_frame(a):
-            return None
-        return f(a, b)
-    return g
+        return fn(a, b)
+    return step
 
 
-def _and(a, b):
-    if not is_frame(a) and not is_frame(b):
-        if a is False or b is False:
-            return False
-        if a is None or b is None:
-            return None
-        return bool(a) and bool(b)
-    return operator.and_(a, b)
+def _kleene_and(a, b, rex):
+    if is_frame(a) or is_frame(b):
+        return operator.and_(a, b)
+    if a is False or b is False:
+        return False
+    return None if (a is None or b is None) else bool(a and b)
 
 
-def _or(a, b):
-    if not is_frame(a) and not is_frame(b):
-        if a is True or b is True:
-            return True
-        if a is None or b is None:
-            return None
-        return bool(a) or bool(b)
-    return operator.or_(a, b)
+def _kleene_or(a, b, rex):
+    if is_frame(a) or is_frame(b):
+        return operator.or_(a, b)
+    if a is True or b is True:
+        return True
+    return None if (a is None or b is None) else bool(a or b)
 
 
-class SQLDivisionOperator(Operation):
-    """SQL '/' truncates toward zero for integer results (call.py:165-189)."""
-
-    needs_rex = True
-
-    def __init__(self):
-        super().__init__(self.div)
-
-    def div(self, lhs, rhs, rex=None):
-        output_type = sql_to_python_type(SqlTypeName.fromString(str(rex.getType()).upper()))
-        is_float = np.issubdtype(output_type, np.floating)
-        if is_frame(lhs):
-            return lhs / rhs if is_float else lhs.sql_div(rhs)
-        if is_frame(rhs):
-            return lhs / rhs if is_float else rhs.sql_div(lhs, rev=True)
-        if lhs is None or rhs is None:
-            return None
-        if is_float:
-            return lhs / rhs
-        return int(np.trunc(lhs / rhs)) if rhs != 0 else None
+def _result_is_float(rex) -> bool:
+    target = sql_to_python_type(SqlTypeName.fromString(str(rex.getType()).upper()))
+    return bool(np.issubdtype(target, np.floating))
 
 
-class CaseOperation(Operation):
-    """CASE WHEN ... (call.py:212-253): operands = when, then[, when, then ...][, else]."""
+def _divide(a, b, rex):
+    """SQL '/': true division when the plan types the result as floating point, otherwise the
+    quotient truncated toward zero (not floored); an integer division by zero is NULL."""
+    if _result_is_float(rex):
+        if not is_frame(a) and not is_frame(b):
+            return None if (a is None or b is None) else a / b
+        return a / b
+    if is_frame(a):
+        return a.sql_div(b)
+    if is_frame(b):
+        return b.sql_div(a, rev=True)
+    if a is None or b is None or b == 0:
+        return None
+    return int(np.trunc(a / b))
 
-    def __init__(self):
-        super().__init__(self.case)
 
-    def case(self, *operands):
-        assert operands
-        where, then = operands[0], operands[1]
-        if len(operands) > 3:
-            other = self.case(*operands[2:])
-        elif len(operands) == 2:
-            other = None
-        else:
-            other = operands[2]
+def _unary(on_series, on_scalar):
+    def run(args, rex):
+        (x,) = args
+        return on_series(x) if is_frame(x) else on_scalar(x)
+    return run
+
+
+def _is_null_scalar(x):
+    return x is None or (isinstance(x, float) and x != x)
+
+
+def _truth(expect: bool, negate: bool):
+    """IS [NOT] TRUE / IS [NOT] FALSE: never NULL, an unknown operand counts as 'not that'."""
+    def run(args, rex):
+        (x,) = args
+        if is_frame(x):
+            as_bool = x.astype("boolean")
+            hit = as_bool.fillna(False) if expect else ~as_bool.fillna(True)
+            return ~hit if negate else hit
+        hit = x is not None and bool(x) == expect
+        return (not hit) if negate else hit
+    return run
+
+
+def _null_test(negate: bool):
+    def run(args, rex):
+        (x,) = args
+        if is_frame(x):
+            return x.notna() if negate else x.isna()
+        return _is_null_scalar(x) != negate
+    return run
+
+
+def _case(args, rex):
+    """CASE: operands are  when_1, then_1, when_2, then_2, ... [, else];  the first true WHEN wins.
+    Built back to front so that each WHEN wraps what follows it."""
+    from .... import expr as E
+    from ....frame import LazySeries
+
+    args = list(args)
+    result = args.pop() if len(args) % 2 else None
+    while args:
+        then, when = args.pop(), args.pop()
+        if not is_frame(when):
+            if when:                         # a literal TRUE condition hides everything after it
+                result = then
+            continue
         if is_frame(then):
-            return then.where(where, other=other)
-        if is_frame(where):
-            from ....frame import LazySeries
-            from .... import expr as E
-            return LazySeries(where.source, where.pred,
-                              E.case(where.expr, E.as_expr(then) if not is_frame(then) else then.expr,
-                                     other.expr if is_frame(other) else E.as_expr(other)))
-        # `where` is a scalar here: the CASE folds to one branch
-        return then if where else other
+            result = then.where(when, other=result)
+        else:
+            other = result.expr if is_frame(result) else E.as_expr(result)
+            result = LazySeries(when.source, when.pred, E.case(when.expr, E.as_expr(then), other))
+    return result
 
 
-class CastOperation(Operation):
-    """CAST(x AS type) (call.py:256-292)."""
-
-    needs_rex = True
-
-    def __init__(self):
-        super().__init__(self.cast)
-
-    def cast(self, operand, rex=None):
-        sql_type = SqlTypeName.fromString(rex.getType())
-        if not is_frame(operand):
-            return sql_to_python_value(sql_type, operand)
-        python_type = sql_to_python_type(sql_type)
-        out = cast_column_to_type(operand, python_type)
-        return operand if out is None else out
+def _cast(args, rex):
+    (x,) = args
+    sql_type = SqlTypeName.fromString(rex.getType())
+    if not is_frame(x):
+        return sql_to_python_value(sql_type, x)
+    converted = cast_column_to_type(x, sql_to_python_type(sql_type))
+    return x if converted is None else converted      # None: already of that type family
 
 
-class IsFalseOperation(Operation):
-    def __init__(self):
-        super().__init__(self.false_)
-
-    def false_(self, df):
-        if is_frame(df):
-            return ~(df.astype("boolean").fillna(True))
-        return df is not None and not bool(df)
-
-
-class IsTrueOperation(Operation):
-    def __init__(self):
-        super().__init__(self.true_)
-
-    def true_(self, df):
-        if is_frame(df):
-            return df.astype("boolean").fillna(False)
-        return df is not None and bool(df)
+def _between(args, rex):
+    x, low, high = args
+    if any(is_frame(v) for v in (x, low, high)):
+        inside = x.between(low, high, inclusive="both") if is_frame(x) else ((low <= x) & (high >= x))
+        return ~inside if rex.isNegated() else inside
+    if x is None or low is None or high is None:
+        return None
+    return (low <= x <= high) != bool(rex.isNegated())
 
 
-class NegativeOperation(Operation):
-    def __init__(self):
-        super().__init__(lambda df: None if df is None else -df)
+def _in_list(args, rex):
+    x, candidates = args[0], args[1:]
+    if is_frame(x):
+        found = x.isin(candidates)
+        return ~found if rex.isNegated() else found
+    return (x in candidates) != bool(rex.isNegated())
 
 
-class NotOperation(Operation):
-    """NOT x (call.py:348-364)."""
+_COMPARISONS = {"=": operator.eq, "!=": operator.ne, "<>": operator.ne, ">": operator.gt, ">=": operator.ge,
+                "<": operator.lt, "<=": operator.le}
 
-    def __init__(self):
-        super().__init__(self.not_)
-
-    def not_(self, df):
-        if is_frame(df):
-            return ~(df.astype("boolean"))
-        return None if df is None else not df
-
-
-class IsNullOperation(Operation):
-    """x IS NULL (call.py:367-383); NaN counts as NULL for floats, as in pandas isna()."""
-
-    def __init__(self):
-        super().__init__(self.null)
-
-    def null(self, df):
-        if is_frame(df):
-            return df.isna()
-        return df is None or (isinstance(df, float) and df != df)
-
-
-class BetweenOperation(Operation):
-    """x [NOT] BETWEEN low AND high, bounds inclusive (call.py:963-978)."""
-
-    needs_rex = True
-
-    def __init__(self):
-        super().__init__(self.between)
-
-    def between(self, series, low, high, rex=None):
-        if is_frame(series):
-            res = series.between(low, high, inclusive="both")
-            return ~res if rex.isNegated() else res
-        res = (series >= low) & (series <= high) if is_frame(low) or is_frame(high) else low <= series <= high
-        return ~res if (rex.isNegated() and is_frame(res)) else ((not res) if rex.isNegated() else res)
+OPERATORS = {name: _left_fold(_strict(fn)) for name, fn in _COMPARISONS.items()}
+OPERATORS.update({
+    "and": _left_fold(_kleene_and),
+    "or": _left_fold(_kleene_or),
+    "+": _left_fold(_strict(operator.add), alone=lambda x: x),
+    "-": _left_fold(_strict(operator.sub), alone=lambda x: None if x is None else -x),
+    "*": _left_fold(_strict(operator.mul)),
+    "%": _left_fold(_strict(operator.mod)),
+    "/": _left_fold(_divide),
+    "negative": _unary(operator.neg, lambda x: None if x is None else -x),
+    "abs": _unary(lambda s: s.abs(), lambda x: None if x is None else abs(x)),
+    "not": _unary(lambda s: ~s.astype("boolean"), lambda x: None if x is None else not x),
+    "is null": _null_test(False),
+    "is not null": _null_test(True),
+    "is unknown": _null_test(False),
+    "is not unknown": _null_test(True),
+    "is true": _truth(True, False),
+    "is not true": _truth(True, True),
+    "is false": _truth(False, False),
+    "is not false": _truth(False, True),
+    "case": _case,
+    "cast": _cast,
+    "between": _between,
+    "in list": _in_list,
+})
 
 
-class InListOperation(Operation):
-    """x [NOT] IN (v1, v2, ...) (call.py:981-993)."""
-
-    needs_rex = True
-
-    def __init__(self):
-        super().__init__(self.inList)
-
-    def inList(self, series, *operands, rex=None):
-        if is_frame(series):
-            result = series.isin(operands)
-            return ~result if rex.isNegated() else result
-        result = series in operands
-        return (not result) if rex.isNegated() else result
-
-
-def _abs(x):
-    return x.abs() if is_frame(x) else (None if x is None else abs(x))
+def _as_positional(fn):
+    """The same operator callable the way the reference's table exposes it: f(*operands, rex=...)."""
+    def call(*operands, rex=None, **_ignored):
+        return fn(list(operands), rex)
+    return call
 
 
 class RexCallPlugin(BaseRexPlugin):
-    """Operator name -> Operation (call.py:1047-1156, hot-path rows)."""
+    """RexType.Call -> the function registered for the operator name; functions registered on the
+    schema (context.schema[...].functions) are the fallback, as in call.py:1158-1216."""
 
     class_name = "RexCall"
 
-    OPERATION_MAPPING = {
-        "between": BetweenOperation(),
-        "and": ReduceOperation(operation=_and),
-        "or": ReduceOperation(operation=_or),
-        ">": ReduceOperation(operation=_null_safe(operator.gt)),
-        ">=": ReduceOperation(operation=_null_safe(operator.ge)),
-        "<": ReduceOperation(operation=_null_safe(operator.lt)),
-        "<=": ReduceOperation(operation=_null_safe(operator.le)),
-        "=": ReduceOperation(operation=_null_safe(operator.eq)),
-        "!=": ReduceOperation(operation=_null_safe(operator.ne)),
-        "<>": ReduceOperation(operation=_null_safe(operator.ne)),
-        "+": ReduceOperation(operation=_null_safe(operator.add), unary_operation=lambda x: x),
-        "-": ReduceOperation(operation=_null_safe(operator.sub), unary_operation=lambda x: -x),
-        "/": ReduceOperation(operation=SQLDivisionOperator()),
-        "*": ReduceOperation(operation=_null_safe(operator.mul)),
-        "%": ReduceOperation(operation=_null_safe(operator.mod)),
-        "cast": CastOperation(),
-        "case": CaseOperation(),
-        "negative": NegativeOperation(),
-        "not": NotOperation(),
-        "in list": InListOperation(),
-        "is null": IsNullOperation(),
-        "is not null": NotOperation().of(IsNullOperation()),
-        "is true": IsTrueOperation(),
-        "is not true": NotOperation().of(IsTrueOperation()),
-        "is false": IsFalseOperation(),
-        "is not false": NotOperation().of(IsFalseOperation()),
-        "is unknown": IsNullOperation(),
-        "is not unknown": NotOperation().of(IsNullOperation()),
-        "abs": Operation(_abs),
-    }
+    # name -> callable(*operands, rex=None): kept for code that looks operators up by name the way
+    # it would in the reference (tests/unit/test_call.py:109-153 use the table like this)
+    OPERATION_MAPPING = {name: _as_positional(fn) for name, fn in OPERATORS.items()}
 
     def convert(self, rel, expr, dc, context):
         operands = [RexConverter.convert(rel, o, dc, context=context) for o in expr.getOperands()]
-        schema_name = context.schema_name
-        operator_name = expr.getOperatorName().lower()
-        try:
-            operation = self.OPERATION_MAPPING[operator_name]
-        except KeyError:
-            try:
-                operation = context.schema[schema_name].functions[operator_name]
-            except KeyError:  # pragma: no cover
-                raise NotImplementedError(f"RexCall operator '{operator_name}' not (yet) implemented")
-        logger.debug(f"Executing {operator_name} on {[str(LoggableDataFrame(df)) for df in operands]}")
-        kwargs = {}
-        if Operation.op_needs_dc(operation):
-            kwargs["dc"] = dc
-        if Operation.op_needs_rex(operation):
-            kwargs["rex"] = expr
-        if Operation.op_needs_context(operation):
-            kwargs["context"] = context
-        if Operation.op_needs_rel(operation):
-            kwargs["rel"] = rel
-        return operation(*operands, **kwargs)
+        name = str(expr.getOperatorName()).lower()
+        logger.debug("%s on %s", name, [str(LoggableDataFrame(o)) for o in operands])
+        fn = OPERATORS.get(name)
+        if fn is not None:
+            return fn(operands, expr)
+        registered = context.schema[context.schema_name].functions
+        if name in registered:
+            return registered[name](*operands)
+        raise NotImplementedError(f"RexCall operator '{name}' not (yet) implemented")

@@ -167,11 +167,17 @@ def test_order_by_limit_and_moment_aggregates_plan():
     assert isinstance(lim, LimitSource) and (lim.offset, lim.fetch) == (2, 10)
     srt = lim.child.source
     assert isinstance(srt, SortSource) and [(a, nf) for _, a, nf in srt.keys] == [(False, True), (True, False)]
-    # STDDEV = sqrt of the (count, sum, sum of squares) recipe, accumulated in the same AggSource
+    # STDDEV travels by name in the same AggSource as SUM: the executor expands it into shifted
+    # (count, sum, sum of squares) accumulators of the same fused pass
     agg = srt.child.source
     assert isinstance(agg, AggSource)
-    fns = sorted(f for _, _, f in agg.aggs)
-    assert fns == ["count", "sum", "sum", "sum"]
+    assert sorted(f for _, _, f in agg.aggs) == ["stddev_samp", "sum"]
+    from dask_sql_b200 import executor as X, _lib as L
+    child = agg.child
+    aggs = [(child.exprs[i], o, f) for i, o, f in agg.aggs]
+    plan = X.AggPlan(aggs, lambda e: True, {repr(aggs[1][0]): 12.5})
+    assert [k.op for k in plan.kaggs] == [L.AGG_SUM] * 3 and "sub(" in repr(plan.kaggs[1].expr)
+    assert list(plan.second.values()) == [2]
 
 
 def test_unoptimized_plan_keeps_filter_node():

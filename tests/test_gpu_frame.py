@@ -447,3 +447,87 @@ def test_groupby_range_partitioned_matches_direct(nullable_key, monkeypatch):
                                              sg=("g", lambda s: s.sum(min_count=1)), mn=("w", "min"),
                                              mx=("v", "max"), n=("v", "size")).reset_index()
     assert_frames(parted, exp, float_cols=fl, sort_by=["key"])
+
+
+@pytest.mark.parametrize("variant", ["block", "warp8", "warp16"])
+@pytest.mark.parametrize("ncarry", [1, 3])
+def test_range_partition_scatter_variants(variant, ncarry, monkeypatch):
+    """The scatter kernels (round-1 block-wide tile; warp-autonomous with 8 / 16 rows per lane; one to
+    three carried columns, i.e. staged and gathered ones) must produce the same groups.  Many buckets,
+    a ragged tail, a predicate, NULL keys."""
+    from dask_sql_b200 import executor
+    rng = np.random.default_rng(77)
+    n, nkeys = 250_013, 40_000
+    key = rng.integers(-500, -500 + nkeys, n)
+    df = pd.DataFrame({"key": pd.array(np.where(rng.random(n) < 0.01, None, key), dtype="Int64"),
+                       "v": rng.random(n), "w": rng.integers(-100, 100, n), "u": rng.random(n) * 3,
+                       "x": rng.integers(0, 10, n)})
+    spec = [("v", "sv", "sum"), ("v", "av", "mean")]
+    if ncarry == 3:
+        spec += [("w", "sw", "sum"), ("u", "mu", "max")]
+    monkeypatch.setenv("B200SQL_PARTITION_MIN_BYTES", "1")
+    monkeypatch.setenv("B200SQL_PARTITION_BUCKET_BYTES", "4096")
+    monkeypatch.setenv("B200SQL_SCATTER", variant)
+    before = executor.stats["partitioned_groupby"]
+    f = _table(df, 4)
+    got = agg(f[f["x"] > 1], ["key"], spec)
+    assert executor.stats["partitioned_groupby"] == before + 1
+    d = df[df["x"] > 1]
+    named = dict(sv=("v", "sum"), av=("v", "mean"))
+    if ncarry == 3:
+        named.update(sw=("w", "sum"), mu=("u", "max"))
+    exp = d.groupby("key", dropna=False).agg(**named).reset_index()
+    assert_frames(got, exp, float_cols=("sv", "av"), sort_by=["key"])
+
+
+def test_join_agg_fused_global_aggregates():
+    """Aggregate(no GROUP BY) <- Inner Join on a unique dense key runs as ONE pass over the probe side
+    (b2_join_agg): mixed-side products / sums / differences, single-sided inputs, COUNT(*), NULLs on
+    both sides, predicates on both sides, int and float payloads; against pandas on the merged frame."""
+    from dask_sql_b200 import Context, executor
+    rng = np.random.default_rng(12)
+    nd, nf = 20_000, 400_003
+    dim = pd.DataFrame({"pk": rng.permutation(nd) + 1000, "w": rng.integers(0, 1000, nd),
+                        "r": np.where(rng.random(nd) < 0.05, np.nan, rng.random(nd) * 10),
+                        "flag": rng.integers(0, 10, nd)})
+    fact = pd.DataFrame({"fk": pd.array(np.where(rng.random(nf) < 0.01, None, rng.integers(1000, 1000 + int(nd * 1.25), nf)),
+                                        dtype="Int64"),
+                         "v": np.where(rng.random(nf) < 0.03, np.nan, rng.random(nf)),
+                         "q": rng.integers(-50, 50, nf), "x": rng.integers(-100, 100, nf)})
+    c = Context()
+    c.create_table("fact", fact, npartitions=3, persist=True)
+    c.create_table("dim", dim, persist=True)
+    before = executor.stats.get("join_agg", 0)
+    where = "FROM fact f JOIN dim d ON f.fk = d.pk WHERE f.x > -50 AND d.flag < 7"
+    got1 = c.sql(f"SELECT SUM(f.v * d.w) AS s_vw, SUM(f.q * d.w) AS s_qw, SUM(d.r - f.v) AS s_rv, AVG(d.w) AS a_w, "
+                 f"COUNT(*) AS n {where}", return_futures=False)
+    got2 = c.sql(f"SELECT COUNT(f.v) AS n_v, MIN(f.q + d.w) AS mn, MAX(f.v * d.r) AS mx, SUM(f.q) AS s_q {where}",
+                 return_futures=False)
+    assert executor.stats.get("join_agg", 0) == before + 2
+    got = pd.concat([got1, got2], axis=1)
+    j = fact[fact.x > -50].dropna(subset=["fk"]).astype({"fk": "int64"}).merge(dim[dim.flag < 7], left_on="fk", right_on="pk")
+    exp = {"s_vw": (j.v * j.w).sum(), "s_qw": int((j.q * j.w).sum()), "s_rv": (j.r - j.v).sum(), "a_w": j.w.mean(),
+           "n": len(j), "n_v": int(j.v.count()), "mn": int((j.q + j.w).min()), "mx": (j.v * j.r).max(),
+           "s_q": int(j.q.sum())}
+    assert len(got) == 1
+    for k in ("s_qw", "n", "n_v", "mn", "s_q"):
+        assert int(got[k][0]) == exp[k], k
+    for k in ("s_vw", "s_rv", "a_w", "mx"):
+        np.testing.assert_allclose(float(got[k][0]), exp[k], rtol=RTOL, err_msg=k)
+    # no match at all -> zero rows, like the reference's groupby over an empty frame
+    got = c.sql("SELECT SUM(f.v * d.w) AS s FROM fact f JOIN dim d ON f.fk = d.pk WHERE d.flag > 100",
+                return_futures=False)
+    assert len(got) == 0
+
+
+def test_join_agg_falls_back_on_duplicate_build_keys():
+    from dask_sql_b200 import Context
+    dim = pd.DataFrame({"pk": [1, 2, 2, 3], "w": [10, 20, 30, 40]})
+    fact = pd.DataFrame({"fk": [1, 2, 3, 3, 9], "v": [1.0, 2.0, 3.0, 4.0, 5.0]})
+    c = Context()
+    c.create_table("fact", fact, persist=True)
+    c.create_table("dim", dim, persist=True)
+    got = c.sql("SELECT SUM(f.v * d.w) AS s, COUNT(*) AS n FROM fact f JOIN dim d ON f.fk = d.pk", return_futures=False)
+    j = fact.merge(dim, left_on="fk", right_on="pk")
+    assert int(got.n[0]) == len(j)
+    np.testing.assert_allclose(float(got.s[0]), (j.v * j.w).sum(), rtol=RTOL)

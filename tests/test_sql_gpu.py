@@ -156,6 +156,57 @@ def test_stddev_variance(c):
     np.testing.assert_allclose([got.sd[0], got.vs[0]], [e.i.std(), e.v.var()], rtol=1e-9)
 
 
+def test_variance_is_stable_for_large_means(c):
+    """sum-of-squares around zero loses every digit of VAR when mean >> spread (1e9 +- 1 in float64:
+    S2/n - mean^2 cancels ~18 of 16 digits); the shifted moments must agree with pandas (Welford)."""
+    rng = np.random.default_rng(8)
+    n = 200_000
+    df = pd.DataFrame({"k": rng.integers(0, 50, n), "v": 1e9 + rng.normal(0, 1, n),
+                       "w": rng.integers(10**12, 10**12 + 1000, n)})
+    c.create_table("t", df, npartitions=4)
+    got = c.sql("SELECT k, VAR_SAMP(v) AS vs, STDDEV_POP(v) AS sp, VAR_POP(w) AS vw FROM t GROUP BY k",
+                return_futures=False)
+    g = df.groupby("k")
+    exp = pd.DataFrame({"k": sorted(df.k.unique()), "vs": g.v.var().values, "sp": g.v.std(ddof=0).values,
+                        "vw": g.w.var(ddof=0).values})
+    assert_same(got, exp, ["vs", "sp", "vw"], rtol=1e-7)      # pandas itself is only ~1e-9 here
+    got = c.sql("SELECT VARIANCE(v) AS vs, STDDEV(w) AS sw FROM t", return_futures=False)
+    np.testing.assert_allclose([got.vs[0], got.sw[0]], [df.v.var(), df.w.std()], rtol=1e-7)
+    # a constant group has variance exactly 0 (not NaN from sqrt of -1e-17); one row: sample variance NULL
+    c.create_table("u", pd.DataFrame({"k": [1, 1, 1, 2], "v": [3.3e8 + 0.1] * 3 + [7.0]}))
+    got = c.sql("SELECT k, STDDEV_POP(v) AS sp, VAR_SAMP(v) AS vs FROM u GROUP BY k", return_futures=False)
+    got = got.sort_values("k").reset_index(drop=True)
+    assert got.sp.tolist() == [0.0, 0.0] and got.vs[0] == 0.0 and pd.isna(got.vs[1])
+
+
+def test_distinct_and_plain_aggregates_together(c):
+    """COUNT(DISTINCT x) next to ordinary aggregates: one pass per distinct input, stitched on the keys
+    (a literal key when there is no GROUP BY)."""
+    rng = np.random.default_rng(21)
+    n = 20_000
+    df = pd.DataFrame({"k": rng.integers(0, 30, n), "a": rng.integers(0, 100, n), "b": rng.integers(0, 7, n),
+                       "v": rng.random(n)})
+    c.create_table("t", df, npartitions=3)
+    got = c.sql("""SELECT k, COUNT(DISTINCT a) AS da, COUNT(DISTINCT b) AS db, SUM(v) AS s, COUNT(*) AS n
+                   FROM t GROUP BY k""", return_futures=False)
+    g = df.groupby("k")
+    exp = pd.DataFrame({"k": sorted(df.k.unique()), "da": g.a.nunique().values, "db": g.b.nunique().values,
+                        "s": g.v.sum().values, "n": g.size().values})
+    assert_same(got, exp, ["s"])
+    got = c.sql("SELECT COUNT(DISTINCT a) AS da, SUM(v) AS s, COUNT(DISTINCT b) AS db FROM t WHERE k < 10",
+                return_futures=False)
+    e = df[df.k < 10]
+    assert len(got) == 1 and int(got.da[0]) == e.a.nunique() and int(got.db[0]) == e.b.nunique()
+    np.testing.assert_allclose(float(got.s[0]), e.v.sum(), rtol=1e-9)
+    got = c.sql("SELECT k, SUM(v) FILTER (WHERE a > 50) AS s, COUNT(*) FILTER (WHERE b = 3) AS n3, COUNT(*) AS n "
+                "FROM t GROUP BY k", return_futures=False)
+    exp = pd.DataFrame({"k": sorted(df.k.unique()),
+                        "s": df[df.a > 50].groupby("k").v.sum().reindex(sorted(df.k.unique())).values,
+                        "n3": df[df.b == 3].groupby("k").size().reindex(sorted(df.k.unique()), fill_value=0).values,
+                        "n": g.size().values})
+    assert_same(got, exp, ["s"])
+
+
 def test_order_by_limit(c):
     # ORDER BY / LIMIT (tests/integration/test_sort.py: results compared in order)
     rng = np.random.default_rng(5)
