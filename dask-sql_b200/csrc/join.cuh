@@ -446,7 +446,9 @@ b2_join_onepass_kernel(const __grid_constant__ b2_scan_t s, int key_col, const _
                        const uint32_t* __restrict__ match_mask, int64_t* __restrict__ total,
                        const __grid_constant__ b2_joingather_arg g) {
   // tile_off != NULL: offsets were counted by b2_join_count8_kernel + scan (three launches, still no
-  // host round trip); tile_off == NULL: decoupled look-back over `status` (one launch)
+  // host round trip); tile_off == NULL && status != NULL: decoupled look-back over `status` (one launch);
+  // both NULL: every warp reserves its output range with one atomicAdd on *total (one launch, every
+  // input byte read once, output order = order in which the warps got there)
   constexpr int R = B2_JOP_R;
   __shared__ int64_t sh[B2_WARPS];
   __shared__ int64_t sh_excl;
@@ -547,6 +549,10 @@ b2_join_onepass_kernel(const __grid_constant__ b2_scan_t s, int key_col, const _
       // counted mode: warp-granular offsets, no barrier -- warps of a block drift freely
       off = __ldg(tile_off + tile * B2_WARPS + warp);
       if (tile == ntiles - 1 && threadIdx.x == 0) *total = tile_off[ntiles * B2_WARPS];
+    } else if (!status) {
+      unsigned long long r = 0;
+      if (lane == 0 && wtotal) r = atomicAdd(reinterpret_cast<unsigned long long*>(total), (unsigned long long)wtotal);
+      off = (int64_t)__shfl_sync(FULL_MASK, r, 0);
     } else {
       if (lane == 0) sh[warp] = wtotal;
       __syncthreads();
@@ -647,6 +653,72 @@ b2_join_onepass_kernel(const __grid_constant__ b2_scan_t s, int key_col, const _
   }
 }
 
+
+// ---- streaming probe, specialised --------------------------------------------------------------------
+// The shape of C3 (and of most star-schema joins): INNER / SEMI probe of a key-ordered table, output =
+// [probe key] [one more 8-byte probe column] [one build column], nothing nullable.  One launch, every
+// input byte read once, no match mask, no count pass, no block barrier:
+//   trip 1  key + predicate columns + the probe column      (streaming, coalesced)
+//   trip 2  presence word + payload at the key offset        (L2-resident table, evict_last)
+//   ranks   ballots inside the warp; ONE atomicAdd per warp batch reserves the output range
+//   stores  streaming (evict_first), consecutive lanes -> consecutive rows of the reserved range
+// Output rows of one warp batch stay in probe order; batches land in the order the warps reserve.
+// SQL leaves the row order of a join unspecified (the reference's tests sort before comparing,
+// tests/integration/test_compatibility.py:7-9); callers that want probe order use the counted mode.
+template <bool HAS_P, bool HAS_B, bool B32, bool OUT_KEY>
+__global__ void __launch_bounds__(B2_BLOCK, 3)
+b2_join_stream_kernel(const __grid_constant__ b2_scan_t s, int key_col, int p_col, const __grid_constant__ b2_jointable_t jt,
+                      const void* __restrict__ payload, int64_t pay_base, int64_t ntiles, int64_t* __restrict__ out_key,
+                      int64_t* __restrict__ out_p, int64_t* __restrict__ out_b, unsigned long long* __restrict__ total) {
+  constexpr int R = B2_JOP_R;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t lt_mask = (1u << lane) - 1;
+  const uint64_t range = (uint64_t)jt.range;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t row0 = tile * B2_JOP_TILE + (int64_t)warp * (32 * R) + lane;
+    bool full0;
+    const uint32_t inb = b2_bounds_bits<R>(row0, s.n, full0);
+    int64_t key[R], pv[R];
+    b2_load_batch64<R>(s.cols[key_col].data, row0, inb, full0, key);
+    if (HAS_P) b2_load_batch64<R>(s.cols[p_col].data, row0, inb, full0, pv);
+    bool full;
+    const uint32_t bits = s.nterms ? b2_eval_terms<R>(s, row0, full) : inb;
+    uint32_t word[R];
+    int64_t pay[R];
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      const uint64_t d = (uint64_t)key[j] - (uint64_t)jt.kmin;
+      const bool ok = ((bits >> j) & 1) && d < range;
+      word[j] = ok ? (uint32_t)b2_ld_keep_i32(jt.lookup + (d >> 5)) : 0u;
+      if (HAS_B) {
+        pay[j] = 0;
+        if (ok) pay[j] = B32 ? (int64_t)(uint32_t)b2_ld_keep_i32(reinterpret_cast<const int32_t*>(payload) + d)
+                             : b2_ld_keep_i64(reinterpret_cast<const int64_t*>(payload) + d);
+      }
+    }
+    uint32_t emit = 0;
+#pragma unroll
+    for (int j = 0; j < R; ++j) emit |= ((word[j] >> (((uint64_t)key[j] - (uint64_t)jt.kmin) & 31)) & 1u) << j;
+    int rel[R];
+    int wtotal = 0;
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      const uint32_t b = __ballot_sync(FULL_MASK, (emit >> j) & 1);
+      rel[j] = ((emit >> j) & 1) ? wtotal + __popc(b & lt_mask) : -1;
+      wtotal += __popc(b);
+    }
+    unsigned long long r = 0;
+    if (lane == 0 && wtotal) r = atomicAdd(total, (unsigned long long)wtotal);
+    const int64_t off = (int64_t)__shfl_sync(FULL_MASK, r, 0);
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      if (rel[j] < 0) continue;
+      if (OUT_KEY) b2_st_stream(out_key + off + rel[j], key[j]);
+      if (HAS_P) b2_st_stream(out_p + off + rel[j], pv[j]);
+      if (HAS_B) b2_st_stream(out_b + off + rel[j], B32 ? pay_base + pay[j] : pay[j]);
+    }
+  }
+}
 
 // per-WARP emit counts for b2_join_onepass_kernel's geometry (a warp owns 256 consecutive probe rows of
 // its 2048-row tile) plus the match mask; reads key + presence only.  With warp-granular offsets the
@@ -853,7 +925,57 @@ int32_t b2_join_onepass(const b2_scan_t* scan, const int32_t* probe_keys, const 
   int64_t* total = reinterpret_cast<int64_t*>(d_ws);      // ws[0]; ws[1 .. ntiles+1] = status words / tile offsets
   int64_t* tiles = total + 1;
   int grid = b2_wave_grid(b2_join_onepass_kernel, B2_BLOCK, ntiles);
-  if (lookback) {
+  if (lookback == 2) {
+    // unordered single pass.  Specialised kernel when the shape is [key] [<=1 more probe column] [<=1 build
+    // column] on a key-ordered table with nothing nullable; the generic kernel otherwise.
+    const b2_col_t& kc = scan->cols[pk.cols[0]];
+    bool fits = jt->dense == 2 && (mode == B2_JOIN_INNER || mode == B2_JOIN_SEMI) && kc.dtype == B2_I64 && !kc.valid &&
+                nbuild <= 1 && nprobe <= 2;
+    int p_col = -1, key_out = -1, p_out = -1;
+    for (int k = 0; fits && k < nprobe; ++k) {
+      const b2_col_t& c = scan->cols[g.probe_cols[k]];
+      if (g.probe_valid[k] || c.valid || c.dtype == B2_U8) fits = false;
+      else if (g.probe_cols[k] == pk.cols[0] && key_out < 0) key_out = k;
+      else if (p_col < 0) { p_col = g.probe_cols[k]; p_out = k; }
+      else fits = false;
+    }
+    if (fits && nbuild == 1)
+      fits = !g.build_valid[0] && !g.build_cols[0].valid && g.build_cols[0].dtype != B2_U8 && mode == B2_JOIN_INNER;
+    if (fits) {
+      const bool hp = p_col >= 0, hb = nbuild == 1, b32 = hb && g.build_cols[0].dtype == B2_U32, ok = key_out >= 0;
+      const void* payload = hb ? g.build_cols[0].data : nullptr;
+      const int64_t base = hb ? g.build_base[0] : 0;
+      int64_t* o_key = ok ? reinterpret_cast<int64_t*>(g.probe_out[key_out]) : nullptr;
+      int64_t* o_p = hp ? reinterpret_cast<int64_t*>(g.probe_out[p_out]) : nullptr;
+      int64_t* o_b = hb ? reinterpret_cast<int64_t*>(g.build_out[0]) : nullptr;
+      unsigned long long* tot = reinterpret_cast<unsigned long long*>(total);
+#define B2_JS_LAUNCH(HP, HB, B32, OK)                                                                            \
+      do {                                                                                                        \
+        int sg = b2_wave_grid(b2_join_stream_kernel<HP, HB, B32, OK>, B2_BLOCK, ntiles);                          \
+        b2_join_stream_kernel<HP, HB, B32, OK><<<sg, B2_BLOCK, 0, st>>>(*scan, pk.cols[0], hp ? p_col : 0, *jt,   \
+                                                                        payload, base, ntiles, o_key, o_p, o_b, tot); \
+      } while (0)
+      if (hp && hb && b32 && ok) B2_JS_LAUNCH(true, true, true, true);
+      else if (hp && hb && !b32 && ok) B2_JS_LAUNCH(true, true, false, true);
+      else if (hp && hb && b32) B2_JS_LAUNCH(true, true, true, false);
+      else if (hp && hb) B2_JS_LAUNCH(true, true, false, false);
+      else if (hp && ok) B2_JS_LAUNCH(true, false, false, true);
+      else if (hp) B2_JS_LAUNCH(true, false, false, false);
+      else if (hb && b32 && ok) B2_JS_LAUNCH(false, true, true, true);
+      else if (hb && ok) B2_JS_LAUNCH(false, true, false, true);
+      else if (hb && b32) B2_JS_LAUNCH(false, true, true, false);
+      else if (hb) B2_JS_LAUNCH(false, true, false, false);
+      else if (ok) B2_JS_LAUNCH(false, false, false, true);
+      else fits = false;
+#undef B2_JS_LAUNCH
+      if (fits) {
+        B2_CHECK_LAUNCH("b2_join_stream_kernel");
+        return B2_OK;
+      }
+    }
+    b2_join_onepass_kernel<<<grid, B2_BLOCK, 0, st>>>(*scan, pk.cols[0], *jt, mode, ntiles, nullptr, nullptr, nullptr,
+                                                      total, g);
+  } else if (lookback) {
     b2_join_onepass_kernel<<<grid, B2_BLOCK, 0, st>>>(*scan, pk.cols[0], *jt, mode, ntiles,
                                                       reinterpret_cast<uint64_t*>(tiles), nullptr, nullptr, total, g);
   } else {

@@ -570,7 +570,13 @@ def join_probe_onepass(scan, probe_keys, jt: JoinTable, mode, device, scan_cols,
     else:
         bc = (L.Col * max(1, nb))(*[c.as_struct() for c in build_cols])
         bb = None
-    lookback = 1 if os.environ.get("B200SQL_JOIN_LOOKBACK") == "1" else 0
+    # offsets of the output rows: "stream" (default) = one launch, every warp batch reserves its range with an
+    # atomic, row order across batches unspecified (as SQL leaves it); "counted" = count + scan + write, output
+    # in probe order; "lookback" = one launch, probe order, offsets by decoupled look-back (measured slower)
+    order = os.environ.get("B200SQL_JOIN_ORDER", "stream")
+    if os.environ.get("B200SQL_JOIN_LOOKBACK") == "1":
+        order = "lookback"
+    lookback = {"stream": 2, "lookback": 1}.get(order, 0)
     L.join_onepass(C.byref(scan), pk, C.byref(jt.struct), mode, lookback, ptr(ws), np_, pc, po, pv, nb, bc, bb,
                    bo, bv, stream_ptr())
 

@@ -334,12 +334,38 @@ def select_part(part: Part, pred: Sequence[Expr], names: Sequence[str]) -> Part:
 # ---------------------------------------------------------------------------------------------
 # sources
 # ---------------------------------------------------------------------------------------------
+def _split_out(src: Source) -> int:
+    return max(1, int((getattr(src, "options", None) or {}).get("split_out") or 1))
+
+
 def source_npartitions(src: Source) -> int:
     if isinstance(src, TableSource):
         return len(src.table.partitions)
     if isinstance(src, JoinSource):
         return max(source_npartitions(src.left.source), source_npartitions(src.right.source))
+    if isinstance(src, AggSource):
+        return _split_out(src)           # sql.aggregate.split_out (aggregate.py:321,581): output partitions
     return 1
+
+
+def split_part(part: Part, k: int) -> List[Part]:
+    """The rows of `part` as k contiguous partitions (boundaries on multiples of 32 rows, so validity
+    bitmaps split on word boundaries; column slices are views).  A compacted dense group table is in
+    key order, so these are key ranges: every group lives in exactly one output partition, which is
+    what dask's split_out guarantees (there by hashing the keys)."""
+    part = part.resolve()
+    n = part.n
+    step = max(32, (-(-n // k) + 31) // 32 * 32)
+    out = []
+    for i in range(k):
+        lo, hi = min(n, i * step), min(n, (i + 1) * step)
+        if hi > lo:
+            piece = Part({name: c.slice(lo, hi) for name, c in part.items()}, hi - lo)
+        else:
+            piece = Part({name: DeviceColumn(c.data[:0], None, c.dtype, c.logical) for name, c in part.items()}, 0)
+        piece.dist = part.dist
+        out.append(piece)
+    return out
 
 
 def frame_distribution(frame: LazyFrame) -> str:
@@ -436,7 +462,9 @@ def materialize(src: Source, needed: Set[str], top: bool = False) -> List[Part]:
         return run_join(src, needed)
     if isinstance(src, AggSource):
         part = run_aggregate(src)
-        return [part if top else gather_keyrange(part)]
+        part = part if top else gather_keyrange(part)
+        k = _split_out(src)
+        return split_part(part, k) if k > 1 else [part]
     if isinstance(src, SortSource):
         return [run_sort(src, needed)]
     if isinstance(src, LimitSource):

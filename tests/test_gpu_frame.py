@@ -347,10 +347,13 @@ def test_dense_result_is_pending_until_used():
 
 
 @pytest.mark.parametrize("how", ["inner", "left", "leftsemi", "leftanti"])
-def test_join_key_ordered_payload_layout(how, monkeypatch):
+@pytest.mark.parametrize("order", ["counted", "stream"])
+def test_join_key_ordered_payload_layout(how, order, monkeypatch):
     """Unique dense build keys: build columns are re-laid in key order (narrow uint32 offsets for
-    small-range ints, 8 bytes otherwise, bool, nullable) and probed by key offset."""
+    small-range ints, 8 bytes otherwise, bool, nullable) and probed by key offset.  order=stream runs
+    the generic single-pass kernel with atomically reserved output ranges (nullable key, many columns)."""
     from dask_sql_b200 import executor
+    monkeypatch.setenv("B200SQL_JOIN_ORDER", order)
     rng = np.random.default_rng(31)
     nd, nf = 20_000, 150_003
     pk = rng.permutation(nd * 2)[:nd].astype(np.int64) - 777           # unique, with holes, negative kmin
@@ -372,7 +375,11 @@ def test_join_key_ordered_payload_layout(how, monkeypatch):
     monkeypatch.setenv("B200SQL_NO_KEY_LAYOUT", "1")
     plain = f.merge(d, left_on=["fk"], right_on=["pk"], how=how).compute()
     assert executor.stats["keyed_join"] == before + 1
-    pd.testing.assert_frame_equal(got, plain)                            # same rows, same order, same dtypes
+    if order == "counted":
+        pd.testing.assert_frame_equal(got, plain)                        # same rows, same order, same dtypes
+    else:
+        assert list(got.dtypes) == list(plain.dtypes)
+        assert_frames(got, plain, sort_by=["fk", "v"])
     from oracle import pandas_oracle as O
     exp = O.join_on_columns(fact, dim, ["fk"], ["pk"], how)
     assert_frames(got[list(exp.columns)], exp, sort_by=["fk", "v"])
@@ -399,14 +406,24 @@ def test_join_single_pass_lookback_equals_two_pass(how, match, monkeypatch):
         parts = executor.execute(j)
         return parts, j.compute()
 
+    from oracle import pandas_oracle as O
+    exp = O.join_on_columns(fact[fact["x"] > -3], dim, ["fk"], ["pk"], how)
+    # default: streaming single pass (row order across warp batches unspecified) -> compare as multisets
+    parts, streamed = run()
+    assert all(isinstance(p, executor.PendingPart) for p in parts)
+    assert len(streamed) == len(exp)
+    assert_frames(streamed[list(exp.columns)], exp, sort_by=["fk", "v"])
+    # the two probe-order protocols must agree row for row
+    monkeypatch.setenv("B200SQL_JOIN_ORDER", "counted")
     parts, got = run()
     assert all(isinstance(p, executor.PendingPart) for p in parts)
+    monkeypatch.setenv("B200SQL_JOIN_ORDER", "lookback")
+    _, got_lb = run()
+    pd.testing.assert_frame_equal(got, got_lb)
     monkeypatch.setenv("B200SQL_NO_ONEPASS", "1")
     parts2, two_pass = run()
     assert not any(isinstance(p, executor.PendingPart) for p in parts2)
     pd.testing.assert_frame_equal(got, two_pass)
-    from oracle import pandas_oracle as O
-    exp = O.join_on_columns(fact[fact["x"] > -3], dim, ["fk"], ["pk"], how)
     assert len(got) == len(exp)
     assert_frames(got[list(exp.columns)], exp, sort_by=["fk", "v"])
 

@@ -207,6 +207,32 @@ def test_distinct_and_plain_aggregates_together(c):
     assert_same(got, exp, ["s"])
 
 
+@pytest.mark.parametrize("split_out", [1, 2, 4])
+def test_groupby_split_out(c, split_out):
+    """sql.aggregate.split_out (tests/integration/test_groupby.py:491-523): the result has that many
+    partitions, every group in exactly one of them; also for DISTINCT and with a NULL-able key."""
+    from dask_sql_b200 import executor
+    rng = np.random.default_rng(split_out)
+    n = 3_000
+    df = pd.DataFrame({"user_id": pd.array(np.where(rng.random(n) < 0.05, None, rng.integers(0, 300, n)), dtype="Int64"),
+                       "b": rng.integers(0, 50, n)})
+    c.create_table("user_table_1", df, npartitions=3)
+    lazy = c.sql('SELECT user_id, SUM(b) AS "S" FROM user_table_1 GROUP BY user_id',
+                 config_options={"sql.aggregate.split_out": split_out})
+    assert lazy.npartitions == split_out
+    parts = executor.execute(lazy)
+    assert len(parts) == split_out
+    seen = [set(executor.D.column_to_host(p["user_id"]).tolist() if p.n else []) for p in parts]
+    for i in range(len(seen)):
+        for j in range(i + 1, len(seen)):
+            assert not ({x for x in seen[i] if x is not pd.NA} & {x for x in seen[j] if x is not pd.NA})
+    exp = df.groupby("user_id", dropna=False).agg(S=("b", "sum")).reset_index()
+    assert_same(lazy.compute(), exp)
+    lazy = c.sql("SELECT DISTINCT(user_id) FROM user_table_1", config_options={"sql.aggregate.split_out": split_out})
+    assert lazy.npartitions == split_out
+    assert_same(lazy.compute(), df[["user_id"]].drop_duplicates())
+
+
 def test_order_by_limit(c):
     # ORDER BY / LIMIT (tests/integration/test_sort.py: results compared in order)
     rng = np.random.default_rng(5)
