@@ -127,14 +127,31 @@ b2_expr_kernel(const __grid_constant__ b2_prog_t prog, const __grid_constant__ b
 }
 
 // ---- column statistics ------------------------------------------------------------------
-// out: {min(ordered image), max(ordered image), nulls, nans}
+// out: {min(ordered image), max(ordered image), nulls, nans, repeating rows of the sample, rows sampled}
 __global__ void b2_stats_init_kernel(int64_t* out) {
-  out[0] = LLONG_MAX; out[1] = LLONG_MIN; out[2] = 0; out[3] = 0;
+  out[0] = LLONG_MAX; out[1] = LLONG_MIN; out[2] = 0; out[3] = 0; out[4] = 0; out[5] = 0;
 }
 __global__ void __launch_bounds__(B2_BLOCK)
 b2_stats_kernel(const __grid_constant__ b2_col_t col, int64_t n, int64_t* __restrict__ out) {
   long long mn = LLONG_MAX, mx = LLONG_MIN;
   unsigned long long nulls = 0, nans = 0;
+  {
+    // repeat sample: of the 32 consecutive rows each warp meets first (spread over the whole column by
+    // the grid stride), how many share their value with another one?  Decides whether a GROUP BY on
+    // this column pre-aggregates per warp (out[4] = such rows, out[5] = rows sampled).
+    const int64_t row = (int64_t)blockIdx.x * B2_BLOCK + threadIdx.x;
+    bool ok = row < n && !(col.valid && !b2_bit(col.valid, row));
+    int64_t raw = ok ? b2_load_raw(col, row) : 0;
+    if (ok && col.dtype == B2_F64) { const double d = __longlong_as_double(raw); ok = d == d; }
+    const uint32_t act = __ballot_sync(FULL_MASK, ok);
+    uint32_t m = 0;
+    if (ok) m = __match_any_sync(act, raw);
+    const uint32_t rep = __ballot_sync(FULL_MASK, ok && __popc(m) > 1);
+    if ((threadIdx.x & 31) == 0 && act) {
+      atomicAdd(reinterpret_cast<unsigned long long*>(out + 4), (unsigned long long)__popc(rep));
+      atomicAdd(reinterpret_cast<unsigned long long*>(out + 5), (unsigned long long)__popc(act));
+    }
+  }
   for (int64_t row = (int64_t)blockIdx.x * B2_BLOCK + threadIdx.x; row < n;
        row += (int64_t)gridDim.x * B2_BLOCK) {
     if (col.valid && !b2_bit(col.valid, row)) { ++nulls; continue; }

@@ -6,25 +6,25 @@
 #pragma once
 #include "common.cuh"
 #include "pipeline.cuh"
+#include "warpagg.cuh"
 
 #define B2_GB_R 8
 #define B2_GB_ROWS_PER_BLOCK (B2_BLOCK * B2_GB_R)
 #define B2_MAX_PROBE 1024
 
 // ---- dense ------------------------------------------------------------------------------
-template <class LD>
-__device__ __forceinline__ void b2_dense_body(const b2_scan_t& s, const LD& ld, int key_col, int64_t kmin,
-                                              int64_t nslots, const b2_aggs_arg& aggs, const b2_aggstate_t& st) {
+template <int R, class LD>
+__device__ __forceinline__ void b2_dense_slots_of(const b2_scan_t& s, const LD& ld, int key_col, int64_t kmin,
+                                                  int64_t nslots, int64_t (&slot)[R]) {
   const b2_col_t& kc = s.cols[key_col];
   bool full;
-  const uint32_t bits = b2_eval_terms<B2_GB_R>(s, ld, full);
-  int64_t key[B2_GB_R];
-  ld.template load<B2_GB_R>(key_col, bits, full, key);
+  const uint32_t bits = b2_eval_terms<R>(s, ld, full);
+  int64_t key[R];
+  ld.template load<R>(key_col, bits, full, key);
   uint32_t kvalid = bits;
-  if (kc.valid) kvalid = b2_valid_bits<B2_GB_R>(kc.valid, ld.row0, bits);
-  int64_t slot[B2_GB_R];
+  if (kc.valid) kvalid = b2_valid_bits<R>(kc.valid, ld.row0, bits);
 #pragma unroll
-  for (int j = 0; j < B2_GB_R; ++j) {
+  for (int j = 0; j < R; ++j) {
     slot[j] = -1;
     if ((bits >> j) & 1) {
       if (!((kvalid >> j) & 1)) slot[j] = nslots - 1;
@@ -34,6 +34,13 @@ __device__ __forceinline__ void b2_dense_body(const b2_scan_t& s, const LD& ld, 
       }
     }
   }
+}
+
+template <class LD>
+__device__ __forceinline__ void b2_dense_body(const b2_scan_t& s, const LD& ld, int key_col, int64_t kmin,
+                                              int64_t nslots, const b2_aggs_arg& aggs, const b2_aggstate_t& st) {
+  int64_t slot[B2_GB_R];
+  b2_dense_slots_of<B2_GB_R>(s, ld, key_col, kmin, nslots, slot);
   b2_apply_aggs<B2_GB_R>(s, ld, aggs.a, aggs.n, st, slot);
 }
 
@@ -46,6 +53,27 @@ b2_groupby_dense_kernel(const __grid_constant__ b2_scan_t s, const __grid_consta
   if (PIPE) b2_tile_pipeline(s, pp, body);
   else if (ticket) b2_tile_ticket<B2_GB_R>(s, ticket, body);
   else b2_tile_direct<B2_GB_R>(s, body);
+}
+
+// Keys that repeat inside a warp (skewed distributions; chosen by the host from the column's repeat
+// statistic): batches whose first step shows duplicate slots pre-aggregate per warp and per CTA
+// (warpagg.cuh) instead of issuing one atomic per row.  A separate kernel so that the per-row-atomic
+// kernel above keeps its 48 registers / 5 CTAs per SM.
+__global__ void __launch_bounds__(B2_BLOCK)
+b2_groupby_dense_grouped_kernel(const __grid_constant__ b2_scan_t s, int key_col, int64_t kmin, int64_t nslots,
+                                const __grid_constant__ b2_aggs_arg aggs, const __grid_constant__ b2_aggstate_t st,
+                                const __grid_constant__ b2_hot_t hot) {
+  extern __shared__ __align__(128) uint8_t b2_smem[];
+  const b2_hot_smem hs = b2_hot_init(hot, b2_smem);
+  b2_tile_direct<B2_GB_R>(s, [&](const b2_gld& ld) {
+    int64_t slot[B2_GB_R];
+    b2_dense_slots_of<B2_GB_R>(s, ld, key_col, kmin, nslots, slot);
+    if (b2_batch_repeats<B2_GB_R>(slot, threadIdx.x & 31))
+      b2_apply_aggs_grouped<B2_GB_R>(s, ld, aggs.a, aggs.n, st, slot, hot, hs);
+    else
+      b2_apply_aggs<B2_GB_R>(s, ld, aggs.a, aggs.n, st, slot);
+  });
+  b2_hot_flush(hot, hs, aggs, st);
 }
 
 // ---- hash, single 64-bit key ----------------------------------------------------------------
@@ -390,6 +418,33 @@ static int32_t b2_groupby_dense_impl(const b2_scan_t* scan, int32_t key_col, int
 int32_t b2_groupby_dense(const b2_scan_t* scan, int32_t key_col, int64_t kmin, int64_t nslots,
                          const b2_agg_t* aggs, int32_t naggs, const b2_aggstate_t* st, void* stream) {
   return b2_groupby_dense_impl(scan, key_col, kmin, nslots, aggs, naggs, st, nullptr, stream);
+}
+
+int32_t b2_groupby_dense_grouped(const b2_scan_t* scan, int32_t key_col, int64_t kmin, int64_t nslots,
+                                 const b2_agg_t* aggs, int32_t naggs, const b2_aggstate_t* st, void* stream) {
+  int32_t rc = b2_check_scan(scan);
+  if (rc) return rc;
+  b2_aggs_arg aa;
+  if ((rc = b2_check_aggs(scan, aggs, naggs, &aa))) return rc;
+  if ((rc = b2_check_state(aa, st))) return rc;
+  B2_REQUIRE(key_col >= 0 && key_col < scan->ncols, "key column out of range");
+  B2_REQUIRE(scan->cols[key_col].dtype == B2_I64 || scan->cols[key_col].dtype == B2_U8, "dense keys must be integers");
+  B2_REQUIRE(nslots >= 2 && nslots < ((int64_t)1 << 31), "nslots must cover the key range plus the NULL slot, below 2^31");
+  if (scan->n == 0) return B2_OK;
+  b2_hot_t hot;
+  b2_make_hot(*scan, aa, *st, &hot);
+  const size_t smem = b2_hot_smem_bytes(hot);
+  if (smem > 48 * 1024)
+    B2_CUDA_TRY(cudaFuncSetAttribute(b2_groupby_dense_grouped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int64_t nblk = (scan->n + B2_GB_ROWS_PER_BLOCK - 1) / B2_GB_ROWS_PER_BLOCK;
+  int occ = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, b2_groupby_dense_grouped_kernel, B2_BLOCK, smem);
+  int64_t grid = (int64_t)b2_sm_count() * (occ < 1 ? 1 : occ);
+  if (grid > nblk) grid = nblk;
+  if (grid < 1) grid = 1;
+  b2_groupby_dense_grouped_kernel<<<(int)grid, B2_BLOCK, smem, (cudaStream_t)stream>>>(*scan, key_col, kmin, nslots, aa, *st, hot);
+  B2_CHECK_LAUNCH("b2_groupby_dense_grouped_kernel");
+  return B2_OK;
 }
 
 int32_t b2_groupby_dense_ordered(const b2_scan_t* scan, int32_t key_col, int64_t kmin, int64_t nslots,

@@ -887,15 +887,17 @@ def _key_stats(parts: List[Part], e: Expr, child: LazyFrame):
         return child.source.table.column_stats(e.name)
     mn = mx = None
     nulls = 0
+    repeat = 0.0
     for p in parts:
         if p.n == 0:
             continue
         st = eval_expr(p, e).ensure_stats()
         nulls += st.nulls
+        repeat = max(repeat, st.repeat)
         if st.vmin is not None:
             mn = st.vmin if mn is None else min(mn, st.vmin)
             mx = st.vmax if mx is None else max(mx, st.vmax)
-    return D.Stats(mn, mx, nulls)
+    return D.Stats(mn, mx, nulls, repeat)
 
 
 def grouped_aggregate(parts, pred, gexprs, gnames, plan: AggPlan, child, sharded, options) -> Part:
@@ -934,6 +936,9 @@ def grouped_aggregate(parts, pred, gexprs, gnames, plan: AggPlan, child, sharded
             lo = hi = 0
         if hi - lo + 2 <= DENSE_MAX_SLOTS and (hi - lo) <= 8 * max(total_rows_all, 1) + 1024:
             mode, kmin, rng = "dense", lo, hi - lo + 1
+            # keys that repeat inside a warp: pre-aggregate per warp / CTA (b2_groupby_dense_grouped).
+            # A rank-local choice: both kernels fill the same table.
+            repeats = st.repeat >= REPEAT_MIN and os.environ.get("B200SQL_NO_WARPAGG") != "1"
         elif gexprs[0].dtype == I64:
             mode = "hash1"
     elif len(gexprs) == 1 and gexprs[0].dtype == F64:
@@ -999,8 +1004,9 @@ def grouped_aggregate(parts, pred, gexprs, gnames, plan: AggPlan, child, sharded
                 gs.bind(ctx)
                 stats["launches"] += 1
                 ev = _kernel_event_begin("b2_groupby_dense_kernel", part.n)
-                D.groupby_dense(ctx.scan(), kslot, kmin, gs.table)
+                D.groupby_dense(ctx.scan(), kslot, kmin, gs.table, grouped=repeats)
                 _kernel_event_end(ev)
+            stats["grouped_groupby"] = stats.get("grouped_groupby", 0) + (1 if repeats else 0)
         key_nullable = E.may_be_null(gexprs[0], lambda n: any(n in p and p[n].valid is not None for p in parts))
         if sharded:
             # a rank whose shard has no NULL key must still agree that the NULL slot may be occupied
@@ -1049,6 +1055,7 @@ def grouped_aggregate(parts, pred, gexprs, gnames, plan: AggPlan, child, sharded
     return finish(raw, plan)
 
 
+REPEAT_MIN = 0.05      # Stats.repeat above which a dense GROUP BY pre-aggregates (uniform 1M keys: 0.0005; Zipf 1.1: > 0.3)
 PARTITION_MIN_TABLE_BYTES = 256 << 20     # below this the table (mostly) lives in the 126 MB L2 anyway
 PARTITION_BUCKET_BYTES = 24 << 20         # slice of the group table touched by one bucket
 

@@ -238,6 +238,7 @@ class DeviceTable:
         Computed on the GPU the first time a plan needs them, then cached."""
         mn = mx = None
         nulls = 0
+        repeat = 0.0
         for p in self.partitions:
             c = p[name]
             if c.stats is None:
@@ -248,10 +249,11 @@ class DeviceTable:
                     c.ensure_stats()
             st = c.stats
             nulls += st.nulls
+            repeat = max(repeat, st.repeat)
             if st.vmin is not None:
                 mn = st.vmin if mn is None else min(mn, st.vmin)
                 mx = st.vmax if mx is None else max(mx, st.vmax)
-        return Stats(mn, mx, nulls)
+        return Stats(mn, mx, nulls, repeat)
 
     # -- construction -------------------------------------------------------------------------
     @classmethod

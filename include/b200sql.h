@@ -182,9 +182,11 @@ int64_t b2_num_tiles(int64_t n);
 
 /* ---- ingest ---------------------------------------------------------------------- */
 /* Column statistics computed once at Context.create_table (context.py:168-293 keeps only
- * Statistics(row_count)); d_out = int64[4]: {min, max, null_count, n_nan}; min/max are the
- * raw 64-bit pattern of the column type and cover non-null (non-NaN) values only.
- * ws: device scratch of >= b2_stats_ws_bytes() bytes. */
+ * Statistics(row_count)); d_out = int64[6]: {min, max, null_count, n_nan, repeats, sampled};
+ * min/max are the raw 64-bit pattern of the column type and cover non-null (non-NaN) values only.
+ * repeats / sampled: of `sampled` rows taken as groups of 32 consecutive rows spread over the
+ * column, `repeats` share their value with another row of their group -- the skew estimate that
+ * selects b2_groupby_dense_grouped.  ws: device scratch of >= b2_stats_ws_bytes() bytes. */
 int64_t b2_stats_ws_bytes(void);
 int32_t b2_col_stats(const b2_col_t* col, int64_t n, int64_t* d_out, void* ws, void* stream);
 
@@ -231,6 +233,16 @@ int32_t b2_gather(const b2_col_t* col, const int32_t* idx, int64_t n_idx,
 int32_t b2_groupby_dense(const b2_scan_t* scan, int32_t key_col, int64_t kmin, int64_t nslots,
                          const b2_agg_t* aggs, int32_t naggs, const b2_aggstate_t* st,
                          void* stream);
+
+/* b2_groupby_dense for keys that REPEAT within a warp (skewed distributions, e.g. Zipf): same
+ * arguments and results (float sums up to summation order), but a batch whose rows share slots
+ * combines them per warp (match + shuffles, one atomic per distinct slot and 32-row step) and
+ * collects slots seen twice in a step in a per-CTA shared-memory table that is flushed with one atomic
+ * per accumulator at the end.  The L2 serialises atomics per ADDRESS: without this a key that takes
+ * 12 % of the rows costs several times the whole uniform-key query.  nslots < 2^31. */
+int32_t b2_groupby_dense_grouped(const b2_scan_t* scan, int32_t key_col, int64_t kmin, int64_t nslots,
+                                 const b2_agg_t* aggs, int32_t naggs, const b2_aggstate_t* st,
+                                 void* stream);
 
 /* Hash group table on ONE 64-bit key (int64, or float64 bits normalised -0.0 -> 0.0).
  * table_keys = int64[cap+2] pre-filled with B2_EMPTY_KEY, cap a power of two; slot cap holds

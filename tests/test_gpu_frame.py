@@ -548,3 +548,47 @@ def test_join_agg_falls_back_on_duplicate_build_keys():
     j = fact.merge(dim, left_on="fk", right_on="pk")
     assert int(got.n[0]) == len(j)
     np.testing.assert_allclose(float(got.s[0]), (j.v * j.w).sum(), rtol=RTOL)
+
+
+@pytest.mark.parametrize("hot_table", [True, False])
+@pytest.mark.parametrize("nullable_key", [False, True])
+def test_groupby_skewed_keys_preaggregate(hot_table, nullable_key, monkeypatch):
+    """Keys that repeat inside a warp (Zipf-like) take b2_groupby_dense_grouped: per-warp match/shuffle
+    pre-aggregation + the per-CTA shared-memory table of hot slots (or the warp level alone).  Every
+    accumulator kind, NULL inputs, a predicate, NULL keys, a ragged tail; against pandas."""
+    from dask_sql_b200 import executor
+    if not hot_table:
+        monkeypatch.setenv("B200SQL_NO_HOT_TABLE", "1")
+    rng = np.random.default_rng(91)
+    n, nkeys = 400_037, 3_000
+    w = 1.0 / np.arange(1, nkeys + 1) ** 1.1
+    key = rng.permutation(nkeys)[rng.choice(nkeys, size=n, p=w / w.sum())] + 50
+    df = pd.DataFrame({
+        "key": pd.array(np.where(rng.random(n) < 0.03, None, key), dtype="Int64") if nullable_key else key,
+        "v": rng.random(n), "w": rng.integers(-100, 100, n),
+        "g": np.where(rng.random(n) < 0.2, np.nan, rng.random(n)), "x": rng.integers(0, 10, n)})
+    spec = [("v", "sv", "sum"), ("w", "sw", "sum"), ("w", "aw", "mean"), ("g", "cg", "count"), ("g", "sg", "sum"),
+            ("w", "mn", "min"), ("g", "mx", "max"), (None, "n", "size")]
+    before = executor.stats.get("grouped_groupby", 0)
+    f = _table(df, 3)
+    got = agg(f[f["x"] > 1], ["key"], spec)
+    assert executor.stats.get("grouped_groupby", 0) == before + 1
+    d = df[df["x"] > 1]
+    exp = d.groupby("key", dropna=False).agg(sv=("v", "sum"), sw=("w", "sum"), aw=("w", "mean"), cg=("g", "count"),
+                                             sg=("g", lambda s: s.sum(min_count=1)), mn=("w", "min"),
+                                             mx=("g", "max"), n=("v", "size")).reset_index()
+    assert_frames(got, exp, float_cols=("sv", "aw", "sg"), sort_by=["key"])
+    # a single float SUM over a never-NULL column: the accumulator doubles as the existence flag
+    got = agg(f, ["key"], [("v", "sv", "sum")])
+    exp = df.groupby("key", dropna=False).agg(sv=("v", "sum")).reset_index()
+    assert_frames(got, exp, float_cols=("sv",), sort_by=["key"])
+
+
+def test_uniform_keys_keep_the_per_row_atomic_kernel():
+    from dask_sql_b200 import executor
+    rng = np.random.default_rng(92)
+    df = pd.DataFrame({"key": rng.integers(0, 1_000_000, 300_000), "v": rng.random(300_000)})
+    before = executor.stats.get("grouped_groupby", 0)
+    got = agg(_table(df, 2), ["key"], [("v", "sv", "sum")])
+    assert executor.stats.get("grouped_groupby", 0) == before
+    assert_frames(got, df.groupby("key").agg(sv=("v", "sum")).reset_index(), float_cols=("sv",), sort_by=["key"])
