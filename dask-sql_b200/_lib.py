@@ -12,6 +12,7 @@ LIB_PATH = os.environ.get("B200SQL_LIB") or os.path.join(HERE, "libb200sql.so") 
 # ---- constants (mirror include/b200sql.h) ----
 I64, F64, U8 = 0, 1, 2
 U32 = 3          # storage-only: narrowed key-ordered join payload
+COL_SENTINEL = 1
 MAX_COLS, MAX_TERMS, MAX_AGGS, MAX_KEYS, MAX_GATHER, MAX_PROG = 16, 8, 8, 4, 8, 64
 TILE = 4096
 EQ, NE, LT, LE, GT, GE, IS_NULL, IS_NOT_NULL, IS_TRUE = range(9)
@@ -27,7 +28,7 @@ OP_AND, OP_OR, OP_NOT, OP_ISNULL_I, OP_ISNULL_F, OP_CASE, OP_FILLNA, OP_ORD2F = 
 
 
 class Col(C.Structure):
-    _fields_ = [("data", C.c_void_p), ("valid", C.c_void_p), ("dtype", C.c_int32), ("pad_", C.c_int32)]
+    _fields_ = [("data", C.c_void_p), ("valid", C.c_void_p), ("dtype", C.c_int32), ("flags", C.c_int32)]
 
 
 class Term(C.Structure):

@@ -665,12 +665,15 @@ b2_join_onepass_kernel(const __grid_constant__ b2_scan_t s, int key_col, const _
 // Output rows of one warp batch stay in probe order; batches land in the order the warps reserve.
 // SQL leaves the row order of a join unspecified (the reference's tests sort before comparing,
 // tests/integration/test_compatibility.py:7-9); callers that want probe order use the counted mode.
-template <bool HAS_P, bool HAS_B, bool B32, bool OUT_KEY>
+// BMODE: how the build column is stored -- 0 none, 1 eight bytes, 2 uint32 offsets (+ presence bitmap),
+// 3 uint32 offsets in which 0xFFFFFFFF marks "no build row" (B2_COL_SENTINEL: no bitmap access at all)
+template <bool HAS_P, int BMODE, bool OUT_KEY>
 __global__ void __launch_bounds__(B2_BLOCK, 3)
 b2_join_stream_kernel(const __grid_constant__ b2_scan_t s, int key_col, int p_col, const __grid_constant__ b2_jointable_t jt,
                       const void* __restrict__ payload, int64_t pay_base, int64_t ntiles, int64_t* __restrict__ out_key,
                       int64_t* __restrict__ out_p, int64_t* __restrict__ out_b, unsigned long long* __restrict__ total) {
   constexpr int R = B2_JOP_R;
+  constexpr bool HAS_B = BMODE != 0;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t lt_mask = (1u << lane) - 1;
   const uint64_t range = (uint64_t)jt.range;
@@ -683,22 +686,33 @@ b2_join_stream_kernel(const __grid_constant__ b2_scan_t s, int key_col, int p_co
     if (HAS_P) b2_load_batch64<R>(s.cols[p_col].data, row0, inb, full0, pv);
     bool full;
     const uint32_t bits = s.nterms ? b2_eval_terms<R>(s, row0, full) : inb;
-    uint32_t word[R];
     int64_t pay[R];
-#pragma unroll
-    for (int j = 0; j < R; ++j) {
-      const uint64_t d = (uint64_t)key[j] - (uint64_t)jt.kmin;
-      const bool ok = ((bits >> j) & 1) && d < range;
-      word[j] = ok ? (uint32_t)b2_ld_keep_i32(jt.lookup + (d >> 5)) : 0u;
-      if (HAS_B) {
-        pay[j] = 0;
-        if (ok) pay[j] = B32 ? (int64_t)(uint32_t)b2_ld_keep_i32(reinterpret_cast<const int32_t*>(payload) + d)
-                             : b2_ld_keep_i64(reinterpret_cast<const int64_t*>(payload) + d);
-      }
-    }
     uint32_t emit = 0;
+    if (BMODE == 3) {
 #pragma unroll
-    for (int j = 0; j < R; ++j) emit |= ((word[j] >> (((uint64_t)key[j] - (uint64_t)jt.kmin) & 31)) & 1u) << j;
+      for (int j = 0; j < R; ++j) {
+        const uint64_t d = (uint64_t)key[j] - (uint64_t)jt.kmin;
+        const bool ok = ((bits >> j) & 1) && d < range;
+        const uint32_t raw = ok ? (uint32_t)b2_ld_keep_i32(reinterpret_cast<const int32_t*>(payload) + d) : 0xffffffffu;
+        pay[j] = (int64_t)raw;
+        emit |= (uint32_t)(raw != 0xffffffffu) << j;
+      }
+    } else {
+      uint32_t word[R];
+#pragma unroll
+      for (int j = 0; j < R; ++j) {
+        const uint64_t d = (uint64_t)key[j] - (uint64_t)jt.kmin;
+        const bool ok = ((bits >> j) & 1) && d < range;
+        word[j] = ok ? (uint32_t)b2_ld_keep_i32(jt.lookup + (d >> 5)) : 0u;
+        if (HAS_B) {
+          pay[j] = 0;
+          if (ok) pay[j] = BMODE == 2 ? (int64_t)(uint32_t)b2_ld_keep_i32(reinterpret_cast<const int32_t*>(payload) + d)
+                                      : b2_ld_keep_i64(reinterpret_cast<const int64_t*>(payload) + d);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < R; ++j) emit |= ((word[j] >> (((uint64_t)key[j] - (uint64_t)jt.kmin) & 31)) & 1u) << j;
+    }
     int rel[R];
     int wtotal = 0;
 #pragma unroll
@@ -715,7 +729,7 @@ b2_join_stream_kernel(const __grid_constant__ b2_scan_t s, int key_col, int p_co
       if (rel[j] < 0) continue;
       if (OUT_KEY) b2_st_stream(out_key + off + rel[j], key[j]);
       if (HAS_P) b2_st_stream(out_p + off + rel[j], pv[j]);
-      if (HAS_B) b2_st_stream(out_b + off + rel[j], B32 ? pay_base + pay[j] : pay[j]);
+      if (HAS_B) b2_st_stream(out_b + off + rel[j], BMODE >= 2 ? pay_base + pay[j] : pay[j]);
     }
   }
 }
@@ -942,31 +956,34 @@ int32_t b2_join_onepass(const b2_scan_t* scan, const int32_t* probe_keys, const 
     if (fits && nbuild == 1)
       fits = !g.build_valid[0] && !g.build_cols[0].valid && g.build_cols[0].dtype != B2_U8 && mode == B2_JOIN_INNER;
     if (fits) {
-      const bool hp = p_col >= 0, hb = nbuild == 1, b32 = hb && g.build_cols[0].dtype == B2_U32, ok = key_out >= 0;
+      const bool hp = p_col >= 0, hb = nbuild == 1, ok = key_out >= 0;
+      int bmode = 0;
+      if (hb) bmode = g.build_cols[0].dtype != B2_U32 ? 1 : ((g.build_cols[0].flags & B2_COL_SENTINEL) ? 3 : 2);
       const void* payload = hb ? g.build_cols[0].data : nullptr;
       const int64_t base = hb ? g.build_base[0] : 0;
       int64_t* o_key = ok ? reinterpret_cast<int64_t*>(g.probe_out[key_out]) : nullptr;
       int64_t* o_p = hp ? reinterpret_cast<int64_t*>(g.probe_out[p_out]) : nullptr;
       int64_t* o_b = hb ? reinterpret_cast<int64_t*>(g.build_out[0]) : nullptr;
       unsigned long long* tot = reinterpret_cast<unsigned long long*>(total);
-#define B2_JS_LAUNCH(HP, HB, B32, OK)                                                                            \
+#define B2_JS_LAUNCH(HP, BM, OK)                                                                                 \
       do {                                                                                                        \
-        int sg = b2_wave_grid(b2_join_stream_kernel<HP, HB, B32, OK>, B2_BLOCK, ntiles);                          \
-        b2_join_stream_kernel<HP, HB, B32, OK><<<sg, B2_BLOCK, 0, st>>>(*scan, pk.cols[0], hp ? p_col : 0, *jt,   \
-                                                                        payload, base, ntiles, o_key, o_p, o_b, tot); \
+        int sg = b2_wave_grid(b2_join_stream_kernel<HP, BM, OK>, B2_BLOCK, ntiles);                               \
+        b2_join_stream_kernel<HP, BM, OK><<<sg, B2_BLOCK, 0, st>>>(*scan, pk.cols[0], hp ? p_col : 0, *jt,        \
+                                                                   payload, base, ntiles, o_key, o_p, o_b, tot);  \
       } while (0)
-      if (hp && hb && b32 && ok) B2_JS_LAUNCH(true, true, true, true);
-      else if (hp && hb && !b32 && ok) B2_JS_LAUNCH(true, true, false, true);
-      else if (hp && hb && b32) B2_JS_LAUNCH(true, true, true, false);
-      else if (hp && hb) B2_JS_LAUNCH(true, true, false, false);
-      else if (hp && ok) B2_JS_LAUNCH(true, false, false, true);
-      else if (hp) B2_JS_LAUNCH(true, false, false, false);
-      else if (hb && b32 && ok) B2_JS_LAUNCH(false, true, true, true);
-      else if (hb && ok) B2_JS_LAUNCH(false, true, false, true);
-      else if (hb && b32) B2_JS_LAUNCH(false, true, true, false);
-      else if (hb) B2_JS_LAUNCH(false, true, false, false);
-      else if (ok) B2_JS_LAUNCH(false, false, false, true);
-      else fits = false;
+#define B2_JS_BM(HP, OK)                                                                                          \
+      do {                                                                                                        \
+        if (bmode == 0) B2_JS_LAUNCH(HP, 0, OK);                                                                  \
+        else if (bmode == 1) B2_JS_LAUNCH(HP, 1, OK);                                                             \
+        else if (bmode == 2) B2_JS_LAUNCH(HP, 2, OK);                                                             \
+        else B2_JS_LAUNCH(HP, 3, OK);                                                                             \
+      } while (0)
+      if (!hp && !hb && !ok) fits = false;
+      else if (hp && ok) B2_JS_BM(true, true);
+      else if (hp) B2_JS_BM(true, false);
+      else if (ok) B2_JS_BM(false, true);
+      else B2_JS_BM(false, false);
+#undef B2_JS_BM
 #undef B2_JS_LAUNCH
       if (fits) {
         B2_CHECK_LAUNCH("b2_join_stream_kernel");

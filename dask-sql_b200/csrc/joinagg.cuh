@@ -24,7 +24,7 @@ struct b2_joinagg_arg {
 };
 
 // build value of one matched row as a raw 64-bit word of the payload's LOGICAL type
-__device__ __forceinline__ int64_t b2_ja_payload(const b2_col_t& c, int64_t base, uint64_t d) {
+__device__ __forceinline__ int64_t b2_ja_payload(const b2_col_t& c, int64_t base, uint32_t d) {
   if (c.dtype == B2_U32) return base + (int64_t)(uint32_t)b2_ld_keep_i32(reinterpret_cast<const int32_t*>(c.data) + d);
   return b2_ld_keep_i64(reinterpret_cast<const int64_t*>(c.data) + d);
 }
@@ -34,40 +34,57 @@ __device__ __forceinline__ void b2_join_agg_body(const b2_scan_t& s, const b2_gl
                                                  const b2_jointable_t& jt, const b2_joinagg_arg& ja,
                                                  int64_t (*sh_acc)[B2_BLOCK], int32_t (*sh_cnt)[B2_BLOCK], int tid) {
   const b2_col_t& kc = s.cols[key_col];
-  // trip 1: the join key is requested together with the predicate columns
-  bool full0;
-  const uint32_t inb = b2_bounds_bits<R>(ld.row0, s.n, full0);
-  int64_t key[R];
-  ld.template load<R>(key_col, inb, full0, key);
-  bool full;
-  const uint32_t bits = b2_eval_terms<R>(s, ld, full);
-  uint32_t live = bits;
-  if (kc.valid) live &= b2_valid_bits<R>(kc.valid, ld.row0, bits);
-  const uint64_t range = (uint64_t)jt.range;
-  uint64_t d[R];
+  // trip 1: the join key is requested together with the predicate columns.  Only the key OFFSETS are
+  // kept (32 bits: a key-ordered table spans < 2^31 keys), the keys themselves die here.
+  uint32_t d[R];
   uint32_t inr = 0;
+  {
+    bool full0;
+    const uint32_t inb = b2_bounds_bits<R>(ld.row0, s.n, full0);
+    int64_t key[R];
+    ld.template load<R>(key_col, inb, full0, key);
+    bool full;
+    const uint32_t bits = b2_eval_terms<R>(s, ld, full);
+    uint32_t live = bits;
+    if (kc.valid) live &= b2_valid_bits<R>(kc.valid, ld.row0, bits);
+    const uint64_t range = (uint64_t)jt.range;
 #pragma unroll
-  for (int j = 0; j < R; ++j) {
-    d[j] = (uint64_t)key[j] - (uint64_t)jt.kmin;
-    inr |= (uint32_t)(((live >> j) & 1) && d[j] < range) << j;
+    for (int j = 0; j < R; ++j) {
+      const uint64_t dd = (uint64_t)key[j] - (uint64_t)jt.kmin;
+      inr |= (uint32_t)(((live >> j) & 1) && dd < range) << j;
+      d[j] = (uint32_t)dd;
+    }
   }
   // trip 2: presence words, and -- speculatively, for every in-range row -- both inputs of the first
   // aggregate (the payload at an offset without a build row is garbage that nobody reads)
-  uint32_t word[R];
-#pragma unroll
-  for (int j = 0; j < R; ++j) word[j] = (inr >> j) & 1 ? (uint32_t)b2_ld_keep_i32(jt.lookup + (d[j] >> 5)) : 0u;
   const b2_joinagg_t a0 = ja.a[0];
   const bool pre_b = ja.n > 0 && a0.bcol >= 0 && ja.bcols[a0.bcol].dtype != B2_U8;
   const bool pre_p = ja.n > 0 && a0.pcol >= 0 && s.cols[a0.pcol].dtype != B2_U8;
   int64_t pb[R], pp[R];
-  if (pre_b) {
-#pragma unroll
-    for (int j = 0; j < R; ++j) pb[j] = (inr >> j) & 1 ? b2_ja_payload(ja.bcols[a0.bcol], ja.bbase[a0.bcol], d[j]) : 0;
-  }
-  if (pre_p) ld.template load<R>(a0.pcol, inr, false, pp);
   uint32_t matched = 0;
+  if (pre_b && (ja.bcols[a0.bcol].flags & B2_COL_SENTINEL)) {
+    // the payload marks absent keys itself (0xFFFFFFFF): no presence-bitmap request at all
+    const int32_t* pay32 = reinterpret_cast<const int32_t*>(ja.bcols[a0.bcol].data);
+    const int64_t base = ja.bbase[a0.bcol];
 #pragma unroll
-  for (int j = 0; j < R; ++j) matched |= ((word[j] >> (d[j] & 31)) & 1u) << j;
+    for (int j = 0; j < R; ++j) {
+      const uint32_t raw = (inr >> j) & 1 ? (uint32_t)b2_ld_keep_i32(pay32 + d[j]) : 0xffffffffu;
+      matched |= (uint32_t)(raw != 0xffffffffu) << j;
+      pb[j] = base + (int64_t)raw;
+    }
+    if (pre_p) ld.template load<R>(a0.pcol, inr, false, pp);
+  } else {
+    uint32_t word[R];
+#pragma unroll
+    for (int j = 0; j < R; ++j) word[j] = (inr >> j) & 1 ? (uint32_t)b2_ld_keep_i32(jt.lookup + (d[j] >> 5)) : 0u;
+    if (pre_b) {
+#pragma unroll
+      for (int j = 0; j < R; ++j) pb[j] = (inr >> j) & 1 ? b2_ja_payload(ja.bcols[a0.bcol], ja.bbase[a0.bcol], d[j]) : 0;
+    }
+    if (pre_p) ld.template load<R>(a0.pcol, inr, false, pp);
+#pragma unroll
+    for (int j = 0; j < R; ++j) matched |= ((word[j] >> (d[j] & 31)) & 1u) << j;
+  }
 
   for (int a = 0; a < ja.n; ++a) {
     const b2_joinagg_t ag = ja.a[a];
@@ -76,99 +93,80 @@ __device__ __forceinline__ void b2_join_agg_body(const b2_scan_t& s, const b2_gl
       continue;
     }
     uint32_t ok = matched;
-    int64_t p[R], b[R];
+    int64_t x[R];          // probe input, then the combined value
     bool pf = false, bf = false;
     if (ag.pcol >= 0) {
       const b2_col_t& c = s.cols[ag.pcol];
       pf = c.dtype == B2_F64;
       if (a == 0 && pre_p) {
 #pragma unroll
-        for (int j = 0; j < R; ++j) p[j] = pp[j];
+        for (int j = 0; j < R; ++j) x[j] = pp[j];
       } else {
-        ld.template load<R>(ag.pcol, matched, false, p);
+        ld.template load<R>(ag.pcol, matched, false, x);
       }
-      if (c.valid || pf) ok &= ~b2_null_bits<R>(c, ld.row0, matched, p);
+      if (c.valid || pf) ok &= ~b2_null_bits<R>(c, ld.row0, matched, x);
     }
     if (ag.bcol >= 0) {
       const b2_col_t& c = ja.bcols[ag.bcol];
       bf = c.dtype == B2_F64;
-      if (a == 0 && pre_b) {
+      const bool isf = pf || bf;
+      uint32_t bnull = 0;
 #pragma unroll
-        for (int j = 0; j < R; ++j) b[j] = pb[j];
-      } else if (c.dtype == B2_U8) {
-#pragma unroll
-        for (int j = 0; j < R; ++j) b[j] = (matched >> j) & 1 ? (int64_t) reinterpret_cast<const uint8_t*>(c.data)[d[j]] : 0;
-      } else {
-#pragma unroll
-        for (int j = 0; j < R; ++j) b[j] = (matched >> j) & 1 ? b2_ja_payload(c, ja.bbase[ag.bcol], d[j]) : 0;
+      for (int j = 0; j < R; ++j) {
+        int64_t y = 0;
+        if (a == 0 && pre_b) y = pb[j];
+        else if ((matched >> j) & 1) y = b2_ja_payload(c, ja.bbase[ag.bcol], d[j]);
+        if (bf) { const double t = __longlong_as_double(y); bnull |= (uint32_t)(t != t) << j; }
+        if (ag.combine == B2_JA_B) { x[j] = y; continue; }
+        if (isf) {
+          const double u = pf ? __longlong_as_double(x[j]) : (double)x[j];
+          const double w = bf ? __longlong_as_double(y) : (double)y;
+          double r;
+          switch (ag.combine) {
+            case B2_JA_MUL: r = u * w; break;
+            case B2_JA_ADD: r = u + w; break;
+            case B2_JA_SUB: r = u - w; break;
+            default: r = w - u; break;  // B2_JA_RSUB
+          }
+          x[j] = __double_as_longlong(r);
+        } else {
+          const uint64_t u = (uint64_t)x[j], w = (uint64_t)y;
+          uint64_t r;
+          switch (ag.combine) {
+            case B2_JA_MUL: r = u * w; break;
+            case B2_JA_ADD: r = u + w; break;
+            case B2_JA_SUB: r = u - w; break;
+            default: r = w - u; break;
+          }
+          x[j] = (int64_t)r;
+        }
       }
+      ok &= ~bnull;
       if (c.valid) {
 #pragma unroll
         for (int j = 0; j < R; ++j)
           if (((ok >> j) & 1) && !b2_bit(c.valid, (int64_t)d[j])) ok &= ~(1u << j);
       }
-      if (bf) {
-#pragma unroll
-        for (int j = 0; j < R; ++j) {
-          const double x = __longlong_as_double(b[j]);
-          if (x != x) ok &= ~(1u << j);
-        }
-      }
     }
-    // combine into one 64-bit value per row, in float64 as soon as either side is float
     const bool isf = pf || bf;
-    int64_t v[R];
-    if (ag.combine == B2_JA_P) {
-#pragma unroll
-      for (int j = 0; j < R; ++j) v[j] = p[j];
-    } else if (ag.combine == B2_JA_B) {
-#pragma unroll
-      for (int j = 0; j < R; ++j) v[j] = b[j];
-    } else if (isf) {
-#pragma unroll
-      for (int j = 0; j < R; ++j) {
-        const double x = pf ? __longlong_as_double(p[j]) : (double)p[j];
-        const double y = bf ? __longlong_as_double(b[j]) : (double)b[j];
-        double r;
-        switch (ag.combine) {
-          case B2_JA_MUL: r = x * y; break;
-          case B2_JA_ADD: r = x + y; break;
-          case B2_JA_SUB: r = x - y; break;
-          default: r = y - x; break;  // B2_JA_RSUB
-        }
-        v[j] = __double_as_longlong(r);
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < R; ++j) {
-        const uint64_t x = (uint64_t)p[j], y = (uint64_t)b[j];
-        uint64_t r;
-        switch (ag.combine) {
-          case B2_JA_MUL: r = x * y; break;
-          case B2_JA_ADD: r = x + y; break;
-          case B2_JA_SUB: r = x - y; break;
-          default: r = y - x; break;
-        }
-        v[j] = (int64_t)r;
-      }
-    }
     sh_cnt[a][tid] += __popc(ok);
     int64_t acc = sh_acc[a][tid];
     switch (b2_agg_kind(ag.op, isf ? B2_F64 : B2_I64)) {
-      case B2_K_SUM_I: acc = b2_fold_batch<R, B2_K_SUM_I>(acc, v, ok); break;
-      case B2_K_SUM_F: acc = b2_fold_batch<R, B2_K_SUM_F>(acc, v, ok); break;
-      case B2_K_SUMF_I: acc = b2_fold_batch<R, B2_K_SUMF_I>(acc, v, ok); break;
-      case B2_K_MIN_I: acc = b2_fold_batch<R, B2_K_MIN_I>(acc, v, ok); break;
-      case B2_K_MAX_I: acc = b2_fold_batch<R, B2_K_MAX_I>(acc, v, ok); break;
-      case B2_K_MIN_F: acc = b2_fold_batch<R, B2_K_MIN_F>(acc, v, ok); break;
-      case B2_K_MAX_F: acc = b2_fold_batch<R, B2_K_MAX_F>(acc, v, ok); break;
+      case B2_K_SUM_I: acc = b2_fold_batch<R, B2_K_SUM_I>(acc, x, ok); break;
+      case B2_K_SUM_F: acc = b2_fold_batch<R, B2_K_SUM_F>(acc, x, ok); break;
+      case B2_K_SUMF_I: acc = b2_fold_batch<R, B2_K_SUMF_I>(acc, x, ok); break;
+      case B2_K_MIN_I: acc = b2_fold_batch<R, B2_K_MIN_I>(acc, x, ok); break;
+      case B2_K_MAX_I: acc = b2_fold_batch<R, B2_K_MAX_I>(acc, x, ok); break;
+      case B2_K_MIN_F: acc = b2_fold_batch<R, B2_K_MIN_F>(acc, x, ok); break;
+      case B2_K_MAX_F: acc = b2_fold_batch<R, B2_K_MAX_F>(acc, x, ok); break;
       default: break;
     }
     sh_acc[a][tid] = acc;
   }
 }
 
-__global__ void __launch_bounds__(B2_BLOCK)
+template <int MINB>   // CTAs per SM the register allocation aims for: 2 = no spills (116 regs), 3 = 80 regs + ~270 B spills
+__global__ void __launch_bounds__(B2_BLOCK, MINB)
 b2_join_agg_kernel(const __grid_constant__ b2_scan_t s, int key_col, const __grid_constant__ b2_jointable_t jt,
                    const __grid_constant__ b2_joinagg_arg ja, b2_partial* __restrict__ partials) {
   __shared__ int64_t sh_acc[B2_MAX_AGGS][B2_BLOCK];
@@ -241,9 +239,18 @@ int32_t b2_join_agg(const b2_scan_t* scan, int32_t probe_key, const b2_jointable
   cudaStream_t st = (cudaStream_t)stream;
   b2_partial* partials = reinterpret_cast<b2_partial*>(ws);
   int64_t nblk = (scan->n + B2_JA_ROWS_PER_BLOCK - 1) / B2_JA_ROWS_PER_BLOCK;
-  int grid = b2_wave_grid(b2_join_agg_kernel, B2_BLOCK, nblk);
-  if (grid > 148 * 16) grid = 148 * 16;
-  b2_join_agg_kernel<<<grid, B2_BLOCK, 0, st>>>(*scan, probe_key, *jt, ja, partials);
+  int minb = 3;
+  if (const char* e = getenv("B200SQL_JA_MINB")) minb = atoi(e) == 2 ? 2 : 3;
+  int grid;
+  if (minb == 2) {
+    grid = b2_wave_grid(b2_join_agg_kernel<2>, B2_BLOCK, nblk);
+    if (grid > 148 * 16) grid = 148 * 16;
+    b2_join_agg_kernel<2><<<grid, B2_BLOCK, 0, st>>>(*scan, probe_key, *jt, ja, partials);
+  } else {
+    grid = b2_wave_grid(b2_join_agg_kernel<3>, B2_BLOCK, nblk);
+    if (grid > 148 * 16) grid = 148 * 16;
+    b2_join_agg_kernel<3><<<grid, B2_BLOCK, 0, st>>>(*scan, probe_key, *jt, ja, partials);
+  }
   B2_CHECK_LAUNCH("b2_join_agg_kernel");
   b2_scan_agg_final_kernel<<<naggs, B2_BLOCK, 0, st>>>(fa, partials, grid, d_out_acc, d_out_cnt, accumulate);
   B2_CHECK_LAUNCH("b2_scan_agg_final_kernel");

@@ -18,6 +18,19 @@
 #define B2_PART_R 8
 #define B2_PART_TILE (B2_BLOCK * B2_PART_R)
 #define B2_PART_MAX_BUCKETS 1024
+// Output positions are reserved with returning atomics on per-bucket cursors.  Atomics on ONE address are
+// served one at a time by the L2 (scripts/microbench/redg.cu "red_hot": 1.5 ns each without a return
+// value, far more with one), and with ~100 buckets every reservation of the whole GPU lands on ~100
+// addresses -- measured, that alone is most of the scatter's time.  So every bucket is fed through
+// B2_PART_GROUPS independent cursors: CTA c only ever touches group c % B2_PART_GROUPS, the histogram
+// pass counts per (group, bucket) with the same tile -> CTA assignment, and the scan lays a bucket's
+// groups out back to back.  Contention per address drops by the number of groups.
+#define B2_PART_GROUPS 64
+static inline int b2_part_grid(int64_t ntiles) {   // hist and scatter MUST use the same grid (tile -> CTA -> group)
+  int64_t g = (int64_t)b2_sm_count() * 4;
+  if (g > ntiles) g = ntiles;
+  return (int)(g < 1 ? 1 : g);
+}
 
 struct b2_partcarry_arg {
   int32_t n;
@@ -65,21 +78,40 @@ b2_part_hist_kernel(const __grid_constant__ b2_scan_t s, int key_col, int64_t km
       if (slot[j] >= 0) atomicAdd(&hist[(int)(slot[j] >> shift)], 1);
   }
   __syncthreads();
+  unsigned long long* mine = counts + (size_t)(blockIdx.x % B2_PART_GROUPS) * nbuckets;
   for (int b = threadIdx.x; b < nbuckets; b += B2_BLOCK)
-    if (hist[b]) atomicAdd(counts + b, (unsigned long long)hist[b]);
+    if (hist[b]) atomicAdd(mine + b, (unsigned long long)hist[b]);
 }
 
-// ws: [0, nb] bucket starts (in: counts), [nb+1, 2nb] write cursors
-__global__ void b2_part_scan_kernel(int64_t* __restrict__ ws, int nbuckets) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  int64_t run = 0;
-  for (int b = 0; b < nbuckets; ++b) {
-    const int64_t c = ws[b];
-    ws[b] = run;
-    ws[nbuckets + 1 + b] = run;
-    run += c;
+// ws: [0, nb] bucket starts (out), then cursors[group][bucket] (in: row counts from the histogram pass,
+// out: first output row of that group's share of the bucket)
+__global__ void __launch_bounds__(1024) b2_part_scan_kernel(int64_t* __restrict__ ws, int nbuckets) {
+  __shared__ int64_t warp_tot[32];
+  int64_t* cur = ws + nbuckets + 1;
+  const int b = threadIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int64_t total = 0;
+  if (b < nbuckets)
+    for (int g = 0; g < B2_PART_GROUPS; ++g) total += cur[(size_t)g * nbuckets + b];
+  int64_t incl = total;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int64_t t = __shfl_up_sync(FULL_MASK, incl, o);
+    if (lane >= o) incl += t;
   }
-  ws[nbuckets] = run;
+  if (lane == 31) warp_tot[warp] = incl;
+  __syncthreads();
+  int64_t off = 0;
+  for (int w = 0; w < warp; ++w) off += warp_tot[w];
+  int64_t run = off + incl - total;          // first output row of bucket b
+  if (b < nbuckets) {
+    ws[b] = run;
+    for (int g = 0; g < B2_PART_GROUPS; ++g) {
+      const int64_t c = cur[(size_t)g * nbuckets + b];
+      cur[(size_t)g * nbuckets + b] = run;
+      run += c;
+    }
+    if (b == nbuckets - 1) ws[nbuckets] = run;
+  }
 }
 
 // Scatter one 2048-row tile: ranks by shared-memory atomics, then the tile's rows are ordered by
@@ -138,7 +170,8 @@ b2_part_scatter_kernel(const __grid_constant__ b2_scan_t s, int key_col, int64_t
         const int b = threadIdx.x * PER + k;
         if (b < nbuckets) {
           prefix[b] = run;
-          base[b] = v[k] ? (long long)atomicAdd(cursor + b, (unsigned long long)v[k]) : 0;
+          base[b] = v[k] ? (long long)atomicAdd(cursor + (size_t)(blockIdx.x % B2_PART_GROUPS) * nbuckets + b,
+                                                (unsigned long long)v[k]) : 0;
           run += v[k];
         }
       }
@@ -202,6 +235,7 @@ b2_part_scatter_warp_kernel(const __grid_constant__ b2_scan_t s, int key_col, in
   uint16_t* st_src = st_bkt + ROWS;                                          // [ROWS] row within the chunk
   const int per = nb_pad >> 5;                                               // buckets per lane in the scan
   const int64_t nwarps = (int64_t)gridDim.x * B2_WARPS;
+  unsigned long long* mycur = cursor + (size_t)(blockIdx.x % B2_PART_GROUPS) * nbuckets;   // this CTA's cursor group
   for (int64_t chunk = (int64_t)blockIdx.x * B2_WARPS + warp; chunk < nchunks; chunk += nwarps) {
     for (int b = lane; b < nb_pad; b += 32) hist[b] = 0;
     __syncwarp();
@@ -234,7 +268,7 @@ b2_part_scatter_warp_kernel(const __grid_constant__ b2_scan_t s, int key_col, in
       const int b = lane * per + k;
       const int c = hist[b];
       hist[b] = run;
-      if (c) basem[b] = (long long)atomicAdd(cursor + b, (unsigned long long)c) - run;
+      if (c) basem[b] = (long long)atomicAdd(mycur + b, (unsigned long long)c) - run;
       run += c;
     }
     __syncwarp();
@@ -278,12 +312,10 @@ static int32_t b2_launch_scatter_warp(const b2_scan_t* scan, int32_t key_col, in
   int occ = 1;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, B2_BLOCK, smem);
   if (occ < 1) return b2_fail(B2_ERR_ARG, "range partition: %zu bytes of shared memory per CTA do not fit", smem);
+  static_assert(32 * R * B2_WARPS == B2_PART_TILE, "a CTA of the warp kernel covers exactly one histogram tile per step");
   const int64_t nchunks = (scan->n + 32 * R - 1) / (32 * R);
-  int64_t grid = (int64_t)b2_sm_count() * occ;
-  const int64_t need = (nchunks + B2_WARPS - 1) / B2_WARPS;
-  if (grid > need) grid = need;
-  if (grid < 1) grid = 1;
-  kern<<<(int)grid, B2_BLOCK, smem, st>>>(*scan, key_col, kmin, nslots, shift, nbuckets, nb_pad, nchunks, cursor, out_key,
+  const int grid = b2_part_grid((scan->n + B2_PART_TILE - 1) / B2_PART_TILE);
+  kern<<<grid, B2_BLOCK, smem, st>>>(*scan, key_col, kmin, nslots, shift, nbuckets, nb_pad, nchunks, cursor, out_key,
                                           carry);
   B2_CHECK_LAUNCH("b2_part_scatter_warp_kernel");
   return B2_OK;
@@ -291,7 +323,9 @@ static int32_t b2_launch_scatter_warp(const b2_scan_t* scan, int32_t key_col, in
 
 extern "C" {
 
-int64_t b2_range_partition_ws_bytes(int32_t nbuckets) { return 8 * (2 * (int64_t)nbuckets + 2); }
+int64_t b2_range_partition_ws_bytes(int32_t nbuckets) {
+  return 8 * ((int64_t)nbuckets + 2 + (int64_t)B2_PART_GROUPS * nbuckets);
+}
 
 static int32_t b2_part_check(const b2_scan_t* scan, int32_t key_col, int64_t nslots, int32_t shift, int32_t nbuckets,
                              const void* d_ws) {
@@ -310,16 +344,17 @@ int32_t b2_range_partition_hist(const b2_scan_t* scan, int32_t key_col, int64_t 
   if (rc) return rc;
   const int64_t ntiles = (scan->n + B2_PART_TILE - 1) / B2_PART_TILE;
   if (ntiles <= 0) return B2_OK;
-  int grid = b2_wave_grid(b2_part_hist_kernel, B2_BLOCK, ntiles);
-  b2_part_hist_kernel<<<grid, B2_BLOCK, 0, (cudaStream_t)stream>>>(*scan, key_col, kmin, nslots, shift, nbuckets, ntiles,
-                                                                  reinterpret_cast<unsigned long long*>(d_ws));
+  const int grid = b2_part_grid(ntiles);
+  b2_part_hist_kernel<<<grid, B2_BLOCK, 0, (cudaStream_t)stream>>>(
+      *scan, key_col, kmin, nslots, shift, nbuckets, ntiles,
+      reinterpret_cast<unsigned long long*>(reinterpret_cast<int64_t*>(d_ws) + nbuckets + 1));
   B2_CHECK_LAUNCH("b2_part_hist_kernel");
   return B2_OK;
 }
 
 int32_t b2_range_partition_scan(int32_t nbuckets, void* d_ws, void* stream) {
   B2_REQUIRE(nbuckets >= 1 && nbuckets <= B2_PART_MAX_BUCKETS && d_ws, "bad arguments");
-  b2_part_scan_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(reinterpret_cast<int64_t*>(d_ws), nbuckets);
+  b2_part_scan_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(reinterpret_cast<int64_t*>(d_ws), nbuckets);
   B2_CHECK_LAUNCH("b2_part_scan_kernel");
   return B2_OK;
 }
@@ -344,25 +379,19 @@ int32_t b2_range_partition_scatter(const b2_scan_t* scan, int32_t key_col, int64
   if (ntiles <= 0) return B2_OK;
   int64_t* ws = reinterpret_cast<int64_t*>(d_ws);
   // variant: B200SQL_SCATTER = "block" (round-1 kernel) | "warp8" | "warp16" (default warp8: rows per lane)
-  int variant = 8;   // re-read per call (cheap) so that tests and A/B runs can switch in-process
+  int variant = 8;   // "warp" (default) | "block" (round-1 kernel); re-read per call so tests can switch in-process
   if (const char* e = getenv("B200SQL_SCATTER")) {
     if (!strcmp(e, "block")) variant = 0;
-    else if (!strcmp(e, "warp16")) variant = 16;
   }
   if (variant) {
     unsigned long long* cur = reinterpret_cast<unsigned long long*>(ws + nbuckets + 1);
     cudaStream_t st = (cudaStream_t)stream;
     const int nc = ncarry >= 2 ? 2 : ncarry;
-    if (variant == 16) {
-      if (nc == 0) return b2_launch_scatter_warp<16, 0>(scan, key_col, kmin, nslots, shift, nbuckets, cur, out_key, carry, st);
-      if (nc == 1) return b2_launch_scatter_warp<16, 1>(scan, key_col, kmin, nslots, shift, nbuckets, cur, out_key, carry, st);
-      return b2_launch_scatter_warp<16, 2>(scan, key_col, kmin, nslots, shift, nbuckets, cur, out_key, carry, st);
-    }
     if (nc == 0) return b2_launch_scatter_warp<8, 0>(scan, key_col, kmin, nslots, shift, nbuckets, cur, out_key, carry, st);
     if (nc == 1) return b2_launch_scatter_warp<8, 1>(scan, key_col, kmin, nslots, shift, nbuckets, cur, out_key, carry, st);
     return b2_launch_scatter_warp<8, 2>(scan, key_col, kmin, nslots, shift, nbuckets, cur, out_key, carry, st);
   }
-  int grid = b2_wave_grid(b2_part_scatter_kernel, B2_BLOCK, ntiles);
+  const int grid = b2_part_grid(ntiles);
   b2_part_scatter_kernel<<<grid, B2_BLOCK, 0, (cudaStream_t)stream>>>(
       *scan, key_col, kmin, nslots, shift, nbuckets, ntiles, reinterpret_cast<unsigned long long*>(ws + nbuckets + 1),
       out_key, carry);

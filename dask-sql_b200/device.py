@@ -61,7 +61,7 @@ class Stats:
 class DeviceColumn:
     """values buffer + optional Arrow validity bitmap (stored as int32 words) on one GPU."""
 
-    __slots__ = ("data", "valid", "dtype", "logical", "n", "stats")
+    __slots__ = ("data", "valid", "dtype", "logical", "n", "stats", "flags")
 
     def __init__(self, data: torch.Tensor, valid: Optional[torch.Tensor], dtype: int, logical=None, stats=None):
         self.data = data
@@ -70,6 +70,7 @@ class DeviceColumn:
         self.logical = logical if logical is not None else {I64: "int64", F64: "float64", U8: "bool"}[dtype]
         self.n = int(data.shape[0])
         self.stats = stats
+        self.flags = 0
 
     @property
     def device(self):
@@ -80,6 +81,7 @@ class DeviceColumn:
         c.data = self.data.data_ptr() if self.n else 0
         c.valid = self.valid.data_ptr() if self.valid is not None and self.n else 0
         c.dtype = self.dtype
+        c.flags = self.flags
         return c
 
     def nbytes(self):
@@ -485,13 +487,21 @@ class JoinTable:
                 st = c.ensure_stats()
                 if st.vmin is not None and st.vmax - st.vmin < (1 << 32):
                     out_dtype, base = L.U32, int(st.vmin)
-            out = torch.empty(rng, dtype=store[out_dtype], device=dev)     # only present offsets are read
+            # a narrowed payload whose offsets leave 0xFFFFFFFF free marks absent keys itself (B2_COL_SENTINEL):
+            # the streaming probe and b2_join_agg then skip the presence bitmap (one random access per row)
+            sentinel = out_dtype == L.U32 and c.valid is None and st.vmax - st.vmin < (1 << 32) - 1
+            if sentinel:
+                out = torch.full((rng,), -1, dtype=torch.int32, device=dev)
+            else:
+                out = torch.empty(rng, dtype=store[out_dtype], device=dev)     # only present offsets are read
             ovalid = torch.zeros(bitmap_words(rng), dtype=torch.int32, device=dev) if c.valid is not None else None
             cs = c.as_struct()
             L.join_key_layout(C.byref(ks), n, kmin, rng, C.byref(cs), out_dtype, base, ptr(out), ptr(ovalid),
                               ptr(present) if first else None, stream_ptr())
             first = False
-            self.keyed_cols.append(DeviceColumn(out, ovalid, out_dtype, c.logical))
+            kc = DeviceColumn(out, ovalid, out_dtype, c.logical)
+            kc.flags = L.COL_SENTINEL if sentinel else 0
+            self.keyed_cols.append(kc)
             self.keyed_base.append(base)
         if first:
             L.join_key_layout(C.byref(ks), n, kmin, rng, None, 0, 0, None, None, ptr(present), stream_ptr())

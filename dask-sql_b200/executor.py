@@ -428,8 +428,10 @@ def estimated_rows(frame: LazyFrame) -> int:
 
 def gather_keyrange(part: Part) -> Part:
     """Key-range-sharded aggregate -> the same rows on every rank (all-gather in rank order)."""
+    if P.world()[1] == 1:
+        return part                    # single GPU: nothing to gather, and a pending result stays pending
     part = part.resolve()
-    if part.dist != "keyrange" or P.world()[1] == 1:
+    if part.dist != "keyrange":
         return part
     from .merge import allgather_part
     with _Phase("gather_result"):

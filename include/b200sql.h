@@ -79,8 +79,12 @@ typedef struct b2_col {
   const void*    data;    /* int64_t* / double* / uint8_t* */
   const uint8_t* valid;   /* Arrow validity bitmap or NULL */
   int32_t        dtype;   /* B2_I64 / B2_F64 / B2_U8 */
-  int32_t        pad_;
+  int32_t        flags;   /* B2_COL_* (0 for ordinary columns) */
 } b2_col_t;
+/* a B2_U32 key-ordered join payload in which every offset WITHOUT a build row holds 0xFFFFFFFF: the
+ * probe learns "no partner" from the payload itself and skips the presence bitmap -- one random L2
+ * request per probe row instead of two (the probe kernels are bound by the L2's request rate). */
+#define B2_COL_SENTINEL 1
 
 /* one conjunct of a pushed-down predicate:  cols[col] <op> literal */
 typedef struct b2_term {

@@ -466,7 +466,7 @@ def test_groupby_range_partitioned_matches_direct(nullable_key, monkeypatch):
     assert_frames(parted, exp, float_cols=fl, sort_by=["key"])
 
 
-@pytest.mark.parametrize("variant", ["block", "warp8", "warp16"])
+@pytest.mark.parametrize("variant", ["block", "warp"])
 @pytest.mark.parametrize("ncarry", [1, 3])
 def test_range_partition_scatter_variants(variant, ncarry, monkeypatch):
     """The scatter kernels (round-1 block-wide tile; warp-autonomous with 8 / 16 rows per lane; one to
