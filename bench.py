@@ -544,6 +544,7 @@ def _time_query(torch, executor, c, sql, steps, warmup, kernel_names):
             p.resolve()
     torch.cuda.synchronize()
     executor.kernel_events = []
+    executor.phase_events = []
     l0 = executor.stats["launches"]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -553,8 +554,14 @@ def _time_query(torch, executor, c, sql, steps, warmup, kernel_names):
     torch.cuda.synchronize()
     for p in parts:
         p.resolve()
-    kev = executor.kernel_events
-    executor.kernel_events = None
+    kev, pev = executor.kernel_events, executor.phase_events
+    executor.kernel_events = executor.phase_events = None
+    breakdown = {}
+    for name, _, a, b in kev:
+        breakdown[name] = breakdown.get(name, 0.0) + a.elapsed_time(b) / steps
+    for name, a, b in pev:
+        breakdown["phase:" + name] = breakdown.get("phase:" + name, 0.0) + a.elapsed_time(b) / steps
+    _time_query.breakdown = {k: round(v, 4) for k, v in breakdown.items()}
     return e0.elapsed_time(e1) / steps, kev, parts, (executor.stats["launches"] - l0) // steps
 
 
@@ -580,14 +587,30 @@ def run_configs(args, torch, dev, peak_gbs, peak_src, traffic):
     steps, warmup = max(3, min(args.steps, 5)), max(3, min(args.warmup, 3))
     out = {}
 
-    def entry(name, rows, ms, kev, kernel, bytes_per_row, launches, query, verified, extra=None):
+    # the SM -> L2 request path serves ~200 G random 4/8-byte requests per second on this part
+    # (scripts/microbench/redg.cu "red_spread f64_1red", L2-resident table; profiles/r02_redg.jsonl): the
+    # second roofline of the hash stages ("random 32 B-sector throughput ... report it")
+    L2_REQ_PEAK = 200.7
+
+    def entry(name, rows, ms, kev, kernel, bytes_per_row, launches, query, verified, extra=None, random_per_row=None):
         e = {"rows": rows, "ms": ms, "rows_per_s": rows / (ms * 1e-3), "query": query,
+             "breakdown_ms_per_step": getattr(_time_query, "breakdown", None),
              "algorithmic_gbs_whole_query": rows * bytes_per_row / (ms * 1e-3) / 1e9,
              "frac_of_peak_whole_query": rows * bytes_per_row / (ms * 1e-3) / 1e9 / peak_gbs,
              "roofline": kernel_roofline(kev, kernel, bytes_per_row, peak_gbs, peak_src, traffic, ms * 1e-3, steps),
              "gpu_launches_per_step": launches, "verified": verified, "steps": steps, "warmup": warmup}
         if extra:
             e.update(extra)
+        if random_per_row and e["roofline"]:
+            r = e["roofline"]
+            rows_l = r["algorithmic_bytes_per_launch"] / r["algorithmic_bytes_per_row"]
+            ach = rows_l * random_per_row / (r["avg_launch_ms"] * 1e-3) / 1e9
+            e["roofline_l2_requests"] = {"kernel": kernel, "bound": "SM->L2 random request rate", "unit": "G requests/s",
+                                         "random_requests_per_row": random_per_row, "achieved": ach, "peak": L2_REQ_PEAK,
+                                         "frac": ach / L2_REQ_PEAK,
+                                         "peak_source": "measured: scripts/microbench/redg.cu, one REDG.F64 per row into "
+                                                        "an 8 MB table (profiles/r02_redg.jsonl)",
+                                         "note": "streamed columns add ~0.25-0.5 sector requests per row on top"}
         out[name] = e
 
     def guarded(name, fn):
@@ -653,7 +676,8 @@ def run_configs(args, torch, dev, peak_gbs, peak_src, traffic):
                "checked": "every group against torch index_add_ (fp64 / int64)"},
               {"keys": nkeys, "distribution": "Zipf(1.1), ranks scattered by a permutation" if kind == "zipf"
                else "uniform", "hottest_key_share": top, "val": "int64" if kind == "int" else "float64",
-               "partitions": 8})
+               "partitions": 8, "grouped_kernel": executor.stats.get("grouped_groupby", 0) > 0},
+              random_per_row=None if kind == "zipf" else 1.0)
 
     # ---- C3: INNER JOIN 1B-row fact x 10M-row dim, 80 % match; materialising and fused SUM(v*w)
     def c3(name, fused):
@@ -682,7 +706,7 @@ def run_configs(args, torch, dev, peak_gbs, peak_src, traffic):
             rel = abs(got - exp) / max(abs(exp), 1e-300)
             entry(name, n, ms, kev, "b2_join_agg_kernel", 16, nl, q, {"ok": rel <= 1e-9, "rel_err": rel},
                   {"match_rate": n_match / n, "dim_rows": ndim, "partitions": 8,
-                   "algorithmic_bytes": "16 B per fact row (fk, v) + 16 B per dim row"})
+                   "algorithmic_bytes": "16 B per fact row (fk, v) + 16 B per dim row"}, random_per_row=1.0)
         else:
             q = "SELECT f.fk, f.v, d.w FROM fact f JOIN dim d ON f.fk = d.pk"
             ms, kev, parts, nl = _time_query(torch, executor, c, q, steps, warmup, ())
@@ -726,7 +750,8 @@ def run_configs(args, torch, dev, peak_gbs, peak_src, traffic):
                    "checked": "row count, integer column checksums exact, float checksum 1e-9, partition 0's rows "
                               "one by one as a multiset"},
                   {"match_rate": n_match / n, "dim_rows": ndim, "partitions": 8,
-                   "algorithmic_bytes": "16 B read per fact row + 24 B written per output row (+16 B per dim row)"})
+                   "algorithmic_bytes": "16 B read per fact row + 24 B written per output row (+16 B per dim row)"},
+                  random_per_row=1.0)
 
     # ---- C4 with a sparse primary key: the pk -> slot lookup is a hash table, not a direct-address array
     def c4s():

@@ -128,6 +128,9 @@ _SIGS = {
                          C.POINTER(AggState), _P],
     "b2_groupby_dense_grouped": [C.POINTER(Scan), C.c_int32, C.c_int64, C.c_int64, C.POINTER(Agg), C.c_int32,
                                  C.POINTER(AggState), _P],
+    "b2_hot_slots": [C.POINTER(Col), C.c_int64, C.c_int64, C.c_int64, _P, _P],
+    "b2_groupby_dense_hot": [C.POINTER(Scan), C.c_int32, C.c_int64, C.c_int64, C.POINTER(Agg), C.c_int32,
+                             C.POINTER(AggState), _P, _P],
     "b2_groupby_dense_ordered": [C.POINTER(Scan), C.c_int32, C.c_int64, C.c_int64, C.POINTER(Agg), C.c_int32,
                                  C.POINTER(AggState), _P, _P],
     "b2_groupby_hash1": [C.POINTER(Scan), C.c_int32, _P, C.c_int64, C.POINTER(Agg), C.c_int32,
@@ -205,6 +208,8 @@ gather = _wrap("b2_gather")
 groupby_dense = _wrap("b2_groupby_dense")
 groupby_dense_ordered = _wrap("b2_groupby_dense_ordered")
 groupby_dense_grouped = _wrap("b2_groupby_dense_grouped")
+groupby_dense_hot = _wrap("b2_groupby_dense_hot")
+hot_slots = _wrap("b2_hot_slots")
 groupby_hash1 = _wrap("b2_groupby_hash1")
 groupby_hashk = _wrap("b2_groupby_hashk")
 join_build = _wrap("b2_join_build")

@@ -76,6 +76,22 @@ b2_groupby_dense_grouped_kernel(const __grid_constant__ b2_scan_t s, int key_col
   b2_hot_flush(hot, hs, aggs, st);
 }
 
+// The same for a handful of HEAVY HITTERS named by b2_hot_slots: their rows accumulate in thread-private
+// shared-memory partials (no atomics, no match), everything else takes the per-row atomic.
+__global__ void __launch_bounds__(B2_BLOCK)
+b2_groupby_dense_hh_kernel(const __grid_constant__ b2_scan_t s, int key_col, int64_t kmin, int64_t nslots,
+                           const __grid_constant__ b2_aggs_arg aggs, const __grid_constant__ b2_aggstate_t st,
+                           const __grid_constant__ b2_hot_t hot, const int32_t* __restrict__ d_hot, int cap) {
+  extern __shared__ __align__(128) uint8_t b2_smem[];
+  const b2_hh_smem hs = b2_hh_init(hot, d_hot, cap, b2_smem);
+  b2_tile_direct<B2_GB_R>(s, [&](const b2_gld& ld) {
+    int64_t slot[B2_GB_R];
+    b2_dense_slots_of<B2_GB_R>(s, ld, key_col, kmin, nslots, slot);
+    b2_apply_aggs_hh<B2_GB_R>(s, ld, aggs.a, aggs.n, st, slot, hot, hs);
+  });
+  b2_hh_flush(hot, hs, d_hot, aggs, st);
+}
+
 // ---- hash, single 64-bit key ----------------------------------------------------------------
 __device__ __forceinline__ int64_t b2_hash1_slot(int64_t* __restrict__ tk, int64_t cap, int64_t key,
                                                  int32_t* __restrict__ flags) {
@@ -444,6 +460,48 @@ int32_t b2_groupby_dense_grouped(const b2_scan_t* scan, int32_t key_col, int64_t
   if (grid < 1) grid = 1;
   b2_groupby_dense_grouped_kernel<<<(int)grid, B2_BLOCK, smem, (cudaStream_t)stream>>>(*scan, key_col, kmin, nslots, aa, *st, hot);
   B2_CHECK_LAUNCH("b2_groupby_dense_grouped_kernel");
+  return B2_OK;
+}
+
+int32_t b2_hot_slots(const b2_col_t* key, int64_t n, int64_t kmin, int64_t nslots, int32_t* d_hot, void* stream) {
+  B2_REQUIRE(key && d_hot, "null argument");
+  B2_REQUIRE(key->dtype == B2_I64, "heavy hitters are sampled from an int64 key column");
+  B2_REQUIRE(nslots >= 2 && nslots < ((int64_t)1 << 31), "bad slot range");
+  b2_hot_slots_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(*key, n > 0 ? n : 0, kmin, nslots, d_hot);
+  B2_CHECK_LAUNCH("b2_hot_slots_kernel");
+  return B2_OK;
+}
+
+int32_t b2_groupby_dense_hot(const b2_scan_t* scan, int32_t key_col, int64_t kmin, int64_t nslots,
+                             const b2_agg_t* aggs, int32_t naggs, const b2_aggstate_t* st, const int32_t* d_hot,
+                             void* stream) {
+  int32_t rc = b2_check_scan(scan);
+  if (rc) return rc;
+  b2_aggs_arg aa;
+  if ((rc = b2_check_aggs(scan, aggs, naggs, &aa))) return rc;
+  if ((rc = b2_check_state(aa, st))) return rc;
+  B2_REQUIRE(d_hot, "null heavy-hitter list");
+  B2_REQUIRE(key_col >= 0 && key_col < scan->ncols, "key column out of range");
+  B2_REQUIRE(scan->cols[key_col].dtype == B2_I64 || scan->cols[key_col].dtype == B2_U8, "dense keys must be integers");
+  B2_REQUIRE(nslots >= 2 && nslots < ((int64_t)1 << 31), "nslots must cover the key range plus the NULL slot, below 2^31");
+  if (scan->n == 0) return B2_OK;
+  b2_hot_t hot;
+  b2_make_hot(*scan, aa, *st, &hot);
+  const int cap = b2_hh_capacity(hot.narrays);
+  if (cap == 0)   // nothing SUM-like to privatise (MIN / MAX only): the plain kernel
+    return b2_groupby_dense(scan, key_col, kmin, nslots, aggs, naggs, st, stream);
+  const size_t smem = b2_hh_smem_bytes(hot.narrays);
+  if (smem > 48 * 1024)
+    B2_CUDA_TRY(cudaFuncSetAttribute(b2_groupby_dense_hh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int64_t nblk = (scan->n + B2_GB_ROWS_PER_BLOCK - 1) / B2_GB_ROWS_PER_BLOCK;
+  int occ = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, b2_groupby_dense_hh_kernel, B2_BLOCK, smem);
+  int64_t grid = (int64_t)b2_sm_count() * (occ < 1 ? 1 : occ);
+  if (grid > nblk) grid = nblk;
+  if (grid < 1) grid = 1;
+  b2_groupby_dense_hh_kernel<<<(int)grid, B2_BLOCK, smem, (cudaStream_t)stream>>>(*scan, key_col, kmin, nslots, aa, *st, hot,
+                                                                                 d_hot, cap);
+  B2_CHECK_LAUNCH("b2_groupby_dense_hh_kernel");
   return B2_OK;
 }
 

@@ -667,13 +667,20 @@ b2_join_onepass_kernel(const __grid_constant__ b2_scan_t s, int key_col, const _
 // tests/integration/test_compatibility.py:7-9); callers that want probe order use the counted mode.
 // BMODE: how the build column is stored -- 0 none, 1 eight bytes, 2 uint32 offsets (+ presence bitmap),
 // 3 uint32 offsets in which 0xFFFFFFFF marks "no build row" (B2_COL_SENTINEL: no bitmap access at all)
-template <bool HAS_P, int BMODE, bool OUT_KEY>
+// CTA_RES: the 8 warps of a tile reserve their output range together (two barriers per 2048-row tile, one
+// atomic) instead of one atomic per warp batch: *total is ONE address, and the L2 serves same-address
+// atomics one at a time (~1.5 ns each, scripts/microbench/redg.cu) -- 488k reservations per 125M-row
+// partition were most of the kernel's time.
+template <bool HAS_P, int BMODE, bool OUT_KEY, bool CTA_RES>
 __global__ void __launch_bounds__(B2_BLOCK, 3)
 b2_join_stream_kernel(const __grid_constant__ b2_scan_t s, int key_col, int p_col, const __grid_constant__ b2_jointable_t jt,
                       const void* __restrict__ payload, int64_t pay_base, int64_t ntiles, int64_t* __restrict__ out_key,
                       int64_t* __restrict__ out_p, int64_t* __restrict__ out_b, unsigned long long* __restrict__ total) {
   constexpr int R = B2_JOP_R;
   constexpr bool HAS_B = BMODE != 0;
+  __shared__ int sh_cnt[2][B2_WARPS];
+  __shared__ long long sh_base[2];
+  int phase = 0;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t lt_mask = (1u << lane) - 1;
   const uint64_t range = (uint64_t)jt.range;
@@ -721,9 +728,26 @@ b2_join_stream_kernel(const __grid_constant__ b2_scan_t s, int key_col, int p_co
       rel[j] = ((emit >> j) & 1) ? wtotal + __popc(b & lt_mask) : -1;
       wtotal += __popc(b);
     }
-    unsigned long long r = 0;
-    if (lane == 0 && wtotal) r = atomicAdd(total, (unsigned long long)wtotal);
-    const int64_t off = (int64_t)__shfl_sync(FULL_MASK, r, 0);
+    int64_t off;
+    if (CTA_RES) {
+      // double-buffered by tile parity: a warp that runs ahead writes the OTHER buffer
+      if (lane == 0) sh_cnt[phase][warp] = wtotal;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        int t = 0;
+#pragma unroll
+        for (int w = 0; w < B2_WARPS; ++w) t += sh_cnt[phase][w];
+        sh_base[phase] = t ? (long long)atomicAdd(total, (unsigned long long)t) : 0;
+      }
+      __syncthreads();
+      off = sh_base[phase];
+      for (int w = 0; w < warp; ++w) off += sh_cnt[phase][w];
+      phase ^= 1;
+    } else {
+      unsigned long long r = 0;
+      if (lane == 0 && wtotal) r = atomicAdd(total, (unsigned long long)wtotal);
+      off = (int64_t)__shfl_sync(FULL_MASK, r, 0);
+    }
 #pragma unroll
     for (int j = 0; j < R; ++j) {
       if (rel[j] < 0) continue;
@@ -965,11 +989,19 @@ int32_t b2_join_onepass(const b2_scan_t* scan, const int32_t* probe_keys, const 
       int64_t* o_p = hp ? reinterpret_cast<int64_t*>(g.probe_out[p_out]) : nullptr;
       int64_t* o_b = hb ? reinterpret_cast<int64_t*>(g.build_out[0]) : nullptr;
       unsigned long long* tot = reinterpret_cast<unsigned long long*>(total);
+      bool cta_res = true;   // B200SQL_JOIN_RESERVE=warp: one atomic per warp batch (A/B)
+      if (const char* e = getenv("B200SQL_JOIN_RESERVE")) cta_res = strcmp(e, "warp") != 0;
 #define B2_JS_LAUNCH(HP, BM, OK)                                                                                 \
       do {                                                                                                        \
-        int sg = b2_wave_grid(b2_join_stream_kernel<HP, BM, OK>, B2_BLOCK, ntiles);                               \
-        b2_join_stream_kernel<HP, BM, OK><<<sg, B2_BLOCK, 0, st>>>(*scan, pk.cols[0], hp ? p_col : 0, *jt,        \
-                                                                   payload, base, ntiles, o_key, o_p, o_b, tot);  \
+        if (cta_res) {                                                                                            \
+          int sg = b2_wave_grid(b2_join_stream_kernel<HP, BM, OK, true>, B2_BLOCK, ntiles);                       \
+          b2_join_stream_kernel<HP, BM, OK, true><<<sg, B2_BLOCK, 0, st>>>(*scan, pk.cols[0], hp ? p_col : 0, *jt, \
+                                                                     payload, base, ntiles, o_key, o_p, o_b, tot); \
+        } else {                                                                                                  \
+          int sg = b2_wave_grid(b2_join_stream_kernel<HP, BM, OK, false>, B2_BLOCK, ntiles);                      \
+          b2_join_stream_kernel<HP, BM, OK, false><<<sg, B2_BLOCK, 0, st>>>(*scan, pk.cols[0], hp ? p_col : 0, *jt, \
+                                                                     payload, base, ntiles, o_key, o_p, o_b, tot); \
+        }                                                                                                         \
       } while (0)
 #define B2_JS_BM(HP, OK)                                                                                          \
       do {                                                                                                        \

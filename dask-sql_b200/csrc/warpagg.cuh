@@ -286,3 +286,245 @@ __device__ __forceinline__ void b2_hot_flush(const b2_hot_t& hot, const b2_hot_s
     }
   }
 }
+
+// =====================================================================================================
+// Level 0 for heavy hitters: thread-private accumulators.
+//
+// Measured on B200 (scripts/microbench/redg.cu): MATCH.ANY costs ~4 cycles per DISTINCT value per warp
+// instruction and the unit is shared by the SM, so grouping every 32-row step by match (above) tops out
+// near 70 G rows/s.  The rows that hurt, though, belong to a handful of keys.  A sampling pre-pass
+// (b2_hot_slots) names up to B2_HH_MAX heavy hitters; the aggregation kernel keeps, for each of them and
+// each carried accumulator, one partial PER THREAD in shared memory ([array][hitter][thread]: consecutive
+// lanes -> consecutive words, conflict-free) and updates it with a plain load-add-store -- no atomics, no
+// cross-lane traffic.  Every other row takes the usual fire-and-forget global atomic.  At the end the CTA
+// folds its 256 partials per (hitter, array) and issues ONE global atomic each.
+// =====================================================================================================
+#define B2_HH_MAX 32          // heavy hitters tracked (top of the sample)
+#define B2_HH_MAP 128         // open-addressing slot -> hitter index map in shared memory (power of two)
+#define B2_HH_SAMPLE 32768    // rows sampled by the pre-pass
+#define B2_HH_COUNTERS 4096   // counters of the pre-pass (power of two)
+#define B2_HH_MIN_COUNT 6     // sample occurrences that make a slot a heavy hitter (share >~ 0.02 %)
+
+__device__ __forceinline__ uint32_t b2_hh_hash(int32_t slot) { return (uint32_t)slot * 0x9e3779b1u; }
+
+// One CTA of 1024 threads: strided sample of the key column -> exact counts of the sampled slots in a
+// shared hash table -> the B2_HH_MAX most frequent ones (count >= B2_HH_MIN_COUNT) to d_hot, -1 padded.
+// A performance hint only: results never depend on which slots are listed.
+__global__ void __launch_bounds__(1024)
+b2_hot_slots_kernel(const __grid_constant__ b2_col_t key, int64_t n, int64_t kmin, int64_t nslots,
+                    int32_t* __restrict__ d_hot) {
+  __shared__ int32_t tag[B2_HH_COUNTERS];
+  __shared__ uint32_t cnt[B2_HH_COUNTERS];
+  __shared__ unsigned long long best;
+  for (int i = threadIdx.x; i < B2_HH_COUNTERS; i += 1024) { tag[i] = -1; cnt[i] = 0; }
+  __syncthreads();
+  const int64_t m = n < B2_HH_SAMPLE ? n : B2_HH_SAMPLE;
+  for (int64_t i = threadIdx.x; i < m; i += 1024) {
+    // 32 consecutive rows per sample group, groups spread over the partition
+    const int64_t grp = i >> 5, ngrp = (m + 31) >> 5;
+    int64_t row = (n / ngrp) * grp + (i & 31);
+    if (row >= n) row = n - 1;
+    if (key.valid && !b2_bit(key.valid, row)) continue;
+    const uint64_t d = (uint64_t)(reinterpret_cast<const int64_t*>(key.data)[row]) - (uint64_t)kmin;
+    if (d >= (uint64_t)(nslots - 1)) continue;
+    const int32_t slot = (int32_t)d;
+    uint32_t h = b2_hh_hash(slot) >> 20;
+    for (int probe = 0; probe < 8; ++probe, h = (h + 1) & (B2_HH_COUNTERS - 1)) {
+      h &= B2_HH_COUNTERS - 1;
+      int32_t t = tag[h];
+      if (t == -1) t = atomicCAS(&tag[h], -1, slot), t = (t == -1 ? slot : t);
+      if (t == slot) { atomicAdd(&cnt[h], 1u); break; }
+    }
+  }
+  __syncthreads();
+  for (int round = 0; round < B2_HH_MAX; ++round) {
+    if (threadIdx.x == 0) best = 0;
+    __syncthreads();
+    unsigned long long mine = 0;
+    for (int i = threadIdx.x; i < B2_HH_COUNTERS; i += 1024)
+      if (cnt[i] >= B2_HH_MIN_COUNT) {
+        const unsigned long long v = ((unsigned long long)cnt[i] << 32) | (unsigned)i;
+        mine = v > mine ? v : mine;
+      }
+    if (mine) atomicMax(&best, mine);
+    __syncthreads();
+    const unsigned long long b = best;
+    if (threadIdx.x == 0) {
+      d_hot[round] = b ? tag[(int)(b & 0xffffffffu)] : -1;
+      if (b) cnt[(int)(b & 0xffffffffu)] = 0;
+    }
+    __syncthreads();
+  }
+}
+
+struct b2_hh_smem {
+  int32_t* map_slot;     // [B2_HH_MAP]  slot or -1
+  int32_t* map_idx;      // [B2_HH_MAP]
+  int64_t* part;         // [narrays][nh][B2_BLOCK] thread-private partials
+  int nh;                // hitters actually tracked (<= hot.nh_cap)
+};
+
+// hitters the shared memory budget allows: 64 KB / (arrays x 256 threads x 8 B)
+static inline int b2_hh_capacity(int narrays) {
+  if (narrays <= 0) return 0;
+  int cap = (64 * 1024) / (narrays * B2_BLOCK * 8);
+  return cap > B2_HH_MAX ? B2_HH_MAX : cap;
+}
+static inline size_t b2_hh_smem_bytes(int narrays) {
+  return (size_t)B2_HH_MAP * 8 + (size_t)narrays * b2_hh_capacity(narrays) * B2_BLOCK * 8;
+}
+
+__device__ __forceinline__ b2_hh_smem b2_hh_init(const b2_hot_t& hot, const int32_t* __restrict__ d_hot, int cap,
+                                                 uint8_t* smem) {
+  b2_hh_smem hs;
+  hs.part = reinterpret_cast<int64_t*>(smem);
+  hs.map_slot = reinterpret_cast<int32_t*>(smem + (size_t)hot.narrays * cap * B2_BLOCK * 8);
+  hs.map_idx = hs.map_slot + B2_HH_MAP;
+  for (int i = threadIdx.x; i < B2_HH_MAP; i += blockDim.x) hs.map_slot[i] = -1;
+  // float partials start at -0.0 (the INT64_MIN bit pattern) and only ever receive x + 0.0: a partial that
+  // still reads -0.0 saw no row, -0.0 + -0.0 = -0.0 survives the fold, and anything else (+0.0 included)
+  // means "this CTA met the hitter" -- the same convention as the global accumulators' existence mark
+  for (int i = threadIdx.x; i < hot.narrays * cap * B2_BLOCK; i += blockDim.x)
+    hs.part[i] = hot.is_f64[i / (cap * B2_BLOCK)] ? (int64_t)0x8000000000000000LL : 0;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int k = 0; k < cap; ++k) {
+      const int32_t slot = d_hot[k];
+      if (slot < 0) break;
+      uint32_t h = (b2_hh_hash(slot) >> 24) & (B2_HH_MAP - 1);
+      while (hs.map_slot[h] != -1) h = (h + 1) & (B2_HH_MAP - 1);
+      hs.map_slot[h] = slot;
+      hs.map_idx[h] = k;
+    }
+  }
+  __syncthreads();
+  hs.nh = cap;
+  return hs;
+}
+
+__device__ __forceinline__ int b2_hh_find(const b2_hh_smem& hs, int64_t slot) {
+  if (slot < 0) return -1;
+  uint32_t h = (b2_hh_hash((int32_t)slot) >> 24) & (B2_HH_MAP - 1);
+  for (int probe = 0; probe < B2_HH_MAP; ++probe, h = (h + 1) & (B2_HH_MAP - 1)) {
+    const int32_t t = hs.map_slot[h];
+    if (t == (int32_t)slot) return hs.map_idx[h];
+    if (t == -1) return -1;
+  }
+  return -1;
+}
+
+// b2_apply_aggs with the heavy hitters' rows diverted to the thread-private partials
+template <int R, class LD>
+__device__ __forceinline__ void b2_apply_aggs_hh(const b2_scan_t& s, const LD& ld, const b2_agg_t* __restrict__ aggs,
+                                                 int naggs, const b2_aggstate_t& st, const int64_t (&slot)[R],
+                                                 const b2_hot_t& hot, const b2_hh_smem& hs) {
+  const int64_t row0 = ld.row0;
+  const int tid = threadIdx.x;
+  uint32_t live = 0;
+  int8_t hit[R];                      // index of the heavy hitter this row belongs to, -1 = none
+#pragma unroll
+  for (int j = 0; j < R; ++j) {
+    live |= (uint32_t)(slot[j] >= 0) << j;
+    hit[j] = (int8_t)b2_hh_find(hs, slot[j]);
+  }
+  if (st.out_slot) {
+#pragma unroll
+    for (int j = 0; j < R; ++j)
+      if (row0 + (int64_t)j * 32 < s.n) st.out_slot[row0 + (int64_t)j * 32] = (int32_t)slot[j];
+  }
+  if (st.rows) {
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      if (!((live >> j) & 1)) continue;
+      if (hit[j] >= 0) hs.part[((size_t)hot.rows_arr * hs.nh + hit[j]) * B2_BLOCK + tid] += 1;
+      else atomicAdd(reinterpret_cast<unsigned long long*>(st.rows) + slot[j], 1ULL);
+    }
+  }
+  if (st.present) {
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      if (!((live >> j) & 1)) continue;
+      const uint32_t b = 1u << (slot[j] & 31);
+      if (!(__ldca(st.present + (slot[j] >> 5)) & b)) atomicOr(st.present + (slot[j] >> 5), b);
+    }
+  }
+  for (int a = 0; a < naggs; ++a) {
+    const b2_agg_t ag = aggs[a];
+    if (ag.col < 0) continue;
+    const b2_col_t& c = s.cols[ag.col];
+    int64_t raw[R];
+    ld.template load<R>(ag.col, live, false, raw);
+    uint32_t ok = live;
+    if (c.valid || c.dtype == B2_F64) ok &= ~b2_null_bits<R>(c, row0, live, raw);
+    void* acc = st.acc[a];
+    int64_t* cnt = st.cnt[a];
+    const int kind = acc ? b2_agg_kind(ag.op, c.dtype) : B2_K_NONE;
+    const int acc_arr = hot.acc_arr[a], cnt_arr = hot.cnt_arr[a];
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      if (!((ok >> j) & 1)) continue;
+      const bool h = hit[j] >= 0;
+      if (cnt) {
+        if (h && cnt_arr >= 0) hs.part[((size_t)cnt_arr * hs.nh + hit[j]) * B2_BLOCK + tid] += 1;
+        else atomicAdd(reinterpret_cast<unsigned long long*>(cnt) + slot[j], 1ULL);
+      }
+      if (kind == B2_K_NONE) continue;
+      if (h && acc_arr >= 0) {
+        int64_t* p = hs.part + ((size_t)acc_arr * hs.nh + hit[j]) * B2_BLOCK + tid;
+        if (kind == B2_K_SUM_I) *p = (int64_t)((uint64_t)*p + (uint64_t)raw[j]);
+        else if (kind == B2_K_SUM_F)
+          *p = __double_as_longlong(__longlong_as_double(*p) + __dadd_rn(__longlong_as_double(raw[j]), 0.0));
+        else *p = __double_as_longlong(__longlong_as_double(*p) + __dadd_rn((double)raw[j], 0.0));     // B2_K_SUMF_I
+      } else {
+        switch (kind) {
+          case B2_K_SUM_I: b2_atomic_k<B2_K_SUM_I>(acc, slot[j], raw[j]); break;
+          case B2_K_SUM_F: b2_atomic_k<B2_K_SUM_F>(acc, slot[j], raw[j]); break;
+          case B2_K_SUMF_I: b2_atomic_k<B2_K_SUMF_I>(acc, slot[j], raw[j]); break;
+          case B2_K_MIN_I: b2_atomic_k<B2_K_MIN_I>(acc, slot[j], raw[j]); break;
+          case B2_K_MAX_I: b2_atomic_k<B2_K_MAX_I>(acc, slot[j], raw[j]); break;
+          case B2_K_MIN_F: b2_atomic_k<B2_K_MIN_F>(acc, slot[j], raw[j]); break;
+          default: b2_atomic_k<B2_K_MAX_F>(acc, slot[j], raw[j]); break;
+        }
+      }
+    }
+  }
+}
+
+// CTA epilogue: fold the 256 thread partials of every (array, hitter) and issue one global atomic each.
+// A hitter that this CTA never met contributes exact zeros, which are skipped (an untouched float SUM
+// accumulator must keep its -0.0 "no group" mark).
+__device__ __forceinline__ void b2_hh_flush(const b2_hot_t& hot, const b2_hh_smem& hs, const int32_t* __restrict__ d_hot,
+                                            const b2_aggs_arg& aggs, const b2_aggstate_t& st) {
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int k = warp; k < hot.narrays * hs.nh; k += B2_WARPS) {      // one warp per (array, hitter)
+    const int arr = k / hs.nh, idx = k % hs.nh;
+    const int32_t slot = d_hot[idx];
+    if (slot < 0) continue;
+    const int64_t* p = hs.part + (size_t)k * B2_BLOCK;
+    const bool f = hot.is_f64[arr];
+    double fs = -0.0;
+    uint64_t is = 0;
+    for (int t = lane; t < B2_BLOCK; t += 32) {
+      const int64_t v = p[t];
+      if (f) fs += __longlong_as_double(v);
+      else is += (uint64_t)v;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      fs += __shfl_xor_sync(FULL_MASK, fs, o);
+      is += __shfl_xor_sync(FULL_MASK, is, o);
+    }
+    const bool touched = f ? __double_as_longlong(fs) != (int64_t)0x8000000000000000LL : is != 0;
+    if (lane != 0 || !touched) continue;
+    // which destination does array `arr` belong to?
+    for (int a = 0; a < aggs.n; ++a) {
+      if (hot.acc_arr[a] == arr) {
+        if (f) atomicAdd(reinterpret_cast<double*>(st.acc[a]) + slot, fs);
+        else atomicAdd(reinterpret_cast<unsigned long long*>(st.acc[a]) + slot, (unsigned long long)is);
+      }
+      if (hot.cnt_arr[a] == arr) atomicAdd(reinterpret_cast<unsigned long long*>(st.cnt[a]) + slot, (unsigned long long)is);
+    }
+    if (hot.rows_arr == arr) atomicAdd(reinterpret_cast<unsigned long long*>(st.rows) + slot, (unsigned long long)is);
+  }
+}

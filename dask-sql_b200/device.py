@@ -410,11 +410,25 @@ class GroupTable:
         self.state.present = self.present.data_ptr() if self.present is not None else 0
 
 
-def groupby_dense(scan, key_col, kmin, table: GroupTable, grouped=False):
-    """grouped: the key column repeats inside warps (Stats.repeat): pre-aggregating kernel."""
-    fn = L.groupby_dense_grouped if grouped else L.groupby_dense
-    fn(C.byref(scan), key_col, int(kmin), table.nslots, table.aggs, len(table.specs), C.byref(table.state),
-       stream_ptr())
+def groupby_dense(scan, key_col, kmin, table: GroupTable, skew=None, hot=None):
+    """skew: None = one atomic per row; "warp" = per-warp match/shuffle pre-aggregation + per-CTA table
+    (b2_groupby_dense_grouped); "hot" = thread-private partials for the heavy hitters listed in `hot`
+    (int32[32] device tensor from hot_slots(); b2_groupby_dense_hot)."""
+    args = (C.byref(scan), key_col, int(kmin), table.nslots, table.aggs, len(table.specs), C.byref(table.state))
+    if skew == "hot" and hot is not None:
+        L.groupby_dense_hot(*args, ptr(hot), stream_ptr())
+    elif skew == "warp":
+        L.groupby_dense_grouped(*args, stream_ptr())
+    else:
+        L.groupby_dense(*args, stream_ptr())
+
+
+def hot_slots(key: DeviceColumn, kmin, nslots) -> torch.Tensor:
+    """int32[32]: the heavy hitters of a dense key column (sampled), -1 padded."""
+    out = torch.empty(32, dtype=torch.int32, device=key.device)
+    st = key.as_struct()
+    L.hot_slots(C.byref(st), key.n, int(kmin), int(nslots), ptr(out), stream_ptr())
+    return out
 
 
 def new_flags(device):

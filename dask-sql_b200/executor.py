@@ -974,8 +974,10 @@ def grouped_aggregate(parts, pred, gexprs, gnames, plan: AggPlan, child, sharded
             ws = torch.zeros(L.range_partition_ws_bytes(nbuckets) // 8, dtype=torch.int64, device=dev)
             for part, ctx, kslot, vslots in work:
                 stats["launches"] += 1
+                ev = _kernel_event_begin("b2_part_hist_kernel", part.n)
                 L.range_partition_hist(C.byref(ctx.scan()), kslot, kmin, nslots, shift, nbuckets, D.ptr(ws),
                                        D.stream_ptr())
+                _kernel_event_end(ev)
             stats["launches"] += 1
             L.range_partition_scan(nbuckets, D.ptr(ws), D.stream_ptr())
             ctx0 = work[0][1]
@@ -1002,11 +1004,22 @@ def grouped_aggregate(parts, pred, gexprs, gnames, plan: AggPlan, child, sharded
             _kernel_event_end(ev)
         else:
             gs = GroupState(dev, nslots, plan, need_present=True, alloc=_padded_slots(nslots, sharded))
+            # keys that repeat: "hot" = heavy hitters (sampled once per query from the first partition) go
+            # to thread-private partials; "warp" = match-based warp aggregation + per-CTA table
+            skew = os.environ.get("B200SQL_SKEW", "hot") if repeats else None
+            hot = None
             for part, ctx, kslot, _ in work:
                 gs.bind(ctx)
+                if skew == "hot" and hot is None:
+                    kcol = ctx.cols[kslot]
+                    if kcol.dtype == I64 and nslots < (1 << 31):
+                        stats["launches"] += 1
+                        hot = D.hot_slots(kcol, kmin, nslots)
+                    else:
+                        skew = "warp"
                 stats["launches"] += 1
                 ev = _kernel_event_begin("b2_groupby_dense_kernel", part.n)
-                D.groupby_dense(ctx.scan(), kslot, kmin, gs.table, grouped=repeats)
+                D.groupby_dense(ctx.scan(), kslot, kmin, gs.table, skew=skew, hot=hot)
                 _kernel_event_end(ev)
             stats["grouped_groupby"] = stats.get("grouped_groupby", 0) + (1 if repeats else 0)
         key_nullable = E.may_be_null(gexprs[0], lambda n: any(n in p and p[n].valid is not None for p in parts))
@@ -1015,6 +1028,11 @@ def grouped_aggregate(parts, pred, gexprs, gnames, plan: AggPlan, child, sharded
             t = torch.tensor([1 if key_nullable else 0], dtype=torch.int64, device=dev)
             key_nullable = bool(int(P.allreduce_(t, "max").item()))
         view = _merge_dense(gs.table, plan, sharded, dev)
+        # the NULL group sits in slot rng of the key range; the range-partitioned path allocates one slot
+        # more than that (b2_range_partition encodes NULL as the key value kmin + rng), which stays empty
+        view.nslots = nslots
+        if view.lo == 0 and view.count > nslots and view.dist != "keyrange":
+            view.count = nslots
         return _finalize_dense(view, kmin, gnames[0], gexprs[0], glog[0], plan, dev, key_nullable)
 
     # ---- hash tables: size from the row count, grow on overflow
@@ -1297,7 +1315,10 @@ def _finalize_dense(view: SlotView, kmin, gname, gexpr, glog, plan, dev, key_nul
         out = PendingPart(thunk)
         out.dist = view.dist
         return out
-    out = finish(_extract_dense(view, kmin, gname, gexpr, glog, dev, key_nullable), plan)
+    with _Phase("compact"):
+        raw = _extract_dense(view, kmin, gname, gexpr, glog, dev, key_nullable)
+    with _Phase("finish"):
+        out = finish(raw, plan)
     out.dist = view.dist
     if check is not None and int(check[0].item()):
         return fallback()

@@ -119,6 +119,11 @@ class DaskAggregatePlugin(BaseRelPlugin):
         shared, per_distinct_input = [], OrderedDict()
         for c in calls:
             fn, values = c.fn, c.arg
+            if values is not None and not isinstance(values, LazySeries):
+                # a literal argument (SUM(2), COUNT(1)): a constant column of the input
+                name = new_temporary_column(frame)
+                frame = frame.assign(**{name: values})
+                values = frame[name]
             if c.keep is not None:
                 if values is None:                                    # COUNT(*) FILTER (WHERE f) = COUNT(f or NULL)
                     fn, values = "count", c.keep.where(c.keep)

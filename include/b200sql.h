@@ -248,6 +248,18 @@ int32_t b2_groupby_dense_grouped(const b2_scan_t* scan, int32_t key_col, int64_t
                                  const b2_agg_t* aggs, int32_t naggs, const b2_aggstate_t* st,
                                  void* stream);
 
+/* Heavy hitters of a dense group key, by sampling: d_hot = int32[32] receives the slots (key - kmin) that
+ * occur most often among ~32k sampled rows of `key` (at least 6 times, i.e. a share above ~0.02 %), most
+ * frequent first, padded with -1.  A performance hint for b2_groupby_dense_hot; results never depend on it. */
+int32_t b2_hot_slots(const b2_col_t* key, int64_t n, int64_t kmin, int64_t nslots, int32_t* d_hot, void* stream);
+/* b2_groupby_dense in which the rows of the listed heavy hitters accumulate in thread-private shared
+ * memory partials (SUM / COUNT / COUNT(*) accumulators; no atomics, no cross-lane traffic) that every
+ * CTA flushes with one atomic per hitter and accumulator at its end; all other rows take the per-row
+ * atomic.  For Zipf-like keys: the few addresses that would otherwise serialise in the L2. */
+int32_t b2_groupby_dense_hot(const b2_scan_t* scan, int32_t key_col, int64_t kmin, int64_t nslots,
+                             const b2_agg_t* aggs, int32_t naggs, const b2_aggstate_t* st, const int32_t* d_hot,
+                             void* stream);
+
 /* Hash group table on ONE 64-bit key (int64, or float64 bits normalised -0.0 -> 0.0).
  * table_keys = int64[cap+2] pre-filled with B2_EMPTY_KEY, cap a power of two; slot cap holds
  * the NULL(/NaN) key group and slot cap+1 the group whose key equals B2_EMPTY_KEY.

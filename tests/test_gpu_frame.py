@@ -550,14 +550,17 @@ def test_join_agg_falls_back_on_duplicate_build_keys():
     np.testing.assert_allclose(float(got.s[0]), (j.v * j.w).sum(), rtol=RTOL)
 
 
-@pytest.mark.parametrize("hot_table", [True, False])
+@pytest.mark.parametrize("mode", ["hot", "warp", "warp_only"])
 @pytest.mark.parametrize("nullable_key", [False, True])
-def test_groupby_skewed_keys_preaggregate(hot_table, nullable_key, monkeypatch):
-    """Keys that repeat inside a warp (Zipf-like) take b2_groupby_dense_grouped: per-warp match/shuffle
-    pre-aggregation + the per-CTA shared-memory table of hot slots (or the warp level alone).  Every
-    accumulator kind, NULL inputs, a predicate, NULL keys, a ragged tail; against pandas."""
+def test_groupby_skewed_keys_preaggregate(mode, nullable_key, monkeypatch):
+    """Keys that repeat inside a warp (Zipf-like) do not take one global atomic per row: "hot" = the
+    sampled heavy hitters accumulate in thread-private shared-memory partials (b2_hot_slots +
+    b2_groupby_dense_hot); "warp" = per-warp match/shuffle pre-aggregation + a per-CTA table of claimed
+    slots (b2_groupby_dense_grouped), "warp_only" without that table.  Every accumulator kind, NULL
+    inputs, a predicate, NULL keys, zero-valued rows, a ragged tail; against pandas."""
     from dask_sql_b200 import executor
-    if not hot_table:
+    monkeypatch.setenv("B200SQL_SKEW", "hot" if mode == "hot" else "warp")
+    if mode == "warp_only":
         monkeypatch.setenv("B200SQL_NO_HOT_TABLE", "1")
     rng = np.random.default_rng(91)
     n, nkeys = 400_037, 3_000
@@ -566,7 +569,8 @@ def test_groupby_skewed_keys_preaggregate(hot_table, nullable_key, monkeypatch):
     df = pd.DataFrame({
         "key": pd.array(np.where(rng.random(n) < 0.03, None, key), dtype="Int64") if nullable_key else key,
         "v": rng.random(n), "w": rng.integers(-100, 100, n),
-        "g": np.where(rng.random(n) < 0.2, np.nan, rng.random(n)), "x": rng.integers(0, 10, n)})
+        "g": np.where(rng.random(n) < 0.2, np.nan, rng.random(n)), "x": rng.integers(0, 10, n),
+        "z": np.where(key % 2 == 0, 0.0, -0.0)})          # sums of +-0.0 only: existence must not hinge on the value
     spec = [("v", "sv", "sum"), ("w", "sw", "sum"), ("w", "aw", "mean"), ("g", "cg", "count"), ("g", "sg", "sum"),
             ("w", "mn", "min"), ("g", "mx", "max"), (None, "n", "size")]
     before = executor.stats.get("grouped_groupby", 0)
@@ -582,6 +586,9 @@ def test_groupby_skewed_keys_preaggregate(hot_table, nullable_key, monkeypatch):
     got = agg(f, ["key"], [("v", "sv", "sum")])
     exp = df.groupby("key", dropna=False).agg(sv=("v", "sum")).reset_index()
     assert_frames(got, exp, float_cols=("sv",), sort_by=["key"])
+    got = agg(f, ["key"], [("z", "sz", "sum")])             # every group exists although every sum is 0.0
+    exp = df.groupby("key", dropna=False).agg(sz=("z", "sum")).reset_index()
+    assert_frames(got, exp, float_cols=("sz",), sort_by=["key"])
 
 
 def test_uniform_keys_keep_the_per_row_atomic_kernel():

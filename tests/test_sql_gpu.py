@@ -166,12 +166,17 @@ def test_variance_is_stable_for_large_means(c):
     c.create_table("t", df, npartitions=4)
     got = c.sql("SELECT k, VAR_SAMP(v) AS vs, STDDEV_POP(v) AS sp, VAR_POP(w) AS vw FROM t GROUP BY k",
                 return_futures=False)
-    g = df.groupby("k")
+    # expected values from CENTRED data (v - 1e9 and w - 1e12 are exact in float64): pandas' own running
+    # update on the raw values is itself only good to ~1e-7 here
+    cen = pd.DataFrame({"k": df.k, "v": df.v - 1e9, "w": (df.w - 10**12).astype(float)})
+    g = cen.groupby("k")
     exp = pd.DataFrame({"k": sorted(df.k.unique()), "vs": g.v.var().values, "sp": g.v.std(ddof=0).values,
                         "vw": g.w.var(ddof=0).values})
-    assert_same(got, exp, ["vs", "sp", "vw"], rtol=1e-7)      # pandas itself is only ~1e-9 here
+    assert_same(got, exp, ["vs", "sp", "vw"], rtol=1e-9)
+    g_raw = df.groupby("k")                                      # and pandas on the raw values agrees to its own precision
+    np.testing.assert_allclose(got.sort_values("k").vs.to_numpy(), g_raw.v.var().values, rtol=1e-5)
     got = c.sql("SELECT VARIANCE(v) AS vs, STDDEV(w) AS sw FROM t", return_futures=False)
-    np.testing.assert_allclose([got.vs[0], got.sw[0]], [df.v.var(), df.w.std()], rtol=1e-7)
+    np.testing.assert_allclose([got.vs[0], got.sw[0]], [cen.v.var(), cen.w.std()], rtol=1e-9)
     # a constant group has variance exactly 0 (not NaN from sqrt of -1e-17); one row: sample variance NULL
     c.create_table("u", pd.DataFrame({"k": [1, 1, 1, 2], "v": [3.3e8 + 0.1] * 3 + [7.0]}))
     got = c.sql("SELECT k, STDDEV_POP(v) AS sp, VAR_SAMP(v) AS vs FROM u GROUP BY k", return_futures=False)
