@@ -436,7 +436,7 @@ __device__ __forceinline__ void b2_apply_aggs_hh(const b2_scan_t& s, const LD& l
 #pragma unroll
     for (int j = 0; j < R; ++j) {
       if (!((live >> j) & 1)) continue;
-      if (hit[j] >= 0) hs.part[((size_t)hot.rows_arr * hs.nh + hit[j]) * B2_BLOCK + tid] += 1;
+      if (hit[j] >= 0 && hot.rows_arr >= 0) hs.part[((size_t)hot.rows_arr * hs.nh + hit[j]) * B2_BLOCK + tid] += 1;
       else atomicAdd(reinterpret_cast<unsigned long long*>(st.rows) + slot[j], 1ULL);
     }
   }

@@ -121,7 +121,19 @@ def push_filters(plan: P.LogicalPlan, preds: List[PyExpr]) -> P.LogicalPlan:
                 lp.append(PyExpr("isnotnull", "BOOLEAN", args=[a.clone()]))
                 rp.append(PyExpr("isnotnull", "BOOLEAN", args=[b.clone()]))
         else:
-            res_keep = residual
+            # outer joins: an ON-clause term over the NULL-SUPPLYING side alone only decides which of
+            # that side's rows can be partners, so it filters that input (DataFusion's push_down_filter
+            # does the same with join on-filters); terms over the preserved side must stay in the ON clause
+            into_right = plan.how in ("LEFT", "LEFTSEMI", "LEFTANTI")
+            into_left = plan.how == "RIGHT"
+            for p in residual:
+                s = _side(p, left, right)
+                if s == "right" and into_right:
+                    rp.append(p)
+                elif s == "left" and into_left:
+                    lp.append(p)
+                else:
+                    res_keep.append(p)
         lp, rp = _dedup(lp), _dedup(rp)
         new = P.Join(push_filters(left, lp), push_filters(right, rp), plan.how, plan.on, P.conjunction(res_keep))
         return _wrap(new, keep)
