@@ -193,6 +193,124 @@ b2_join_agg_kernel(const __grid_constant__ b2_scan_t s, int key_col, const __gri
   }
 }
 
+// ---- the common shape, specialised: ONE aggregate SUM(P o B) (o = * + -) plus the join's row count,
+// nothing nullable by bitmap.  The generic kernel above spends ~115 thread-instructions per row on run-time
+// dispatch over aggregates, combines and types (ncu: profiles/r02_ncu_notes.md); with the types fixed at
+// compile time and the accumulators in registers the same work is a few dozen.
+// PF: probe column is float64 (else int64).  BK: build payload 0 = uint32 offsets with the 0xFFFFFFFF
+// "no row" sentinel (no bitmap access), 1 = uint32 + bitmap, 2 = int64 + bitmap, 3 = float64 + bitmap.
+template <bool PF, int BK>
+__global__ void __launch_bounds__(B2_BLOCK, 3)
+b2_join_agg_fast_kernel(const __grid_constant__ b2_scan_t s, int key_col, int p_col, const __grid_constant__ b2_jointable_t jt,
+                        const void* __restrict__ payload, int64_t pay_base, int combine, int sumf,
+                        b2_partial* __restrict__ partials) {
+  constexpr int R = B2_JA_R;
+  constexpr bool ISF = PF || BK == 3;
+  __shared__ int64_t sh_acc[B2_BLOCK];
+  __shared__ int32_t sh_cnt[2][B2_BLOCK];
+  double facc = 0.0;
+  uint64_t iacc = 0;
+  int cnt = 0, rows = 0;
+  const uint64_t range = (uint64_t)jt.range;
+  const int tile_off = (threadIdx.x >> 5) * (32 * R) + (threadIdx.x & 31);
+  for (int64_t base = (int64_t)blockIdx.x * B2_JA_ROWS_PER_BLOCK; base < s.n; base += (int64_t)gridDim.x * B2_JA_ROWS_PER_BLOCK) {
+    const int64_t row0 = base + tile_off;
+    bool full0;
+    const uint32_t inb = b2_bounds_bits<R>(row0, s.n, full0);
+    int64_t key[R], pv[R];
+    b2_load_batch64<R>(s.cols[key_col].data, row0, inb, full0, key);
+    b2_load_batch64<R>(s.cols[p_col].data, row0, inb, full0, pv);
+    bool full;
+    const uint32_t bits = s.nterms ? b2_eval_terms<R>(s, row0, full) : inb;
+    int64_t pay[R];
+    uint32_t m = 0;
+    if (BK == 0) {
+#pragma unroll
+      for (int j = 0; j < R; ++j) {
+        const uint64_t d = (uint64_t)key[j] - (uint64_t)jt.kmin;
+        const bool ok = ((bits >> j) & 1) && d < range;
+        const uint32_t raw = ok ? (uint32_t)b2_ld_keep_i32(reinterpret_cast<const int32_t*>(payload) + d) : 0xffffffffu;
+        m |= (uint32_t)(raw != 0xffffffffu) << j;
+        pay[j] = pay_base + (int64_t)raw;
+      }
+    } else {
+      uint32_t word[R];
+#pragma unroll
+      for (int j = 0; j < R; ++j) {
+        const uint64_t d = (uint64_t)key[j] - (uint64_t)jt.kmin;
+        const bool ok = ((bits >> j) & 1) && d < range;
+        word[j] = ok ? (uint32_t)b2_ld_keep_i32(jt.lookup + (d >> 5)) : 0u;
+        pay[j] = 0;
+        if (ok) pay[j] = BK == 1 ? pay_base + (int64_t)(uint32_t)b2_ld_keep_i32(reinterpret_cast<const int32_t*>(payload) + d)
+                                 : b2_ld_keep_i64(reinterpret_cast<const int64_t*>(payload) + d);
+      }
+#pragma unroll
+      for (int j = 0; j < R; ++j) m |= ((word[j] >> (((uint64_t)key[j] - (uint64_t)jt.kmin) & 31)) & 1u) << j;
+    }
+    rows += __popc(m);
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      if (!((m >> j) & 1)) continue;
+      if (ISF) {
+        const double x = PF ? __longlong_as_double(pv[j]) : (double)pv[j];
+        const double y = BK == 3 ? __longlong_as_double(pay[j]) : (double)pay[j];
+        if ((PF && x != x) || (BK == 3 && y != y)) continue;      // NaN = NULL: the row does not contribute
+        double r;
+        switch (combine) {
+          case B2_JA_MUL: r = x * y; break;
+          case B2_JA_ADD: r = x + y; break;
+          case B2_JA_SUB: r = x - y; break;
+          default: r = y - x; break;
+        }
+        facc += r;
+      } else {
+        const uint64_t x = (uint64_t)pv[j], y = (uint64_t)pay[j];
+        uint64_t r;
+        switch (combine) {
+          case B2_JA_MUL: r = x * y; break;
+          case B2_JA_ADD: r = x + y; break;
+          case B2_JA_SUB: r = x - y; break;
+          default: r = y - x; break;
+        }
+        if (sumf) facc += (double)(int64_t)r;
+        else iacc += r;
+      }
+      ++cnt;
+    }
+  }
+  const bool fres = ISF || sumf;
+  sh_acc[threadIdx.x] = fres ? __double_as_longlong(facc) : (int64_t)iacc;
+  sh_cnt[0][threadIdx.x] = cnt;
+  sh_cnt[1][threadIdx.x] = rows;
+  __syncthreads();
+  if (threadIdx.x == 0) {   // fixed order, like b2_scan_agg_kernel: bit-reproducible for a given grid
+    double f = 0.0;
+    uint64_t u = 0;
+    int64_t c = 0, rws = 0;
+    for (int t = 0; t < B2_BLOCK; ++t) {
+      if (fres) f += __longlong_as_double(sh_acc[t]);
+      else u += (uint64_t)sh_acc[t];
+      c += sh_cnt[0][t];
+      rws += sh_cnt[1][t];
+    }
+    partials[blockIdx.x].acc[0] = fres ? __double_as_longlong(f) : (int64_t)u;
+    partials[blockIdx.x].cnt[0] = c;
+    partials[blockIdx.x].acc[1] = 0;
+    partials[blockIdx.x].cnt[1] = rws;
+  }
+}
+
+template <bool PF, int BK>
+static int b2_launch_join_agg_fast(const b2_scan_t* scan, int key_col, int p_col, const b2_jointable_t* jt,
+                                   const void* payload, int64_t base, int combine, int sumf, b2_partial* partials,
+                                   cudaStream_t st) {
+  int64_t nblk = (scan->n + B2_JA_ROWS_PER_BLOCK - 1) / B2_JA_ROWS_PER_BLOCK;
+  int grid = b2_wave_grid(b2_join_agg_fast_kernel<PF, BK>, B2_BLOCK, nblk);
+  if (grid > 148 * 16) grid = 148 * 16;
+  b2_join_agg_fast_kernel<PF, BK><<<grid, B2_BLOCK, 0, st>>>(*scan, key_col, p_col, *jt, payload, base, combine, sumf, partials);
+  return grid;
+}
+
 extern "C" {
 
 int32_t b2_join_agg(const b2_scan_t* scan, int32_t probe_key, const b2_jointable_t* jt, int32_t nbuild,
@@ -238,6 +356,35 @@ int32_t b2_join_agg(const b2_scan_t* scan, int32_t probe_key, const b2_jointable
   }
   cudaStream_t st = (cudaStream_t)stream;
   b2_partial* partials = reinterpret_cast<b2_partial*>(ws);
+  {
+    // the specialised kernel when the call is  SUM(P o B) [+ COUNT(*)]  over bitmap-free 8-byte columns
+    const b2_joinagg_t& a0 = ja.a[0];
+    const char* off = getenv("B200SQL_JA_GENERIC");
+    bool fast = !(off && off[0] == '1') && naggs == 2 && ja.a[1].combine == B2_JA_ROWS &&
+                (a0.combine == B2_JA_MUL || a0.combine == B2_JA_ADD || a0.combine == B2_JA_SUB || a0.combine == B2_JA_RSUB) &&
+                (a0.op == B2_AGG_SUM || a0.op == B2_AGG_SUMF) && !scan->cols[probe_key].valid;
+    if (fast) {
+      const b2_col_t& pc = scan->cols[a0.pcol];
+      const b2_col_t& bc = ja.bcols[a0.bcol];
+      fast = !pc.valid && !bc.valid && pc.dtype != B2_U8;
+      if (fast) {
+        const bool pf = pc.dtype == B2_F64;
+        int bk;
+        if (bc.dtype == B2_U32) bk = (bc.flags & B2_COL_SENTINEL) ? 0 : 1;
+        else bk = bc.dtype == B2_F64 ? 3 : 2;
+        const int sumf = a0.op == B2_AGG_SUMF;
+        int grid = 0;
+#define B2_JAF(PF, BK) grid = b2_launch_join_agg_fast<PF, BK>(scan, probe_key, a0.pcol, jt, bc.data, ja.bbase[a0.bcol], a0.combine, sumf, partials, st)
+        if (pf) { if (bk == 0) B2_JAF(true, 0); else if (bk == 1) B2_JAF(true, 1); else if (bk == 2) B2_JAF(true, 2); else B2_JAF(true, 3); }
+        else { if (bk == 0) B2_JAF(false, 0); else if (bk == 1) B2_JAF(false, 1); else if (bk == 2) B2_JAF(false, 2); else B2_JAF(false, 3); }
+#undef B2_JAF
+        B2_CHECK_LAUNCH("b2_join_agg_fast_kernel");
+        b2_scan_agg_final_kernel<<<naggs, B2_BLOCK, 0, st>>>(fa, partials, grid, d_out_acc, d_out_cnt, accumulate);
+        B2_CHECK_LAUNCH("b2_scan_agg_final_kernel");
+        return B2_OK;
+      }
+    }
+  }
   int64_t nblk = (scan->n + B2_JA_ROWS_PER_BLOCK - 1) / B2_JA_ROWS_PER_BLOCK;
   int minb = 3;
   if (const char* e = getenv("B200SQL_JA_MINB")) minb = atoi(e) == 2 ? 2 : 3;

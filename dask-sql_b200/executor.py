@@ -722,6 +722,12 @@ def _moment_shifts(aggs, parts, child, sharded):
 
 
 def run_aggregate(src: AggSource, allow_fast=True) -> Part:
+    if allow_fast:
+        # a fused star query that was prepared before: straight to its cached launch descriptors
+        last = src.__dict__.get("_prepared_last")
+        if last is not None and last[0] == (P.world()[1], torch.cuda.current_device()) and last[1] in PreparedStar._live \
+                and os.environ.get("B200SQL_NO_PREPARED") != "1":
+            return last[1].run(src)
     child = src.child
     pred, never = simplify_pred(child.pred)
     gexprs = [child.exprs[g] for g in src.group_cols]
@@ -1141,6 +1147,9 @@ class SlotView:
         return DeviceColumn(keys, self.occ, I64), TermSpec(0, L.IS_NOT_NULL, 0)
 
 
+_PRESENCE_PROG = {}      # compiled once: the three ways a table records "this slot holds a group"
+
+
 def _presence_bytes(t: D.GroupTable, dev) -> torch.Tensor:
     """uint8[alloc]: 1 where this rank's partial table holds a group.  Derived from whatever the
     kernels maintained (row counter, -0.0 indicator accumulator, presence bitmap) in one
@@ -1148,18 +1157,22 @@ def _presence_bytes(t: D.GroupTable, dev) -> torch.Tensor:
     (in-switch NVLS reduction, zero-initialised scratch) under which -0.0 + -0.0 comes back +0.0."""
     n = t.alloc
     if t.rows is not None:
-        e, env = E.binop("gt", ColRef("x", I64), 0), {"x": DeviceColumn(t.rows, None, I64)}
+        kind, col = "rows", DeviceColumn(t.rows, None, I64)
     elif t.indicator is not None:
-        e = E.binop("ne", ColRef("x", I64), L.EMPTY_KEY)
-        env = {"x": DeviceColumn(t.acc[t.indicator].view(torch.int64), None, I64)}
+        kind, col = "indicator", DeviceColumn(t.acc[t.indicator].view(torch.int64), None, I64)
     else:
-        e = E.unop("not", Call("isnull", [ColRef("x", I64)], U8))
         # only the validity bitmap is read; any 8-byte buffer of the right length serves as values
         vals = next((a for a in list(t.acc) + list(t.cnt) if a is not None), None)
         if vals is None:
             vals = torch.zeros(n, dtype=torch.int64, device=dev)
-        env = {"x": DeviceColumn(vals.view(torch.int64), t.present, I64)}
-    return eval_expr(Part(env, n), E.cast(e, U8)).data
+        kind, col = "bitmap", DeviceColumn(vals.view(torch.int64), t.present, I64)
+    prog = _PRESENCE_PROG.get(kind)
+    if prog is None:
+        x = ColRef("x", I64)
+        e = {"rows": lambda: E.binop("gt", x, 0), "indicator": lambda: E.binop("ne", x, L.EMPTY_KEY),
+             "bitmap": lambda: E.unop("not", Call("isnull", [x], U8))}[kind]()
+        prog = _PRESENCE_PROG[kind] = E.compile_expr(E.cast(e, U8), ["x"])
+    return D.expr_eval(prog, [col], n, False).data
 
 
 def _merge_dense(t: D.GroupTable, plan: AggPlan, sharded: bool, dev) -> SlotView:
@@ -1468,6 +1481,195 @@ def _side_of(e: Expr, left_names: Set[str], right_names: Set[str]):
     return "both"
 
 
+class PreparedStar:
+    """Everything about one fused star query that does not change between executions, kept with the
+    (immutable) plan: launch descriptors of every dim / fact partition (ctypes structs over resident
+    columns), the aggregate plan, the lookup buffers and the group table (re-initialised, not
+    re-allocated, per run).  A step of a repeated query then costs the host a few dozen calls instead
+    of re-deriving all of it -- at 8 GPUs a step is ~1 ms of device work, so host time IS the step time.
+
+    Two streams: the build side (lookup fill -> b2_star_build_scan -> NCCL broadcast) runs on its own
+    stream into one of two lookup buffers, the fact scan / merge / compaction on the caller's stream
+    after an event.  Consecutive executions therefore overlap: the next query's build + broadcast
+    proceeds under the current query's scan.  Buffer i is refilled only after the whole run that last
+    read it has been enqueued AND finished (event), so nothing is overwritten while in use; results
+    are always freshly allocated and never alias the reused buffers."""
+
+    _live: "List[PreparedStar]" = []
+    MAX_LIVE = 4          # prepared plans keep ~100 MB of HBM each: keep only the most recent ones
+
+    @classmethod
+    def get(cls, src, fact, dim, fk_e, pk_e, ge, gexpr0, aggs, fpred, dpred, meta, owner, bcast, sharded, dev):
+        key = (sharded, P.world()[1], torch.cuda.current_device())
+        cache = src.__dict__.setdefault("_prepared_star", {})
+        if key in cache:
+            prep = cache[key]
+            if prep is not None and prep not in cls._live:      # evicted meanwhile: its buffers are gone
+                prep = None
+                cache.pop(key)
+            else:
+                return prep
+        try:
+            prep = cls(src, fact, dim, fk_e, pk_e, ge, gexpr0, aggs, fpred, dpred, meta, owner, bcast, sharded, dev)
+        except _NotPreparable:
+            prep = None
+        if P.world()[1] > 1:
+            # every rank must take the same path (the prepared one issues its own collectives): agree once
+            ok = torch.tensor([1 if prep is not None else 0], dtype=torch.int64, device=dev)
+            if int(P.allreduce_(ok, "min").item()) == 0:
+                prep = None
+            elif bcast:
+                prep.group = P.build_group()
+        cache[key] = prep
+        if prep is not None:
+            src.__dict__["_prepared_last"] = ((P.world()[1], torch.cuda.current_device()), prep)
+            cls._live.append(prep)
+            while len(cls._live) > cls.MAX_LIVE:
+                cls._live.pop(0)
+        return prep
+
+    def __init__(self, src, fact, dim, fk_e, pk_e, ge, gexpr0, aggs, fpred, dpred, meta, owner, bcast, sharded, dev):
+        self.dev, self.owner, self.bcast, self.sharded = dev, owner, bcast, sharded
+        self.pmin, self.prange, self.gmin, self.grng, self.gnull = meta
+        self.nslots = self.grng + 1
+        self.gname = src.group_cols[0]
+        self.gexpr0 = gexpr0
+        self.glog = dim.col_type(gexpr0.name)[1] if isinstance(gexpr0, ColRef) else "int64"
+        self.plan = AggPlan([(E.substitute(e, fact.exprs) if e is not None else None, o, f) for e, o, f in aggs],
+                            _nullable_fn(fact))
+        if any(not isinstance(ka.expr, ColRef) for ka in self.plan.kaggs):
+            raise _NotPreparable()
+        # ---- launch descriptors (every referenced column must be resident and used as it is)
+        self.keep = []
+        self.dim_launch = []
+        if owner:
+            needed = {pk_e.name, ge.name}
+            for p in dpred:
+                p.refs(needed)
+            for part in self._resident_parts(dim.source.table, needed):
+                ctx = ScanCtx(part, dpred)
+                pk_slot, g_slot = ctx.slot(pk_e), ctx.slot(ge)
+                self._only_table_columns(ctx)
+                self.dim_launch.append((ctx.scan(), pk_slot, g_slot))
+                self.keep.append(ctx)
+        needed = set(fk_e.refs())
+        for ka in self.plan.kaggs:
+            ka.expr.refs(needed)
+        for p in fpred:
+            p.refs(needed)
+        self.fact_launch = []
+        for part in self._resident_parts(fact.source.table, needed):
+            ctx = ScanCtx(part, fpred)
+            fk_slot = ctx.slot(fk_e)
+            specs = [(ctx.slot(ka.expr), ka.op) for ka in self.plan.kaggs]
+            self._only_table_columns(ctx)
+            self.fact_launch.append((ctx.scan(), fk_slot, D.make_aggs(specs), len(specs), part.n))
+            self.keep.append(ctx)
+        # ---- reused device buffers
+        self.ring = [torch.empty(self.prange + 4, dtype=torch.int32, device=dev) for _ in range(2)]
+        self.lk = []
+        for buf in self.ring:
+            lk = L.StarLookup()
+            lk.dense, lk.lookup, lk.kmin, lk.range = 1, buf.data_ptr(), self.pmin, self.prange
+            self.lk.append(lk)
+        self.gs = GroupState(dev, self.nslots, self.plan, need_present=True, alloc=_padded_slots(self.nslots, sharded))
+        t = self.gs.table
+        self.refill = []          # (tensor, initial value) of every accumulator array
+        for a, acc in enumerate(t.acc):
+            if acc is not None:
+                self.refill.append((acc, float(acc[0].item()) if acc.dtype == torch.float64 else int(acc[0].item())))
+        for cnt in t.cnt:
+            if cnt is not None:
+                self.refill.append((cnt, 0))
+        if t.rows is not None:
+            self.refill.append((t.rows, 0))
+        if t.present is not None:
+            self.refill.append((t.present, 0))
+        self.dirty = False        # a fresh table is already initialised
+        self.group = None         # set by get() once all ranks agreed on the prepared path
+        self.build_stream = torch.cuda.Stream(device=dev)
+        self.build_ptr = C.c_void_p(self.build_stream.cuda_stream)
+        self.built = [torch.cuda.Event() for _ in range(2)]
+        self.free = [None, None]  # event after which ring buffer i may be overwritten
+        self.runs = 0
+
+    @staticmethod
+    def _resident_parts(table, needed):
+        parts = []
+        for p in table.partitions:
+            n = next(iter(p.values())).n if p else 0
+            if n == 0:
+                continue
+            cols = {}
+            for name in needed:
+                c = p[name]
+                if not isinstance(c, DeviceColumn):
+                    raise _NotPreparable()          # host-resident table: uploaded per query, classic path
+                cols[name] = c
+            parts.append(Part(cols, n))
+        return parts
+
+    @staticmethod
+    def _only_table_columns(ctx: "ScanCtx"):
+        if any(not k.startswith("col:") for k in ctx.index):
+            raise _NotPreparable()                  # computed inputs / mask predicates are evaluated per query
+
+    def run(self, src) -> Part:
+        i = self.runs & 1
+        self.runs += 1
+        buf = self.ring[i]
+        main = torch.cuda.current_stream()
+        bs = self.build_stream
+        # ---- build side on its own stream (phase events recorded there: they overlap the previous run's scan)
+        if self.free[i] is not None:
+            bs.wait_event(self.free[i])
+        with torch.cuda.stream(bs):
+            with _Phase("build"):
+                buf.fill_(-1)
+                buf[self.prange:].zero_()
+                for scan, pk_slot, g_slot in self.dim_launch:
+                    stats["launches"] += 1
+                    L.star_build_scan(C.byref(scan), pk_slot, g_slot, self.pmin, self.prange, self.gmin,
+                                      self.nslots - 1, C.c_void_p(buf.data_ptr()),
+                                      C.c_void_p(buf.data_ptr() + 4 * self.prange), self.build_ptr)
+            if self.bcast:
+                with _Phase("bcast"):
+                    P.broadcast_(buf, 0, group=self.group)
+            self.built[i].record(bs)
+        # ---- probe side on the caller's stream
+        with _Phase("wait_build"):
+            main.wait_event(self.built[i])
+        t = self.gs.table
+        with _Phase("scan"):
+            if self.dirty:
+                for tensor, value in self.refill:
+                    tensor.fill_(value)
+            self.dirty = True
+            sp = D.stream_ptr()
+            for scan, fk_slot, aggs_arr, naggs, n in self.fact_launch:
+                stats["launches"] += 1
+                ev = _kernel_event_begin("b2_star_agg_kernel", n)
+                L.star_agg(C.byref(scan), fk_slot, C.byref(self.lk[i]), aggs_arr, naggs, C.byref(t.state), sp)
+                _kernel_event_end(ev)
+        view = _merge_dense(t, self.plan, self.sharded, self.dev)
+        stats["star_fused"] += 1
+
+        def general():   # a duplicate build key showed up: the general path redoes the query
+            stats["star_fused"] -= 1
+            return run_aggregate(src, allow_fast=False)
+
+        out = _finalize_dense(view, self.gmin, self.gname, self.gexpr0, self.glog, self.plan, self.dev,
+                              key_nullable=self.gnull, check=buf[self.prange:], fallback=general)
+        done = torch.cuda.Event()
+        done.record(main)
+        self.free[i] = done
+        return out
+
+
+class _NotPreparable(Exception):
+    pass
+
+
 def _star_dense_fast(src, fact, dim, fk_e, pk_e, gexprs, aggs, fact_pred, dim_pred, sharded, dev) -> Optional[Part]:
     """Star pipeline when the dimension side is a registered table whose join key and (single)
     group key are dense int64 columns: b2_star_build_scan per dim partition, b2_star_agg per fact
@@ -1510,6 +1712,11 @@ def _star_dense_fast(src, fact, dim, fk_e, pk_e, gexprs, aggs, fact_pred, dim_pr
     if never or fnever:
         return None
     nslots = grng + 1
+    if os.environ.get("B200SQL_NO_PREPARED") != "1":
+        prep = PreparedStar.get(src, fact, dim, fk_e, pk_e, ge, gexprs[0], aggs, fpred, dpred,
+                                (pmin, prange, gmin, grng, gnull), owner, world > 1 and dist == "root", sharded, dev)
+        if prep is not None:
+            return prep.run(src)
     # lookup and the 4 flag words share one buffer: one broadcast carries both
     buf = torch.full((prange + 4,), -1, dtype=torch.int32, device=dev)
     lookup, flags = buf[:prange], buf[prange:]

@@ -13,9 +13,19 @@ import torch
 import torch.distributed as dist
 
 
+_WORLD = None        # (rank, size, backend) once a process group exists: asked dozens of times per query
+
+
 def world() -> Tuple[int, int]:
+    global _WORLD
+    if _WORLD is not None:
+        if dist.is_initialized():
+            return _WORLD[0], _WORLD[1]
+        _WORLD = None                      # the group was destroyed
+        globals()["_BUILD_GROUP"] = None
     if dist.is_available() and dist.is_initialized():
-        return dist.get_rank(), dist.get_world_size()
+        _WORLD = (dist.get_rank(), dist.get_world_size(), dist.get_backend())
+        return _WORLD[0], _WORLD[1]
     return 0, 1
 
 
@@ -38,7 +48,7 @@ def allreduce_(t: torch.Tensor, op: str = "sum") -> torch.Tensor:
 
 
 def _backend() -> str:
-    return dist.get_backend() if world()[1] > 1 else "none"
+    return _WORLD[2] if world()[1] > 1 else "none"
 
 
 def reduce_scatter_(t: torch.Tensor, op: str = "sum") -> torch.Tensor:
@@ -98,9 +108,23 @@ def all_gather_ints(values: Sequence[int], device) -> List[List[int]]:
     return torch.stack(bufs).cpu().tolist()
 
 
-def broadcast_(t: torch.Tensor, src: int = 0) -> torch.Tensor:
+_BUILD_GROUP = None
+
+
+def build_group():
+    """A second communicator over the same ranks, used only for build-side broadcasts.  Collectives of
+    ONE communicator execute in issue order on its stream; with its own communicator the next query's
+    lookup broadcast does not queue behind the current query's reduce-scatter (which waits for the
+    fact scan) and really overlaps that scan.  Created on first use (a collective call)."""
+    global _BUILD_GROUP
+    if _BUILD_GROUP is None and world()[1] > 1:
+        _BUILD_GROUP = dist.new_group(backend=_WORLD[2])
+    return _BUILD_GROUP
+
+
+def broadcast_(t: torch.Tensor, src: int = 0, group=None) -> torch.Tensor:
     if world()[1] > 1:
-        dist.broadcast(t, src=src)
+        dist.broadcast(t, src=src, group=group)
     return t
 
 

@@ -599,3 +599,36 @@ def test_uniform_keys_keep_the_per_row_atomic_kernel():
     got = agg(_table(df, 2), ["key"], [("v", "sv", "sum")])
     assert executor.stats.get("grouped_groupby", 0) == before
     assert_frames(got, df.groupby("key").agg(sv=("v", "sum")).reset_index(), float_cols=("sv",), sort_by=["key"])
+
+
+@pytest.mark.parametrize("pcol,bcol,op", [("v", "w", "*"), ("v", "big", "+"), ("q", "w", "*"), ("q", "r", "-"),
+                                          ("v", "r", "*"), ("q", "big", "-")])
+def test_join_agg_single_sum_fast_path(pcol, bcol, op, monkeypatch):
+    """SUM(P o B) alone takes the specialised kernel: float / int probe column x payload stored as uint32
+    with the absent-key sentinel, wide int64, float64; NaNs on either side are skipped; a probe filter."""
+    from dask_sql_b200 import Context, executor
+    rng = np.random.default_rng(33)
+    nd, nf = 30_000, 300_017
+    dim = pd.DataFrame({"pk": rng.permutation(nd * 2)[:nd] - 100, "w": rng.integers(0, 5000, nd),
+                        "big": rng.integers(-2**40, 2**40, nd),
+                        "r": np.where(rng.random(nd) < 0.05, np.nan, rng.random(nd) * 10)})
+    fact = pd.DataFrame({"fk": rng.integers(-500, nd * 2 + 300, nf),
+                         "v": np.where(rng.random(nf) < 0.03, np.nan, rng.random(nf)),
+                         "q": rng.integers(-50, 50, nf), "x": rng.integers(-100, 100, nf)})
+    c = Context()
+    c.create_table("fact", fact, npartitions=3, persist=True)
+    c.create_table("dim", dim, persist=True)
+    lhs, rhs = (f"d.{bcol}", f"f.{pcol}") if (op == "-" and bcol == "big") else (f"f.{pcol}", f"d.{bcol}")
+    q = f"SELECT SUM({lhs} {op} {rhs}) AS s FROM fact f JOIN dim d ON f.fk = d.pk WHERE f.x > -60"
+    j = fact[fact.x > -60].merge(dim, left_on="fk", right_on="pk")
+    a, b = (j[bcol], j[pcol]) if lhs.startswith("d.") else (j[pcol], j[bcol])
+    exp = {"*": a * b, "+": a + b, "-": a - b}[op].sum()
+    before = executor.stats.get("join_agg", 0)
+    got = c.sql(q, return_futures=False)
+    assert executor.stats.get("join_agg", 0) == before + 1
+    monkeypatch.setenv("B200SQL_JA_GENERIC", "1")
+    generic = c.sql(q, return_futures=False)
+    if np.issubdtype(type(exp), np.integer) or isinstance(exp, (int, np.integer)):
+        assert int(got.s[0]) == int(exp) == int(generic.s[0])
+    else:
+        np.testing.assert_allclose([float(got.s[0]), float(generic.s[0])], [exp, exp], rtol=RTOL)
