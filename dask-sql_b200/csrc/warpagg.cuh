@@ -300,7 +300,7 @@ __device__ __forceinline__ void b2_hot_flush(const b2_hot_t& hot, const b2_hot_s
 // folds its 256 partials per (hitter, array) and issues ONE global atomic each.
 // =====================================================================================================
 #define B2_HH_MAX 32          // heavy hitters tracked (top of the sample)
-#define B2_HH_MAP 128         // open-addressing slot -> hitter index map in shared memory (power of two)
+#define B2_HH_MAP 512         // single-probe slot -> hitter index map in shared memory (power of two)
 #define B2_HH_SAMPLE 32768    // rows sampled by the pre-pass
 #define B2_HH_COUNTERS 4096   // counters of the pre-pass (power of two)
 #define B2_HH_MIN_COUNT 6     // sample occurrences that make a slot a heavy hitter (share >~ 0.02 %)
@@ -358,10 +358,9 @@ b2_hot_slots_kernel(const __grid_constant__ b2_col_t key, int64_t n, int64_t kmi
 }
 
 struct b2_hh_smem {
-  int32_t* map_slot;     // [B2_HH_MAP]  slot or -1
-  int32_t* map_idx;      // [B2_HH_MAP]
+  int2* map;             // [B2_HH_MAP]  {slot or -1, hitter index}: ONE probe decides
   int64_t* part;         // [narrays][nh][B2_BLOCK] thread-private partials
-  int nh;                // hitters actually tracked (<= hot.nh_cap)
+  int nh;                // hitters the shared memory budget tracks
 };
 
 // hitters the shared memory budget allows: 64 KB / (arrays x 256 threads x 8 B)
@@ -374,13 +373,14 @@ static inline size_t b2_hh_smem_bytes(int narrays) {
   return (size_t)B2_HH_MAP * 8 + (size_t)narrays * b2_hh_capacity(narrays) * B2_BLOCK * 8;
 }
 
+__device__ __forceinline__ uint32_t b2_hh_bucket(int32_t slot) { return (b2_hh_hash(slot) >> 16) & (B2_HH_MAP - 1); }
+
 __device__ __forceinline__ b2_hh_smem b2_hh_init(const b2_hot_t& hot, const int32_t* __restrict__ d_hot, int cap,
                                                  uint8_t* smem) {
   b2_hh_smem hs;
   hs.part = reinterpret_cast<int64_t*>(smem);
-  hs.map_slot = reinterpret_cast<int32_t*>(smem + (size_t)hot.narrays * cap * B2_BLOCK * 8);
-  hs.map_idx = hs.map_slot + B2_HH_MAP;
-  for (int i = threadIdx.x; i < B2_HH_MAP; i += blockDim.x) hs.map_slot[i] = -1;
+  hs.map = reinterpret_cast<int2*>(smem + (size_t)hot.narrays * cap * B2_BLOCK * 8);
+  for (int i = threadIdx.x; i < B2_HH_MAP; i += blockDim.x) hs.map[i] = make_int2(-1, -1);
   // float partials start at -0.0 (the INT64_MIN bit pattern) and only ever receive x + 0.0: a partial that
   // still reads -0.0 saw no row, -0.0 + -0.0 = -0.0 survives the fold, and anything else (+0.0 included)
   // means "this CTA met the hitter" -- the same convention as the global accumulators' existence mark
@@ -388,13 +388,12 @@ __device__ __forceinline__ b2_hh_smem b2_hh_init(const b2_hot_t& hot, const int3
     hs.part[i] = hot.is_f64[i / (cap * B2_BLOCK)] ? (int64_t)0x8000000000000000LL : 0;
   __syncthreads();
   if (threadIdx.x == 0) {
+    // most frequent first; a hitter whose bucket is taken is simply not tracked (its rows take atomics)
     for (int k = 0; k < cap; ++k) {
       const int32_t slot = d_hot[k];
       if (slot < 0) break;
-      uint32_t h = (b2_hh_hash(slot) >> 24) & (B2_HH_MAP - 1);
-      while (hs.map_slot[h] != -1) h = (h + 1) & (B2_HH_MAP - 1);
-      hs.map_slot[h] = slot;
-      hs.map_idx[h] = k;
+      const uint32_t h = b2_hh_bucket(slot);
+      if (hs.map[h].x == -1) hs.map[h] = make_int2(slot, k);
     }
   }
   __syncthreads();
@@ -403,14 +402,36 @@ __device__ __forceinline__ b2_hh_smem b2_hh_init(const b2_hot_t& hot, const int3
 }
 
 __device__ __forceinline__ int b2_hh_find(const b2_hh_smem& hs, int64_t slot) {
-  if (slot < 0) return -1;
-  uint32_t h = (b2_hh_hash((int32_t)slot) >> 24) & (B2_HH_MAP - 1);
-  for (int probe = 0; probe < B2_HH_MAP; ++probe, h = (h + 1) & (B2_HH_MAP - 1)) {
-    const int32_t t = hs.map_slot[h];
-    if (t == (int32_t)slot) return hs.map_idx[h];
-    if (t == -1) return -1;
+  const int2 e = hs.map[b2_hh_bucket((int32_t)slot)];
+  return (slot >= 0 && e.x == (int32_t)slot) ? e.y : -1;
+}
+
+// one aggregate's batch: rows of tracked hitters go to the thread's partial, the rest to global atomics
+template <int R, int KIND>
+__device__ __forceinline__ void b2_hh_batch(void* acc, int64_t* cnt, const int64_t (&slot)[R], const int64_t (&raw)[R],
+                                            uint32_t ok, const int8_t (&hit)[R], int64_t* part_acc, int64_t* part_cnt,
+                                            int stride) {
+  // part_acc / part_cnt: this thread's partial of hitter 0 for the array (NULL = array not carried);
+  // hitter h's partial is `stride` words further per index
+#pragma unroll
+  for (int j = 0; j < R; ++j) {
+    if (!((ok >> j) & 1)) continue;
+    const int h = hit[j];
+    if (cnt) {
+      if (h >= 0 && part_cnt) part_cnt[h * stride] += 1;
+      else atomicAdd(reinterpret_cast<unsigned long long*>(cnt) + slot[j], 1ULL);
+    }
+    if (KIND == B2_K_NONE) continue;
+    if (h >= 0 && part_acc && (KIND == B2_K_SUM_I || KIND == B2_K_SUM_F || KIND == B2_K_SUMF_I)) {
+      int64_t* p = part_acc + h * stride;
+      if (KIND == B2_K_SUM_I) *p = (int64_t)((uint64_t)*p + (uint64_t)raw[j]);
+      else if (KIND == B2_K_SUM_F)
+        *p = __double_as_longlong(__longlong_as_double(*p) + __dadd_rn(__longlong_as_double(raw[j]), 0.0));
+      else *p = __double_as_longlong(__longlong_as_double(*p) + __dadd_rn((double)raw[j], 0.0));
+    } else {
+      b2_atomic_k<KIND>(acc, slot[j], raw[j]);
+    }
   }
-  return -1;
 }
 
 // b2_apply_aggs with the heavy hitters' rows diverted to the thread-private partials
@@ -420,8 +441,9 @@ __device__ __forceinline__ void b2_apply_aggs_hh(const b2_scan_t& s, const LD& l
                                                  const b2_hot_t& hot, const b2_hh_smem& hs) {
   const int64_t row0 = ld.row0;
   const int tid = threadIdx.x;
+  const int stride = B2_BLOCK;           // words between the partials of consecutive hitters
   uint32_t live = 0;
-  int8_t hit[R];                      // index of the heavy hitter this row belongs to, -1 = none
+  int8_t hit[R];                         // index of the tracked heavy hitter this row belongs to, -1 = none
 #pragma unroll
   for (int j = 0; j < R; ++j) {
     live |= (uint32_t)(slot[j] >= 0) << j;
@@ -433,10 +455,11 @@ __device__ __forceinline__ void b2_apply_aggs_hh(const b2_scan_t& s, const LD& l
       if (row0 + (int64_t)j * 32 < s.n) st.out_slot[row0 + (int64_t)j * 32] = (int32_t)slot[j];
   }
   if (st.rows) {
+    int64_t* pr = hot.rows_arr >= 0 ? hs.part + (size_t)hot.rows_arr * hs.nh * stride + tid : nullptr;
 #pragma unroll
     for (int j = 0; j < R; ++j) {
       if (!((live >> j) & 1)) continue;
-      if (hit[j] >= 0 && hot.rows_arr >= 0) hs.part[((size_t)hot.rows_arr * hs.nh + hit[j]) * B2_BLOCK + tid] += 1;
+      if (hit[j] >= 0 && pr) pr[hit[j] * stride] += 1;
       else atomicAdd(reinterpret_cast<unsigned long long*>(st.rows) + slot[j], 1ULL);
     }
   }
@@ -458,34 +481,17 @@ __device__ __forceinline__ void b2_apply_aggs_hh(const b2_scan_t& s, const LD& l
     if (c.valid || c.dtype == B2_F64) ok &= ~b2_null_bits<R>(c, row0, live, raw);
     void* acc = st.acc[a];
     int64_t* cnt = st.cnt[a];
-    const int kind = acc ? b2_agg_kind(ag.op, c.dtype) : B2_K_NONE;
-    const int acc_arr = hot.acc_arr[a], cnt_arr = hot.cnt_arr[a];
-#pragma unroll
-    for (int j = 0; j < R; ++j) {
-      if (!((ok >> j) & 1)) continue;
-      const bool h = hit[j] >= 0;
-      if (cnt) {
-        if (h && cnt_arr >= 0) hs.part[((size_t)cnt_arr * hs.nh + hit[j]) * B2_BLOCK + tid] += 1;
-        else atomicAdd(reinterpret_cast<unsigned long long*>(cnt) + slot[j], 1ULL);
-      }
-      if (kind == B2_K_NONE) continue;
-      if (h && acc_arr >= 0) {
-        int64_t* p = hs.part + ((size_t)acc_arr * hs.nh + hit[j]) * B2_BLOCK + tid;
-        if (kind == B2_K_SUM_I) *p = (int64_t)((uint64_t)*p + (uint64_t)raw[j]);
-        else if (kind == B2_K_SUM_F)
-          *p = __double_as_longlong(__longlong_as_double(*p) + __dadd_rn(__longlong_as_double(raw[j]), 0.0));
-        else *p = __double_as_longlong(__longlong_as_double(*p) + __dadd_rn((double)raw[j], 0.0));     // B2_K_SUMF_I
-      } else {
-        switch (kind) {
-          case B2_K_SUM_I: b2_atomic_k<B2_K_SUM_I>(acc, slot[j], raw[j]); break;
-          case B2_K_SUM_F: b2_atomic_k<B2_K_SUM_F>(acc, slot[j], raw[j]); break;
-          case B2_K_SUMF_I: b2_atomic_k<B2_K_SUMF_I>(acc, slot[j], raw[j]); break;
-          case B2_K_MIN_I: b2_atomic_k<B2_K_MIN_I>(acc, slot[j], raw[j]); break;
-          case B2_K_MAX_I: b2_atomic_k<B2_K_MAX_I>(acc, slot[j], raw[j]); break;
-          case B2_K_MIN_F: b2_atomic_k<B2_K_MIN_F>(acc, slot[j], raw[j]); break;
-          default: b2_atomic_k<B2_K_MAX_F>(acc, slot[j], raw[j]); break;
-        }
-      }
+    int64_t* pa = hot.acc_arr[a] >= 0 ? hs.part + (size_t)hot.acc_arr[a] * hs.nh * stride + tid : nullptr;
+    int64_t* pc = hot.cnt_arr[a] >= 0 ? hs.part + (size_t)hot.cnt_arr[a] * hs.nh * stride + tid : nullptr;
+    switch (acc ? b2_agg_kind(ag.op, c.dtype) : B2_K_NONE) {
+      case B2_K_SUM_I: b2_hh_batch<R, B2_K_SUM_I>(acc, cnt, slot, raw, ok, hit, pa, pc, stride); break;
+      case B2_K_SUM_F: b2_hh_batch<R, B2_K_SUM_F>(acc, cnt, slot, raw, ok, hit, pa, pc, stride); break;
+      case B2_K_SUMF_I: b2_hh_batch<R, B2_K_SUMF_I>(acc, cnt, slot, raw, ok, hit, pa, pc, stride); break;
+      case B2_K_MIN_I: b2_hh_batch<R, B2_K_MIN_I>(acc, cnt, slot, raw, ok, hit, pa, pc, stride); break;
+      case B2_K_MAX_I: b2_hh_batch<R, B2_K_MAX_I>(acc, cnt, slot, raw, ok, hit, pa, pc, stride); break;
+      case B2_K_MIN_F: b2_hh_batch<R, B2_K_MIN_F>(acc, cnt, slot, raw, ok, hit, pa, pc, stride); break;
+      case B2_K_MAX_F: b2_hh_batch<R, B2_K_MAX_F>(acc, cnt, slot, raw, ok, hit, pa, pc, stride); break;
+      default: b2_hh_batch<R, B2_K_NONE>(acc, cnt, slot, raw, ok, hit, pa, pc, stride); break;
     }
   }
 }
