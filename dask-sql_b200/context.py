@@ -77,6 +77,18 @@ class Context:
         schema_name = schema_name or self.schema_name
         npartitions = kwargs.pop("npartitions", 1)
         distribution = kwargs.pop("distribution", "local")
+        filepath = None
+        if isinstance(input_table, str) and not persist:
+            import os
+            from .table import ParquetTable, location_format
+            if location_format(input_table, format) == "parquet" and os.path.isfile(input_table):
+                # persist=False ('the data will be lazily loaded'): row groups become partitions, read per
+                # query and pruned by the pushed-down filters (table_scan.py:80-99, physical/utils/filter.py)
+                kwargs.pop("gpu", None)
+                filepath = input_table
+                input_table = ParquetTable(input_table, distribution, table_name, kwargs.pop("columns", None))
+                if kwargs:
+                    raise TypeError(f"unsupported options for reading {filepath!r}: {sorted(kwargs)}")
         if isinstance(input_table, LazyFrame):
             df = input_table.persist() if persist else input_table
         else:
@@ -106,8 +118,11 @@ class Context:
         if not statistics:
             statistics = Statistics(float("nan"))
         dc.statistics = statistics
+        dc.filepath = filepath
         self.schema[schema_name].tables[table_name.lower()] = dc
         self.schema[schema_name].statistics[table_name.lower()] = statistics
+        if filepath is not None:
+            self.schema[schema_name].filepaths[table_name.lower()] = filepath
         self._catalog_version += 1
 
     def drop_table(self, table_name: str, schema_name: str = None):

@@ -340,7 +340,7 @@ def _split_out(src: Source) -> int:
 
 def source_npartitions(src: Source) -> int:
     if isinstance(src, TableSource):
-        return len(src.table.partitions)
+        return src.table.npartitions
     if isinstance(src, JoinSource):
         return max(source_npartitions(src.left.source), source_npartitions(src.right.source))
     if isinstance(src, AggSource):
@@ -439,14 +439,33 @@ def gather_keyrange(part: Part) -> Part:
     return out
 
 
-def materialize(src: Source, needed: Set[str], top: bool = False) -> List[Part]:
+def _pushdown_terms(pred) -> list:
+    """the `column <cmp> literal` conjuncts of a pushed-down predicate as (column, B2 op, literal)"""
+    out = []
+    for c in pred or ():
+        t = E.as_term(c)
+        if t is not None:
+            out.append(t)
+    return out
+
+
+def materialize(src: Source, needed: Set[str], top: bool = False, pred=None) -> List[Part]:
     """top: the caller is the outermost frame of a query -- a multi-GPU aggregate may then stay
     sharded by key range (one slice of the groups per rank, the dask result with split_out = world
     size); any operator stacked on top of an aggregate needs all groups and gets them gathered."""
     if isinstance(src, TableSource):
         dev = _dev()
         parts = []
-        for p in src.table.partitions:
+        table = src.table
+        if hasattr(table, "scan_pruned"):
+            # lazy Parquet table: only the referenced columns of the row groups whose statistics admit
+            # a row passing the pushed-down conjuncts (conservative: the kernels still filter every row)
+            before = table.stats["row_groups_skipped"]
+            table_parts = table.scan_pruned(needed, _pushdown_terms(pred))
+            stats["rowgroups_skipped"] = stats.get("rowgroups_skipped", 0) + table.stats["row_groups_skipped"] - before
+        else:
+            table_parts = table.partitions
+        for p in table_parts:
             n = next(iter(p.values())).n if p else 0
             cols = {}
             for name in needed:
@@ -542,7 +561,7 @@ def execute(frame: LazyFrame, needed: Optional[Sequence[str]] = None, top: bool 
         e.refs(src_needed)
     for p in pred:
         p.refs(src_needed)
-    parts = materialize(frame.source, src_needed, top)
+    parts = materialize(frame.source, src_needed, top, pred)
 
     def project(part: Part) -> Part:
         dist = part.dist
@@ -673,9 +692,11 @@ def _nullable_fn(child: LazyFrame):
             return e.value is None
         if isinstance(e, ColRef) and isinstance(src, TableSource):
             t = src.table
-            has_bitmap = any(p[e.name].valid is not None for p in t.partitions)
+            has_bitmap = t.column_nullable(e.name)
             if e.dtype != F64:
                 return has_bitmap
+            if hasattr(t, "scan_pruned"):
+                return True          # lazy Parquet: NaNs are not in the file's null counts; keep the count
             # NaN is NULL for float inputs: whether a count must be kept next to the sum depends on
             # the data.  One statistics pass per resident column (cached) saves an atomic per row
             # on every later query; host-resident columns are not uploaded twice for this.
@@ -749,7 +770,7 @@ def run_aggregate(src: AggSource, allow_fast=True) -> Part:
             e.refs(needed)
     for p in pred:
         p.refs(needed)
-    parts = [] if never else materialize(child.source, needed)
+    parts = [] if never else materialize(child.source, needed, pred=pred)
     plan = AggPlan(aggs, _nullable_fn(child), _moment_shifts(aggs, parts, child, sharded))
     if not gexprs:
         return global_aggregate(parts, pred, plan, sharded)
@@ -1689,7 +1710,7 @@ def _star_dense_fast(src, fact, dim, fk_e, pk_e, gexprs, aggs, fact_pred, dim_pr
     meta = None
     if owner:
         pst, gst = table.column_stats(pk_e.name), table.column_stats(ge.name)
-        gnull = any(p[ge.name].valid is not None for p in table.partitions)
+        gnull = table.column_nullable(ge.name)
         meta = (pst.vmin, pst.vmax, gst.vmin, gst.vmax, table.nrows, gnull)
     if world > 1 and dist == "root":
         # key ranges of the root-only table: one object broadcast per (table, columns), then cached on
@@ -1749,7 +1770,7 @@ def _star_dense_fast(src, fact, dim, fk_e, pk_e, gexprs, aggs, fact_pred, dim_pr
     for p in fpred:
         p.refs(needed)
     with _Phase("scan"):
-        for part in materialize(fact.source, needed):
+        for part in materialize(fact.source, needed, pred=fpred):
             if part.n == 0:
                 continue
             ctx = ScanCtx(part, fpred)
@@ -1911,7 +1932,7 @@ def try_star(src: AggSource, child: LazyFrame, gexprs, aggs, pred, sharded, allo
             ka.expr.refs(needed)
         for p in fpred:
             p.refs(needed)
-        fparts = materialize(fact.source, needed)
+        fparts = materialize(fact.source, needed, pred=fpred)
     for part in fparts:
         if part.n == 0:
             continue
@@ -2058,7 +2079,7 @@ def try_join_agg(src: AggSource, child: LazyFrame, aggs, pred, sharded) -> Optio
         p.refs(needed)
     first = True
     float_acc = [False] * k
-    for part in ([] if never else materialize(probe.source, needed)):
+    for part in ([] if never else materialize(probe.source, needed, pred=ppred)):
         if part.n == 0:
             continue
         ctx = ScanCtx(part, ppred)
@@ -2163,7 +2184,7 @@ def run_join(js: JoinSource, needed: Set[str]) -> List[Part]:
         e.refs(src_needed)
     for p in ppred:
         p.refs(src_needed)
-    pparts = [] if never else materialize(probe.source, src_needed)
+    pparts = [] if never else materialize(probe.source, src_needed, pred=ppred)
     outs: List[Part] = []
     for part in pparts:
         if part.n == 0:

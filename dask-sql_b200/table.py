@@ -128,6 +128,13 @@ def arrow_columns(table) -> Dict[str, ArrowColumn]:
     return out
 
 
+def location_format(location: str, format: Optional[str] = None) -> str:
+    import os
+    if format is None:
+        format = os.path.splitext(location.rstrip("/"))[1].lstrip(".").lower() or "parquet"
+    return format.lower()
+
+
 def read_location(location: str, format: Optional[str] = None, **kwargs):
     """Parquet / CSV file (or directory of Parquet files) -> pyarrow.Table
     (the reference: input_utils/location.py:27-54, dd.read_<format>(location, **kwargs))."""
@@ -227,6 +234,14 @@ class DeviceTable:
     def nrows(self):
         return sum(next(iter(p.values())).n if p else 0 for p in self.partitions)
 
+    @property
+    def npartitions(self):
+        return len(self.partitions)
+
+    def column_nullable(self, name) -> bool:
+        """does any partition of the column carry a validity bitmap?"""
+        return any(p[name].valid is not None for p in self.partitions)
+
     def nbytes(self):
         return sum(c.nbytes() for p in self.partitions for c in p.values())
 
@@ -288,3 +303,162 @@ class DeviceTable:
     def from_pandas(cls, df, npartitions=1, device=None, persist=True, distribution="local", name=None):
         return cls.from_columns({str(c): df[c] for c in df.columns}, npartitions, device, persist,
                                 distribution, name)
+
+
+# ---------------------------------------------------------------------------------------------
+# lazy Parquet tables: row groups as partitions, pruned by the pushed-down predicate
+# ---------------------------------------------------------------------------------------------
+_PRUNE = None
+
+
+def _prune_rule():
+    """(term op) -> function(stats, literal) -> True when NO row of the row group can satisfy the term."""
+    global _PRUNE
+    if _PRUNE is None:
+        from . import _lib as L
+        _PRUNE = {
+            L.EQ: lambda s, v: v < s["min"] or v > s["max"],
+            L.LT: lambda s, v: s["min"] >= v,
+            L.LE: lambda s, v: s["min"] > v,
+            L.GT: lambda s, v: s["max"] <= v,
+            L.GE: lambda s, v: s["max"] < v,
+            L.IS_NULL: lambda s, v: s["nulls"] == 0,
+            L.IS_NOT_NULL: lambda s, v: s["nulls"] == s["rows"],
+        }
+    return _PRUNE
+
+
+class ParquetTable(DeviceTable):
+    """A Parquet file registered with persist=False: nothing is read at create_table.  A query reads only
+    the columns it references and only the row groups whose min/max/null-count statistics admit a row
+    passing the pushed-down `column <cmp> literal` conjuncts -- the reference's predicate pushdown
+    (physical/utils/filter.py:17 attempt_predicate_pushdown regenerates dd.read_parquet(filters=...) from
+    TableScan.getDNFFilters(), table_scan.py:80-99).  Each surviving row group is one partition: Arrow
+    buffers -> pinned host columns -> H2D, the kernels then apply the predicate row by row as always, so
+    pruning is conservative and can only skip IO.  Decoded column chunks are kept (host memory) for the
+    next query, like an OS page cache; `stats` tells how many row groups each scan skipped."""
+
+    def __init__(self, location: str, distribution="local", name=None, columns=None):
+        import pyarrow.parquet as pq
+        self.location = location
+        self.file = pq.ParquetFile(location)
+        md = self.file.metadata
+        names = [self.file.schema_arrow.names[i] for i in range(len(self.file.schema_arrow.names))]
+        self._names = [n for n in names if columns is None or n in columns]
+        self._nrows = md.num_rows
+        self._groups = []                       # per row group: {"rows": n, "cols": {name: {"min","max","nulls","rows"} | None}}
+        for g in range(md.num_row_groups):
+            rg = md.row_group(g)
+            cols = {}
+            for c in range(rg.num_columns):
+                col = rg.column(c)
+                st = col.statistics
+                nm = col.path_in_schema
+                if st is not None and st.has_min_max and st.has_null_count:
+                    cols[nm] = {"min": st.min, "max": st.max, "nulls": st.null_count, "rows": rg.num_rows}
+                else:
+                    cols[nm] = None
+            self._groups.append({"rows": rg.num_rows, "cols": cols})
+        self._cache = {}                        # (row group, column) -> HostColumn
+        self.stats = {"scans": 0, "row_groups_read": 0, "row_groups_skipped": 0}
+        self.distribution = distribution
+        self.name = name
+        self._schema = None
+        self._proto = None
+
+    # -- metadata without touching the data pages
+    def _prototype(self):
+        """zero-row host columns: they carry every column's physical / logical type"""
+        if self._proto is None:
+            empty = self.file.schema_arrow.empty_table().select(self._names)
+            self._proto = {n: _host_column(c, pin=False) for n, c in arrow_columns(empty).items()}
+        return self._proto
+
+    def schema(self):
+        if self._schema is None:
+            out = []
+            for n, c in self._prototype().items():
+                lg = c.logical
+                if self.column_nullable(n):      # the chunks that hold NULLs arrive as pandas nullable dtypes
+                    if lg.startswith(("int", "uint")):
+                        lg = (lg[0].upper() + lg[1:]).replace("Uint", "UInt")
+                    elif lg == "bool":
+                        lg = "boolean"
+                out.append((n, c.dtype, lg))
+            self._schema = out
+        return self._schema
+
+    @property
+    def nrows(self):
+        return self._nrows
+
+    def is_resident(self):
+        return False
+
+    @property
+    def npartitions(self):
+        return max(1, len(self._groups))
+
+    def column_nullable(self, name) -> bool:
+        sts = [g["cols"].get(name) for g in self._groups]
+        return any(s is None or s["nulls"] > 0 for s in sts)
+
+    def column_stats(self, name) -> Stats:
+        """from the file's row-group statistics when every row group carries them, else from the data"""
+        sts = [g["cols"].get(name) for g in self._groups]
+        dt = dict((n, d) for n, d, _ in self.schema())[name]
+        if sts and all(s is not None for s in sts) and dt != F64:       # float NaNs are not in Parquet null counts
+            lo, hi = min(s["min"] for s in sts), max(s["max"] for s in sts)
+            return Stats(int(lo), int(hi), sum(s["nulls"] for s in sts), 0.0)
+        return super().column_stats(name)
+
+    # -- data
+    def _column(self, g: int, name: str) -> HostColumn:
+        key = (g, name)
+        if key not in self._cache:
+            t = self.file.read_row_group(g, columns=[name])
+            self._cache[key] = _host_column(arrow_columns(t)[name], pin=torch.cuda.is_available())
+        return self._cache[key]
+
+    @property
+    def partitions(self):
+        """every row group, every column (generic callers; scans go through scan_pruned)"""
+        return [{n: self._column(g, n) for n in self._names} for g in range(len(self._groups))] or [dict(self._prototype())]
+
+    @partitions.setter
+    def partitions(self, value):          # DeviceTable.__init__ is not used; nothing to set
+        pass
+
+    def surviving_groups(self, terms):
+        """row groups that may hold a row passing all `terms` = [(column, B2 op, literal)]"""
+        rules = _prune_rule()
+        keep = []
+        for g, info in enumerate(self._groups):
+            dead = False
+            for name, op, lit in terms:
+                st = info["cols"].get(name)
+                rule = rules.get(op)
+                if st is None or rule is None:
+                    continue
+                try:
+                    if rule(st, lit):
+                        dead = True
+                        break
+                except TypeError:               # statistics of a type that does not compare with the literal
+                    continue
+            if not dead:
+                keep.append(g)
+        return keep
+
+    def scan_pruned(self, needed, terms):
+        """[{column: HostColumn}] for the row groups that survive `terms`, restricted to `needed`"""
+        keep = self.surviving_groups(terms)
+        self.stats["scans"] += 1
+        self.stats["row_groups_read"] += len(keep)
+        self.stats["row_groups_skipped"] += len(self._groups) - len(keep)
+        cols = [n for n in self._names if n in needed]
+        parts = [{n: self._column(g, n) for n in cols} for g in keep if self._groups[g]["rows"] > 0]
+        if not parts:
+            proto = self._prototype()
+            parts = [{n: proto[n] for n in cols}]
+        return parts

@@ -410,3 +410,41 @@ def test_partition_plan_heuristics(monkeypatch):
     assert X._partition_plan(100_000_001, plan, boolean, 500_000_000) is None
     monkeypatch.setenv("B200SQL_NO_PARTITION", "1")
     assert X._partition_plan(100_000_001, plan, work, 500_000_000) is None
+
+
+def test_lazy_parquet_table_prunes_row_groups(tmp_path):
+    """persist=False Parquet tables read per query: only referenced columns, only the row groups whose
+    min/max/null-count statistics admit the pushed-down conjuncts (physical/utils/filter.py:17,
+    table_scan.py:80-99).  Host-side logic only: which row groups survive, what schema is reported."""
+    import pyarrow as pa
+    import pyarrow.parquet as pq
+    from dask_sql_b200 import Context, _lib as L
+    from dask_sql_b200.table import ParquetTable
+    n = 10_000
+    rng = np.random.default_rng(0)
+    df = pd.DataFrame({"a": np.arange(n), "b": rng.random(n),
+                       "c": pd.array(np.where(np.arange(n) % 7 == 0, None, np.arange(n) % 50), dtype="Int64")})
+    path = str(tmp_path / "t.parquet")
+    pq.write_table(pa.Table.from_pandas(df), path, row_group_size=1000)
+    t = ParquetTable(path)
+    assert (t.nrows, t.npartitions) == (n, 10) and not t._cache           # nothing read yet
+    assert [(nm, lg) for nm, _, lg in t.schema()] == [("a", "int64"), ("b", "float64"), ("c", "Int64")]
+    st = t.column_stats("a")
+    assert (st.vmin, st.vmax, st.nulls) == (0, n - 1, 0) and not t._cache   # from the footer, not the pages
+    assert t.surviving_groups([("a", L.GT, 8500)]) == [8, 9]
+    assert t.surviving_groups([("a", L.LT, 1000)]) == [0]
+    assert t.surviving_groups([("a", L.EQ, 4242), ("b", L.GT, 0.0)]) == [4]
+    assert t.surviving_groups([("c", L.GE, 50)]) == []                   # c < 50 everywhere
+    assert len(t.surviving_groups([("c", L.IS_NULL, 0)])) == 10
+    parts = t.scan_pruned({"a", "b"}, [("a", L.GE, 9000)])
+    assert len(parts) == 1 and set(parts[0]) == {"a", "b"} and parts[0]["a"].n == 1000
+    assert t.stats["row_groups_skipped"] == 9 and set(k[1] for k in t._cache) == {"a", "b"}
+    parts = t.scan_pruned({"a"}, [("a", L.GT, 10**9)])                  # nothing survives: one empty partition
+    assert len(parts) == 1 and parts[0]["a"].n == 0
+    # registration is lazy and keeps the location (the reference stores it in DataContainer.filepath)
+    c = Context()
+    c.create_table("t", path)
+    dc = c.schema[c.schema_name].tables["t"]
+    assert dc.filepath == path and isinstance(dc.df.source.table, ParquetTable) and dc.df.npartitions == 10
+    lazy = c.sql("SELECT SUM(b) AS s FROM t WHERE a >= 9000 AND c > 3")
+    assert [repr(p) for p in lazy.source.child.pred][:1]                 # the filter reached the scan

@@ -428,3 +428,34 @@ def test_parquet_and_csv_locations_and_ddl(c, tmp_path):
         c.sql("SELECT * FROM agg")
     with pytest.raises(AttributeError):
         c.sql("CREATE TABLE nope WITH (format = 'parquet')")                    # location is mandatory
+
+
+def test_lazy_parquet_pushdown_end_to_end(c, tmp_path):
+    """Queries over a persist=False Parquet table read only the surviving row groups and still return
+    exactly what pandas returns on the whole file (filter, group-by, join build side)."""
+    import pyarrow as pa
+    import pyarrow.parquet as pq
+    from dask_sql_b200 import executor
+    n = 40_000
+    rng = np.random.default_rng(17)
+    df = pd.DataFrame({"a": np.arange(n), "k": rng.integers(0, 40, n), "v": rng.random(n),
+                       "m": pd.array(np.where(rng.random(n) < 0.1, None, rng.integers(0, 9, n)), dtype="Int64")})
+    path = str(tmp_path / "t.parquet")
+    pq.write_table(pa.Table.from_pandas(df), path, row_group_size=4096)
+    c.create_table("t", path)
+    table = c.schema[c.schema_name].tables["t"].df.source.table
+    before = executor.stats.get("rowgroups_skipped", 0)
+    got = c.sql("SELECT k, SUM(v) AS s, COUNT(m) AS cm FROM t WHERE a >= 30000 AND a < 36000 GROUP BY k",
+                return_futures=False)
+    e = df[(df.a >= 30000) & (df.a < 36000)]
+    exp = e.groupby("k").agg(s=("v", "sum"), cm=("m", "count")).reset_index()
+    assert_same(got, exp, ["s"])
+    assert executor.stats.get("rowgroups_skipped", 0) - before >= 7           # 10 row groups, at most 3 overlap
+    assert not any(k[1] == "a" and k[0] < 7 for k in table._cache)            # early row groups never decoded
+    got = c.sql("SELECT a, v FROM t WHERE a = 12345 OR a = 5", return_futures=False)   # OR: no pruning, same answer
+    assert_same(got, df[(df.a == 12345) | (df.a == 5)][["a", "v"]], ["v"])
+    c.create_table("d", pd.DataFrame({"k": np.arange(40), "w": np.arange(40) * 2.0}), persist=True)
+    got = c.sql("SELECT d.w, SUM(t.v) AS s FROM t JOIN d ON t.k = d.k WHERE t.a < 5000 GROUP BY d.w",
+                return_futures=False)
+    e = df[df.a < 5000].merge(pd.DataFrame({"k": np.arange(40), "w": np.arange(40) * 2.0}), on="k")
+    assert_same(got, e.groupby("w").agg(s=("v", "sum")).reset_index(), ["s"])
