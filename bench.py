@@ -358,12 +358,27 @@ def main():
     executor.kernel_events = []
     executor.phase_events = [] if world > 1 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    prof = None
+    if os.environ.get("B200SQL_BENCH_PROFILE") == "1" and rank == 0:     # host-side profile of the timed loop
+        import cProfile
+        prof = cProfile.Profile()
     w0 = time.perf_counter()
     e0.record()
+    if prof is not None:
+        prof.enable()
     for _ in range(args.steps):
         parts = step_resident()
+    if prof is not None:
+        prof.disable()
     e1.record()
     host_issue = time.perf_counter() - w0
+    if prof is not None:
+        import io
+        import pstats
+        buf = io.StringIO()
+        pstats.Stats(prof, stream=buf).sort_stats("cumulative").print_stats(45)
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        open(os.path.join(ROOT, "gpurun_out", f"host_profile_n{world}.txt"), "w").write(buf.getvalue())
     barrier()
     sampler.active = False
     wall = time.perf_counter() - w0
