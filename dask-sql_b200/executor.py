@@ -163,22 +163,61 @@ class PendingPart(Part):
         return dict.get(self.resolve(), k, default)
 
 
+class _PinnedRing:
+    """A fixed pool of pinned 64-byte slots for the counts that travel to the host behind the kernels.
+    (A fresh pin_memory tensor per query means a cudaHostAlloc whenever the host runs ahead of the GPU
+    -- the allocator cannot recycle a block whose copy has not finished -- and that call costs far more
+    than the query's launches.)  A slot is reused only after the copy that last used it completed."""
+
+    SLOTS = 1024
+
+    def __init__(self):
+        self.buf = torch.empty(self.SLOTS * 8, dtype=torch.int64, pin_memory=True)
+        self.events = [None] * self.SLOTS
+        self.i = 0
+
+    def take(self):
+        i = self.i
+        self.i = (i + 1) % self.SLOTS
+        ev = self.events[i]
+        if ev is not None:
+            ev.synchronize()           # 1024 counts in flight: wait for the oldest
+        return i, self.buf[i * 8:(i + 1) * 8]
+
+
+_pinned_ring = None
+
+
 class DeviceCount:
-    """An int64 count produced on the device, copied to pinned host memory behind the kernels
-    that wrote it; .get() waits for that copy only."""
+    """Small integer tensors produced on the device (a row count, duplicate-key flags), copied to pinned
+    host memory behind the kernels that wrote them; .get() waits for those copies only and returns the
+    values of all tensors in order."""
 
     def __init__(self, *tensors):
-        flat = torch.cat([t.reshape(-1).to(torch.int64) for t in tensors]) if len(tensors) > 1 else \
-            tensors[0].reshape(-1)
-        self.host = torch.empty(flat.shape, dtype=flat.dtype, pin_memory=True)
-        self.host.copy_(flat, non_blocking=True)
+        global _pinned_ring
+        if _pinned_ring is None:
+            _pinned_ring = _PinnedRing()
+        self.views, slots = [], []
+        for t in tensors:
+            t = t.reshape(-1)
+            assert t.numel() * t.element_size() <= 64, "DeviceCount carries a handful of integers"
+            i, slot = _pinned_ring.take()
+            dst = slot.view(t.dtype)[: t.numel()]
+            dst.copy_(t, non_blocking=True)
+            self.views.append(dst)
+            slots.append(i)
         self.event = torch.cuda.Event()
         self.event.record()
+        for i in slots:
+            _pinned_ring.events[i] = self.event
 
     def get(self):
         self.event.synchronize()
-        stats["d2h_bytes"] += self.host.numel() * 8
-        return self.host.tolist()
+        out = []
+        for v in self.views:
+            stats["d2h_bytes"] += v.numel() * v.element_size()
+            out.extend(v.tolist())
+        return out
 
 
 # ---------------------------------------------------------------------------------------------
