@@ -117,6 +117,7 @@ _SIGS = {
                        C.POINTER(C.c_int32), C.POINTER(C.c_int64)],
     "b2_d2h": [_P, _P, C.c_int64, _P],
     "b2_sync": [_P],
+    "b2_memset": [_P, C.c_int32, C.c_int64, _P],
     "b2_col_stats": [C.POINTER(Col), C.c_int64, _P, _P, _P],
     "b2_expr_eval": [C.POINTER(Prog), C.POINTER(Col), C.c_int32, C.c_int64, _P, _P, _P],
     "b2_scan_agg": [C.POINTER(Scan), C.POINTER(Agg), C.c_int32, _P, _P, C.c_int32, _P, _P],
@@ -199,6 +200,7 @@ version.restype = C.c_int32
 device_info = _wrap("b2_device_info")
 d2h = _wrap("b2_d2h")
 sync = _wrap("b2_sync")
+memset = _wrap("b2_memset")
 col_stats = _wrap("b2_col_stats")
 expr_eval = _wrap("b2_expr_eval")
 scan_agg = _wrap("b2_scan_agg")

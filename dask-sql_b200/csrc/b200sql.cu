@@ -62,6 +62,12 @@ int32_t b2_d2h(void* host_dst, const void* dev_src, int64_t bytes, void* stream)
   return B2_OK;
 }
 
+int32_t b2_memset(void* dev_ptr, int32_t byte, int64_t nbytes, void* stream) {
+  B2_REQUIRE(dev_ptr || nbytes == 0, "null argument");
+  if (nbytes > 0) B2_CUDA_TRY(cudaMemsetAsync(dev_ptr, byte, (size_t)nbytes, (cudaStream_t)stream));
+  return B2_OK;
+}
+
 int32_t b2_sync(void* stream) {
   B2_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
   return B2_OK;

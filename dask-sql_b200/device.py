@@ -22,21 +22,40 @@ def require_cuda():
         raise RuntimeError("dask_sql_b200 executes on a CUDA device (B200, sm_100a); no CPU fallback exists")
 
 
-_stream = [None]
+_stream = [None, None, None]
 
 
-def stream_ptr():
-    """Current torch stream as a C pointer.  torch.cuda.current_stream() costs ~15 us of Python per
-    call and a query makes dozens of launches, so the pointer is cached until reset_stream() (the
-    executor calls it on entry to every query and before resolving a pending result)."""
-    s = _stream[0]
+def cur_stream():
+    """The current torch stream, looked up once per query.  torch.cuda.current_stream() walks through
+    torch._utils._get_available_device_type() on every call (measured ~100 us per call in a
+    torch.distributed job), and Event.record() / wait_event() call it when no stream is passed -- dozens
+    of times per query.  Cached until reset_stream() (the executor calls that on entry to every query
+    and before resolving a pending result); events are always recorded on an explicit stream."""
+    s = _stream[1]
     if s is None:
-        s = _stream[0] = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        s = _stream[1] = torch.cuda.current_stream()
     return s
 
 
+def stream_ptr():
+    """The same stream as a C pointer for the C-ABI calls."""
+    s = _stream[0]
+    if s is None:
+        s = _stream[0] = C.c_void_p(cur_stream().cuda_stream)
+    return s
+
+
+def cur_device():
+    """torch.device of the current CUDA device, looked up once per query (see cur_stream)."""
+    d = _stream[2]
+    if d is None:
+        require_cuda()
+        d = _stream[2] = torch.device("cuda", torch.cuda.current_device())
+    return d
+
+
 def reset_stream():
-    _stream[0] = None
+    _stream[0] = _stream[1] = _stream[2] = None
 
 
 def ptr(t: Optional[torch.Tensor]):
@@ -247,7 +266,7 @@ _ws_cache = {}
 
 
 def _workspace(device, nbytes):
-    key = (device.index, torch.cuda.current_stream().cuda_stream)
+    key = (device.index, cur_stream().cuda_stream)
     ws = _ws_cache.get(key)
     if ws is None or ws.numel() < nbytes:
         ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)

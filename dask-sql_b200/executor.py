@@ -46,7 +46,7 @@ def _kernel_event_begin(name, rows):
     if kernel_events is None:
         return None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
+    e0.record(D.cur_stream())
     rec = [name, rows, e0, e1]
     kernel_events.append(rec)
     return rec
@@ -54,7 +54,7 @@ def _kernel_event_begin(name, rows):
 
 def _kernel_event_end(rec):
     if rec is not None:
-        rec[3].record()
+        rec[3].record(D.cur_stream())
 
 
 # Optional per-phase timing of a query's exchange steps (bench.py sets this to a list): entries are
@@ -63,28 +63,28 @@ phase_events = None
 
 
 class _Phase:
-    __slots__ = ("rec",)
+    __slots__ = ("rec", "stream")
 
-    def __init__(self, name):
+    def __init__(self, name, stream=None):
         self.rec = None
         if phase_events is not None:
             self.rec = [name, torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)]
+            self.stream = stream if stream is not None else D.cur_stream()
 
     def __enter__(self):
         if self.rec is not None:
-            self.rec[1].record()
+            self.rec[1].record(self.stream)
         return self
 
     def __exit__(self, *exc):
         if self.rec is not None:
-            self.rec[2].record()
+            self.rec[2].record(self.stream)
             phase_events.append(self.rec)
         return False
 
 
 def _dev():
-    D.require_cuda()
-    return torch.device("cuda", torch.cuda.current_device())
+    return D.cur_device()
 
 
 class Part(dict):
@@ -207,7 +207,7 @@ class DeviceCount:
             self.views.append(dst)
             slots.append(i)
         self.event = torch.cuda.Event()
-        self.event.record()
+        self.event.record(D.cur_stream())
         for i in slots:
             _pinned_ring.events[i] = self.event
 
@@ -785,7 +785,7 @@ def run_aggregate(src: AggSource, allow_fast=True) -> Part:
     if allow_fast:
         # a fused star query that was prepared before: straight to its cached launch descriptors
         last = src.__dict__.get("_prepared_last")
-        if last is not None and last[0] == (P.world()[1], torch.cuda.current_device()) and last[1] in PreparedStar._live \
+        if last is not None and last[0] == (P.world()[1], _dev().index) and last[1] in PreparedStar._live \
                 and os.environ.get("B200SQL_NO_PREPARED") != "1":
             return last[1].run(src)
     child = src.child
@@ -1560,7 +1560,7 @@ class PreparedStar:
 
     @classmethod
     def get(cls, src, fact, dim, fk_e, pk_e, ge, gexpr0, aggs, fpred, dpred, meta, owner, bcast, sharded, dev):
-        key = (sharded, P.world()[1], torch.cuda.current_device())
+        key = (sharded, P.world()[1], _dev().index)
         cache = src.__dict__.setdefault("_prepared_star", {})
         if key in cache:
             prep = cache[key]
@@ -1582,7 +1582,7 @@ class PreparedStar:
                 prep.group = P.build_group()
         cache[key] = prep
         if prep is not None:
-            src.__dict__["_prepared_last"] = ((P.world()[1], torch.cuda.current_device()), prep)
+            src.__dict__["_prepared_last"] = ((P.world()[1], _dev().index), prep)
             cls._live.append(prep)
             while len(cls._live) > cls.MAX_LIVE:
                 cls._live.pop(0)
@@ -1678,24 +1678,28 @@ class PreparedStar:
         i = self.runs & 1
         self.runs += 1
         buf = self.ring[i]
-        main = torch.cuda.current_stream()
+        main = D.cur_stream()
         bs = self.build_stream
         # ---- build side on its own stream (phase events recorded there: they overlap the previous run's scan)
         if self.free[i] is not None:
             bs.wait_event(self.free[i])
-        with torch.cuda.stream(bs):
-            with _Phase("build"):
-                buf.fill_(-1)
-                buf[self.prange:].zero_()
-                for scan, pk_slot, g_slot in self.dim_launch:
-                    stats["launches"] += 1
-                    L.star_build_scan(C.byref(scan), pk_slot, g_slot, self.pmin, self.prange, self.gmin,
-                                      self.nslots - 1, C.c_void_p(buf.data_ptr()),
-                                      C.c_void_p(buf.data_ptr() + 4 * self.prange), self.build_ptr)
-            if self.bcast:
-                with _Phase("bcast"):
+        with _Phase("build", bs):
+            # lookup := -1 everywhere (0xFF bytes), the 4 flag words behind it := 0
+            L.memset(C.c_void_p(buf.data_ptr()), 0xFF, 4 * self.prange, self.build_ptr)
+            L.memset(C.c_void_p(buf.data_ptr() + 4 * self.prange), 0, 16, self.build_ptr)
+            for scan, pk_slot, g_slot in self.dim_launch:
+                stats["launches"] += 1
+                L.star_build_scan(C.byref(scan), pk_slot, g_slot, self.pmin, self.prange, self.gmin,
+                                  self.nslots - 1, C.c_void_p(buf.data_ptr()),
+                                  C.c_void_p(buf.data_ptr() + 4 * self.prange), self.build_ptr)
+        if self.bcast:
+            with _Phase("bcast", bs):
+                torch.cuda.set_stream(bs)          # torch.distributed orders the collective after the CURRENT stream
+                try:
                     P.broadcast_(buf, 0, group=self.group)
-            self.built[i].record(bs)
+                finally:
+                    torch.cuda.set_stream(main)
+        self.built[i].record(bs)
         # ---- probe side on the caller's stream
         with _Phase("wait_build"):
             main.wait_event(self.built[i])

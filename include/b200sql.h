@@ -181,6 +181,8 @@ int32_t b2_device_info(int32_t device, int32_t* sm_count, int64_t* l2_bytes,
                        int32_t* cc_major, int32_t* cc_minor, int64_t* hbm_bytes);
 int32_t b2_d2h(void* host_dst, const void* dev_src, int64_t bytes, void* stream); /* copies then syncs stream */
 int32_t b2_sync(void* stream);
+/* cudaMemsetAsync on `stream` (re-initialising lookup / table buffers that a prepared query reuses) */
+int32_t b2_memset(void* dev_ptr, int32_t byte, int64_t nbytes, void* stream);
 /* number of B2_TILE tiles covering n rows */
 int64_t b2_num_tiles(int64_t n);
 
