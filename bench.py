@@ -357,6 +357,8 @@ def main():
     launches0 = executor.stats["launches"]
     executor.kernel_events = []
     executor.phase_events = [] if world > 1 else None
+    if os.environ.get("B200SQL_CALL_TIMES") == "1":
+        executor.D.trace = []
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     prof = None
     if os.environ.get("B200SQL_BENCH_PROFILE") == "1" and rank == 0:     # host-side profile of the timed loop
@@ -372,6 +374,19 @@ def main():
         prof.disable()
     e1.record()
     host_issue = time.perf_counter() - w0
+    if rank == 0 and os.environ.get("B200SQL_CALL_TIMES") == "1":
+        torch.cuda.synchronize()
+        tr = executor.D.trace
+        seg = {}
+        for (la, ea), (lb, eb) in zip(tr, tr[1:]):
+            if la != "select:written":
+                seg[la + "->" + lb] = seg.get(la + "->" + lb, 0.0) + ea.elapsed_time(eb)
+        print("[select_launch GPU ms per step] " + json.dumps({k: round(v / args.steps, 4) for k, v in seg.items()}),
+              file=sys.stderr)
+        from dask_sql_b200 import _lib as _L
+        print("[call times over the timed loop + warm-up] " + json.dumps(
+            {k: [v[0], round(v[1] * 1e3, 3)] for k, v in sorted(_L.call_times.items(), key=lambda kv: -kv[1][1])}),
+            file=sys.stderr)
     if prof is not None:
         import io
         import pstats

@@ -180,10 +180,29 @@ EXPORTS = sorted(list(_SIGS) + ["b2_last_error", "b2_num_tiles", "b2_stats_ws_by
                                 "b2_f64_to_ordered", "b2_ordered_to_f64"])
 
 
+call_times = {} if os.environ.get("B200SQL_CALL_TIMES") == "1" else None    # name -> [calls, host seconds]
+
+
 def _wrap(name):
     fn = getattr(_lib, name)
     fn.restype = C.c_int32
     fn.argtypes = _SIGS[name]
+
+    if call_times is not None:
+        import time
+
+        def call(*args):
+            t0 = time.perf_counter()
+            rc = fn(*args)
+            rec = call_times.setdefault(name, [0, 0.0])
+            rec[0] += 1
+            rec[1] += time.perf_counter() - t0
+            if rc != 0:
+                raise B200SqlError(f"{name} failed ({rc}): {_lib.b2_last_error().decode()}")
+            return rc
+
+        call.__name__ = name
+        return call
 
     def call(*args):
         rc = fn(*args)

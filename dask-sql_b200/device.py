@@ -349,6 +349,16 @@ def select(scan: L.Scan, device, gather_cols: Sequence[int] = (), want_idx=True,
     return idx, res, total
 
 
+trace = None      # optional [(label, cuda event)] recorded around the two launches of select_launch (diagnostics)
+
+
+def _mark(label):
+    if trace is not None:
+        e = torch.cuda.Event(enable_timing=True)
+        e.record(cur_stream())
+        trace.append((label, e))
+
+
 def select_launch(scan: L.Scan, device, gather_cols: Sequence[int], cols: Sequence[DeviceColumn]):
     """select() without the host round trip: outputs are allocated at their upper bound (scan.n rows),
     count and write kernels are both enqueued, and the count stays on the device.  Only for inputs
@@ -356,7 +366,9 @@ def select_launch(scan: L.Scan, device, gather_cols: Sequence[int], cols: Sequen
     n = scan.n
     ntiles = L.num_tiles(n)
     tile_off = torch.empty(ntiles + 1, dtype=torch.int64, device=device)
+    _mark("select:begin")
     L.select_count(C.byref(scan), ptr(tile_off), stream_ptr())
+    _mark("select:counted")
     outs = [torch.empty(n, dtype=_TORCH_DTYPE[cols[g].dtype], device=device) for g in gather_cols]
     k = len(gather_cols)
     gc = (C.c_int32 * max(1, k))(*gather_cols)
@@ -364,6 +376,7 @@ def select_launch(scan: L.Scan, device, gather_cols: Sequence[int], cols: Sequen
     ov = (C.c_void_p * max(1, k))(*[0] * k)
     if n > 0:
         L.select_write(C.byref(scan), ptr(tile_off), C.c_void_p(0), k, gc, od, ov, stream_ptr())
+    _mark("select:written")
     return outs, tile_off[ntiles:ntiles + 1]
 
 
