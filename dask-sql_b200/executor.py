@@ -1250,14 +1250,31 @@ def _merge_dense(t: D.GroupTable, plan: AggPlan, sharded: bool, dev) -> SlotView
     with _Phase("presence"):
         pres = _presence_bytes(t, dev)
         stats["launches"] += 1
+    mode = os.environ.get("B200SQL_MERGE", "reduce_scatter")      # diagnostics: "allreduce" | "rs_persist"
     with _Phase("reduce_scatter"):
-        accs, cnts = [], []
-        for ka, acc, cnt in zip(plan.kaggs, t.acc, t.cnt):
-            accs.append(None if acc is None else
-                        P.reduce_scatter_(acc, {L.AGG_MIN: "min", L.AGG_MAX: "max"}.get(ka.op, "sum")))
-            cnts.append(None if cnt is None else P.reduce_scatter_(cnt, "sum"))
-        rows = None if t.rows is None else P.reduce_scatter_(t.rows, "sum")
-        pres = P.reduce_scatter_(pres, "max")
+        if mode == "allreduce":
+            lo = rank * chunk
+            accs, cnts = [], []
+            for ka, acc, cnt in zip(plan.kaggs, t.acc, t.cnt):
+                accs.append(None if acc is None else
+                            P.allreduce_(acc, {L.AGG_MIN: "min", L.AGG_MAX: "max"}.get(ka.op, "sum"))[lo:lo + chunk])
+                cnts.append(None if cnt is None else P.allreduce_(cnt, "sum")[lo:lo + chunk])
+            rows = None if t.rows is None else P.allreduce_(t.rows, "sum")[lo:lo + chunk]
+            pres = P.allreduce_(pres, "max")[lo:lo + chunk]
+        else:
+            keep = t.__dict__.setdefault("_rs_out", {}) if mode == "rs_persist" else None
+            accs, cnts = [], []
+            for i, (ka, acc, cnt) in enumerate(zip(plan.kaggs, t.acc, t.cnt)):
+                accs.append(None if acc is None else
+                            P.reduce_scatter_(acc, {L.AGG_MIN: "min", L.AGG_MAX: "max"}.get(ka.op, "sum"),
+                                              out=None if keep is None else keep.setdefault(("a", i), torch.empty(chunk, dtype=acc.dtype, device=dev))))
+                cnts.append(None if cnt is None else P.reduce_scatter_(cnt, "sum"))
+            rows = None if t.rows is None else P.reduce_scatter_(t.rows, "sum")
+            pres = P.reduce_scatter_(pres, "max",
+                                     out=None if keep is None else keep.setdefault("p", torch.empty(chunk, dtype=pres.dtype, device=dev)))
+        if os.environ.get("B200SQL_PROBE_AFTER_NCCL") == "1":
+            probe = t.__dict__.setdefault("_probe", torch.zeros(4, dtype=torch.int32, device=dev))
+            L.memset(C.c_void_p(probe.data_ptr()), 0, 16, D.stream_ptr())
     return SlotView(t.nslots, rank * chunk, chunk, accs, cnts, rows, "bytes", pres, dist="keyrange")
 
 

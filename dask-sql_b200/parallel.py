@@ -51,7 +51,7 @@ def _backend() -> str:
     return _WORLD[2] if world()[1] > 1 else "none"
 
 
-def reduce_scatter_(t: torch.Tensor, op: str = "sum") -> torch.Tensor:
+def reduce_scatter_(t: torch.Tensor, op: str = "sum", out=None) -> torch.Tensor:
     """Element-wise reduction of `t` over all ranks, of which this rank keeps only its own
     contiguous 1/size slice (t.numel() must be a multiple of the world size).  NCCL: one
     ncclReduceScatter -- (size-1)/size of the array crosses NVLink per rank instead of the
@@ -65,7 +65,8 @@ def reduce_scatter_(t: torch.Tensor, op: str = "sum") -> torch.Tensor:
     chunk = n // size
     rop = {"sum": dist.ReduceOp.SUM, "min": dist.ReduceOp.MIN, "max": dist.ReduceOp.MAX}[op]
     if _backend() == "nccl":
-        out = torch.empty(chunk, dtype=t.dtype, device=t.device)
+        if out is None:
+            out = torch.empty(chunk, dtype=t.dtype, device=t.device)
         dist.reduce_scatter_tensor(out, t, op=rop)
         return out
     dist.all_reduce(t, op=rop)

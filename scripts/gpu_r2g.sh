@@ -2,6 +2,18 @@
 mkdir -p gpurun_out
 cd "$(dirname "$0")/.."
 N=$(python -c "import torch; print(torch.cuda.device_count())")
-( B200SQL_CALL_TIMES=1 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 \
-    bench.py --gpus $N --steps 20 --warmup 5 --no-e2e ) > gpurun_out/r2g_bench$N.json 2> gpurun_out/r2g_bench$N.err
-grep -a 'call times\|select_launch' gpurun_out/r2g_bench$N.err | cut -c1-1500
+run() {
+  name=$1; shift
+  ( env B200SQL_CALL_TIMES=1 "$@" timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 \
+      bench.py --gpus $N --steps 20 --warmup 5 --no-e2e ) > gpurun_out/r2g_${name}_$N.json 2> gpurun_out/r2g_${name}_$N.err
+  echo "== $name"; python -c "
+import json,sys
+d=json.loads(open('gpurun_out/r2g_${name}_$N.json').read().strip().splitlines()[-1])
+print('ms/step %.3f'%d['ms_per_step'], 'ok', d['verified_full_size']['ok'], {k:round(v,3) for k,v in d['exchange'].items() if k.endswith('_ms')})"
+  grep -a 'call times\|select_launch' gpurun_out/r2g_${name}_$N.err | cut -c1-600
+}
+run base
+run probe B200SQL_PROBE_AFTER_NCCL=1
+run allreduce B200SQL_MERGE=allreduce
+run rspersist B200SQL_MERGE=rs_persist
+run noprep B200SQL_NO_PREPARED=1
