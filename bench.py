@@ -349,14 +349,15 @@ def main():
 
     # ---- value: device-resident inputs
     sampler = ClockSampler(local)
-    sampler.start()
+    if os.environ.get("B200SQL_NO_SAMPLER") != "1":
+        sampler.start()
     for _ in range(args.warmup):
         parts = step_resident()
     barrier()
     sampler.active = True
     launches0 = executor.stats["launches"]
     executor.kernel_events = []
-    executor.phase_events = [] if world > 1 else None
+    executor.phase_events = [] if (world > 1 and os.environ.get("B200SQL_NO_PHASES") != "1") else None
     if os.environ.get("B200SQL_CALL_TIMES") == "1":
         executor.D.trace = []
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -383,7 +384,9 @@ def main():
                 seg[la + "->" + lb] = seg.get(la + "->" + lb, 0.0) + ea.elapsed_time(eb)
         print("[select_launch GPU ms per step] " + json.dumps({k: round(v / args.steps, 4) for k, v in seg.items()}),
               file=sys.stderr)
-        from dask_sql_b200 import _lib as _L
+        from dask_sql_b200 import _lib as _L, parallel as _P
+        print("[collective host ms: calls, total] " + json.dumps({k: [v[0], round(v[1] * 1e3, 3)] for k, v in (_P.coll_times or {}).items()}),
+              file=sys.stderr)
         print("[call times over the timed loop + warm-up] " + json.dumps(
             {k: [v[0], round(v[1] * 1e3, 3)] for k, v in sorted(_L.call_times.items(), key=lambda kv: -kv[1][1])}),
             file=sys.stderr)
@@ -403,7 +406,8 @@ def main():
     kev, pev = executor.kernel_events, executor.phase_events
     executor.kernel_events = executor.phase_events = None
     sampler.stop_flag = True
-    sampler.join(timeout=2)
+    if sampler.is_alive():
+        sampler.join(timeout=2)
     n_groups_local = parts[0].n
 
     peak_gbs, peak_src = load_peaks()

@@ -13,7 +13,22 @@ import torch
 import torch.distributed as dist
 
 
+import os
+import time
+
 _WORLD = None        # (rank, size, backend) once a process group exists: asked dozens of times per query
+coll_times = {} if os.environ.get("B200SQL_CALL_TIMES") == "1" else None     # diagnostics: name -> [calls, host s]
+
+
+def _timed(name, fn, *args, **kw):
+    if coll_times is None:
+        return fn(*args, **kw)
+    t0 = time.perf_counter()
+    out = fn(*args, **kw)
+    rec = coll_times.setdefault(name, [0, 0.0])
+    rec[0] += 1
+    rec[1] += time.perf_counter() - t0
+    return out
 
 
 def world() -> Tuple[int, int]:
@@ -43,7 +58,7 @@ def allreduce_(t: torch.Tensor, op: str = "sum") -> torch.Tensor:
     if world()[1] == 1:
         return t
     rop = {"sum": dist.ReduceOp.SUM, "min": dist.ReduceOp.MIN, "max": dist.ReduceOp.MAX}[op]
-    dist.all_reduce(t, op=rop)
+    _timed(f"all_reduce[{t.dtype},{op}]", dist.all_reduce, t, op=rop)
     return t
 
 
@@ -67,7 +82,7 @@ def reduce_scatter_(t: torch.Tensor, op: str = "sum", out=None) -> torch.Tensor:
     if _backend() == "nccl":
         if out is None:
             out = torch.empty(chunk, dtype=t.dtype, device=t.device)
-        dist.reduce_scatter_tensor(out, t, op=rop)
+        _timed(f"reduce_scatter[{t.dtype},{op}]", dist.reduce_scatter_tensor, out, t, op=rop)
         return out
     dist.all_reduce(t, op=rop)
     return t[rank * chunk:(rank + 1) * chunk].clone()
@@ -125,7 +140,7 @@ def build_group():
 
 def broadcast_(t: torch.Tensor, src: int = 0, group=None) -> torch.Tensor:
     if world()[1] > 1:
-        dist.broadcast(t, src=src, group=group)
+        _timed("broadcast", dist.broadcast, t, src=src, group=group)
     return t
 
 

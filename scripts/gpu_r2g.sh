@@ -9,11 +9,10 @@ run() {
   echo "== $name"; python -c "
 import json,sys
 d=json.loads(open('gpurun_out/r2g_${name}_$N.json').read().strip().splitlines()[-1])
-print('ms/step %.3f'%d['ms_per_step'], 'ok', d['verified_full_size']['ok'], {k:round(v,3) for k,v in d['exchange'].items() if k.endswith('_ms')})"
-  grep -a 'call times\|select_launch' gpurun_out/r2g_${name}_$N.err | cut -c1-600
+print('ms/step %.3f'%d['ms_per_step'], 'ok', d['verified_full_size']['ok'], {k:round(v,3) for k,v in (d['exchange'] or {}).items() if k.endswith('_ms')})"
+  grep -a 'collective host\|call times' gpurun_out/r2g_${name}_$N.err | cut -c1-500
 }
-run base
-run probe B200SQL_PROBE_AFTER_NCCL=1
-run allreduce B200SQL_MERGE=allreduce
-run rspersist B200SQL_MERGE=rs_persist
 run noprep B200SQL_NO_PREPARED=1
+run noprep_nosampler B200SQL_NO_PREPARED=1 B200SQL_NO_SAMPLER=1
+run noprep_nophases B200SQL_NO_PREPARED=1 B200SQL_NO_PHASES=1 B200SQL_NO_SAMPLER=1
+run prep_nosampler B200SQL_NO_SAMPLER=1 B200SQL_NO_PHASES=1
