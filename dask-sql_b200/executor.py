@@ -1261,6 +1261,16 @@ def _merge_dense(t: D.GroupTable, plan: AggPlan, sharded: bool, dev) -> SlotView
                 cnts.append(None if cnt is None else P.allreduce_(cnt, "sum")[lo:lo + chunk])
             rows = None if t.rows is None else P.allreduce_(t.rows, "sum")[lo:lo + chunk]
             pres = P.allreduce_(pres, "max")[lo:lo + chunk]
+        elif mode == "allreduce_f64":
+            # diagnostics: existence as float64 counts, summed -- only f64 SUM collectives on the wire
+            lo = rank * chunk
+            accs, cnts = [], []
+            for ka, acc, cnt in zip(plan.kaggs, t.acc, t.cnt):
+                accs.append(None if acc is None else
+                            P.allreduce_(acc, {L.AGG_MIN: "min", L.AGG_MAX: "max"}.get(ka.op, "sum"))[lo:lo + chunk])
+                cnts.append(None if cnt is None else P.allreduce_(cnt, "sum")[lo:lo + chunk])
+            rows = None if t.rows is None else P.allreduce_(t.rows, "sum")[lo:lo + chunk]
+            pres = (P.allreduce_(pres.to(torch.float64), "sum")[lo:lo + chunk] > 0).to(torch.uint8)
         else:
             keep = t.__dict__.setdefault("_rs_out", {}) if mode == "rs_persist" else None
             accs, cnts = [], []
