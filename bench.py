@@ -226,7 +226,7 @@ class ClockSampler(threading.Thread):
                     for bit, name in names.items():
                         if r & bit:
                             self.reasons.add(name)
-                time.sleep(0.002)
+                time.sleep(0.004)
         except Exception as e:  # pragma: no cover
             self.reasons.add(f"sampler_error:{type(e).__name__}")
 
@@ -286,6 +286,10 @@ def main():
     json_fd = os.dup(1)
     os.dup2(2, 1)
 
+    # buffers handed to a collective stay owned by this code until the collective has been waited for
+    # (they are persistent or live to the end of the query), so the allocator need not tie them to the
+    # communicator's stream; without this their blocks cannot be recycled while the host runs ahead
+    os.environ.setdefault("TORCH_NCCL_AVOID_RECORD_STREAMS", "1")
     import torch
     import torch.distributed as dist
 
@@ -356,6 +360,7 @@ def main():
     barrier()
     sampler.active = True
     launches0 = executor.stats["launches"]
+    executor.prefill_timing_events(args.steps * (2 * parts_per_gpu(world) + 24) + 64)
     executor.kernel_events = []
     executor.phase_events = [] if (world > 1 and os.environ.get("B200SQL_NO_PHASES") != "1") else None
     if os.environ.get("B200SQL_CALL_TIMES") == "1":

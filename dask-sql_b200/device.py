@@ -290,9 +290,10 @@ def col_stats(col: DeviceColumn) -> Stats:
     return Stats(mn, mx, nulls + nans, repeat)
 
 
-def expr_eval(prog: L.Prog, cols: Sequence[DeviceColumn], n: int, want_valid: bool) -> DeviceColumn:
-    dev = cols[0].device if cols else torch.device("cuda", torch.cuda.current_device())
-    out = torch.empty(n, dtype=_TORCH_DTYPE[prog.out_dtype], device=dev)
+def expr_eval(prog: L.Prog, cols: Sequence[DeviceColumn], n: int, want_valid: bool, out=None) -> DeviceColumn:
+    dev = cols[0].device if cols else cur_device()
+    if out is None:
+        out = torch.empty(n, dtype=_TORCH_DTYPE[prog.out_dtype], device=dev)
     valid = torch.empty(bitmap_words(n), dtype=torch.int32, device=dev) if want_valid else None
     arr = (L.Col * max(1, len(cols)))()
     for i, c in enumerate(cols):

@@ -12,8 +12,5 @@ d=json.loads(open('gpurun_out/r2g_${name}_$N.json').read().strip().splitlines()[
 print('ms/step %.3f'%d['ms_per_step'], 'ok', d['verified_full_size']['ok'], {k:round(v,3) for k,v in (d['exchange'] or {}).items() if k.endswith('_ms')})"
   grep -a 'collective host\|call times' gpurun_out/r2g_${name}_$N.err | cut -c1-500
 }
-run np_rs B200SQL_NO_PREPARED=1 B200SQL_NO_SAMPLER=1 B200SQL_NO_PHASES=1
-run np_allreduce B200SQL_NO_PREPARED=1 B200SQL_NO_SAMPLER=1 B200SQL_NO_PHASES=1 B200SQL_MERGE=allreduce
-run np_allreduce_f64 B200SQL_NO_PREPARED=1 B200SQL_NO_SAMPLER=1 B200SQL_NO_PHASES=1 B200SQL_MERGE=allreduce_f64
-run np_rs_avoidrec B200SQL_NO_PREPARED=1 B200SQL_NO_SAMPLER=1 B200SQL_NO_PHASES=1 TORCH_NCCL_AVOID_RECORD_STREAMS=1
-run np_rs_nodefer B200SQL_NO_PREPARED=1 B200SQL_NO_SAMPLER=1 B200SQL_NO_PHASES=1 B200SQL_NO_DEFER=1
+run full
+run noprep B200SQL_NO_PREPARED=1

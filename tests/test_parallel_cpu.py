@@ -184,7 +184,7 @@ def _dense_worker(rank, size, port, out_q):
         class Plan:
             kaggs = [KA()]
 
-        X._presence_bytes = lambda t, d: (t.acc[0].view(torch.int64) != -(1 << 63)).to(torch.uint8)
+        X._presence_bytes = lambda t, d, out=None: (t.acc[0].view(torch.int64) != -(1 << 63)).to(torch.uint8)
         view = X._merge_dense(tbl, Plan(), True, dev)
         assert view.dist == "keyrange" and view.count == alloc // size and view.lo == rank * view.count
         assert view.occ_kind == "bytes"
