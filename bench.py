@@ -184,9 +184,22 @@ def workload_config(args, n):
             "planning": "Context.sql() is called every step; its plan (not its result) is served from the "
                         "prepared-statement cache after the first call; build side, lookup and group table "
                         "are rebuilt every step",
-            "parallelism": f"fact sharded over {n} GPU(s); dim on rank 0, its pk->slot lookup broadcast every step "
-                           "(NCCL); dense partial aggregates reduce-scattered by key range (NCCL), every rank "
-                           "compacts and keeps the groups of its range" if n > 1 else "single GPU"}
+            "parallelism": (f"fact sharded over {n} GPU(s); dim on rank 0, its pk->slot lookup broadcast every step "
+                            "(NCCL, second stream + communicator: overlaps the previous step's scan); dense partial "
+                            "aggregates merged by key range -- " + merge_kind() + " -- every rank compacts and keeps "
+                            "the groups of its range") if n > 1 else "single GPU"}
+
+
+def merge_kind():
+    """How the ranks' partial group tables were merged in this process (decided by the executor)."""
+    try:
+        from dask_sql_b200 import executor
+        if executor.stats.get("peer_merge_plans", 0) > 0:
+            return ("b2_peer_merge: one kernel per GPU over NVLink peer memory (in-kernel barrier, rank-ordered "
+                    "reduction of its slot range, existence merged in the same pass)")
+    except Exception:
+        pass
+    return "ncclReduceScatter per accumulator array + presence bytes"
 
 
 # ---------------------------------------------------------------------------------------------

@@ -74,13 +74,26 @@ class JoinAgg(C.Structure):
 
 class StarLookup(C.Structure):
     _fields_ = [("dense", C.c_int32), ("pad_", C.c_int32), ("lookup", C.c_void_p), ("kmin", C.c_int64),
-                ("range", C.c_int64), ("table_keys", C.c_void_p), ("table_slots", C.c_void_p),
-                ("cap", C.c_int64)]
+                ("range", C.c_int64), ("table", C.c_void_p), ("cap", C.c_int64)]
+
+
+MAX_PEERS, PEER_MAX_ARRAYS = 16, 2 * MAX_AGGS + 1
+PEER_SUM_F64, PEER_SUM_I64, PEER_MIN_I64, PEER_MAX_I64 = range(4)
+PEER_PRESENT_ROWS, PEER_PRESENT_INDICATOR, PEER_PRESENT_BITMAP = 1, 2, 3
+
+
+class PeerMerge(C.Structure):
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("narrays", C.c_int32), ("presence_kind", C.c_int32),
+                ("presence_array", C.c_int32), ("ops", C.c_int32 * PEER_MAX_ARRAYS),
+                ("array_off", C.c_int64 * PEER_MAX_ARRAYS), ("bitmap_off", C.c_int64), ("signal_off", C.c_int64),
+                ("peer_base", C.c_void_p * MAX_PEERS), ("out", C.c_void_p * PEER_MAX_ARRAYS),
+                ("out_present", C.c_void_p), ("lo", C.c_int64), ("count", C.c_int64), ("local_ready", C.c_void_p),
+                ("epoch", C.c_uint64)]
 
 
 assert C.sizeof(Col) == 24 and C.sizeof(Term) == 32 and C.sizeof(Scan) == 656
 assert C.sizeof(AggState) == 152 and C.sizeof(Instr) == 24 and C.sizeof(Prog) == 1544
-assert C.sizeof(JoinTable) == 152 and C.sizeof(StarLookup) == 56
+assert C.sizeof(JoinTable) == 152 and C.sizeof(StarLookup) == 48 and C.sizeof(PeerMerge) == 544
 
 
 class B200SqlError(RuntimeError):
@@ -165,12 +178,13 @@ _SIGS = {
                            C.POINTER(C.c_int32), _P, C.POINTER(_P), _P, _P],
     "b2_iota": [_P, C.c_int64, _P],
     "b2_bitmap_or": [_P, _P, C.c_int64, _P],
+    "b2_peer_merge": [C.POINTER(PeerMerge), _P],
     "b2_sort_by": [C.POINTER(Col), C.c_int64, C.c_int32, C.c_int32, _P, _P, _P],
     "b2_dense_slots": [C.POINTER(Col), C.c_int64, C.c_int64, C.c_int32, _P, _P],
     "b2_star_build_dense": [C.POINTER(Col), _P, C.c_int64, _P, C.c_int64, C.c_int64, _P, _P, _P],
     "b2_star_build_scan": [C.POINTER(Scan), C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int32, _P,
                            _P, _P],
-    "b2_star_build_hash": [C.POINTER(Col), _P, C.c_int64, _P, _P, _P, C.c_int64, _P, _P],
+    "b2_star_build_hash": [C.POINTER(Col), _P, C.c_int64, _P, _P, C.c_int64, _P, _P],
     "b2_star_agg": [C.POINTER(Scan), C.c_int32, C.POINTER(StarLookup), C.POINTER(Agg), C.c_int32,
                     C.POINTER(AggState), _P],
 }
@@ -250,6 +264,7 @@ range_partition_scatter = _wrap("b2_range_partition_scatter")
 range_partition_ws_bytes = _lib.b2_range_partition_ws_bytes
 iota = _wrap("b2_iota")
 bitmap_or = _wrap("b2_bitmap_or")
+peer_merge = _wrap("b2_peer_merge")
 sort_by = _wrap("b2_sort_by")
 _lib.b2_sort_ws_bytes.restype = C.c_int64
 _lib.b2_sort_ws_bytes.argtypes = [C.c_int64]

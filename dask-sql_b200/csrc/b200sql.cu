@@ -38,6 +38,7 @@ int b2_sm_count() {
 #include "joinagg.cuh"
 #include "sort.cuh"
 #include "partition.cuh"
+#include "peer.cuh"
 
 extern "C" {
 

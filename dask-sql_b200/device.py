@@ -401,7 +401,7 @@ class GroupTable:
     """Caller-owned accumulator arrays of one group-by (dense / hash1 / hashk)."""
 
     def __init__(self, device, nslots, agg_specs, agg_dtypes, need_cnt, need_rows, need_present, indicator=None,
-                 alloc=None):
+                 alloc=None, new=None):
         """alloc: number of slots to allocate (>= nslots; the kernels only ever touch the first nslots).
         A table whose partial results are reduce-scattered over the ranks is padded to a multiple of
         32 x world size so that every rank's slice -- and its share of a presence bitmap -- is aligned.
@@ -410,7 +410,13 @@ class GroupTable:
         instead of +0.0; the kernels add x + 0.0 (never -0.0), so a slot still holding the -0.0 bit
         pattern (= INT64_MIN = EMPTY_KEY) received no row.  That makes the accumulator itself the
         "group exists" flag and saves the per-row presence-bitmap lookup (an L1 wavefront per row on
-        a path whose bound is the SM's load/store issue rate)."""
+        a path whose bound is the SM's load/store issue rate).
+
+        new: optional allocator `new(n, torch dtype, fill value) -> tensor` for the arrays (a prepared
+        multi-GPU query places them in symmetric memory so that peers can read them over NVLink)."""
+        if new is None:
+            def new(n, dtype, fill):
+                return torch.full((n,), fill, dtype=dtype, device=device)
         self.device, self.nslots = device, nslots
         self.alloc = alloc = max(int(alloc or nslots), nslots)
         self.indicator = indicator
@@ -423,22 +429,22 @@ class GroupTable:
             acc = cnt = None
             if col >= 0 and op != L.AGG_COUNT:
                 if op == L.AGG_MIN:
-                    acc = torch.full((alloc,), (1 << 63) - 1, dtype=torch.int64, device=device)
+                    acc = new(alloc, torch.int64, (1 << 63) - 1)
                 elif op == L.AGG_MAX:
-                    acc = torch.full((alloc,), -(1 << 63), dtype=torch.int64, device=device)
+                    acc = new(alloc, torch.int64, -(1 << 63))
                 elif op == L.AGG_SUMF or dt == F64:
-                    acc = torch.full((alloc,), -0.0 if a == indicator else 0.0, dtype=torch.float64, device=device)
+                    acc = new(alloc, torch.float64, -0.0 if a == indicator else 0.0)
                 else:
-                    acc = torch.zeros(alloc, dtype=torch.int64, device=device)
+                    acc = new(alloc, torch.int64, 0)
             if col >= 0 and (op == L.AGG_COUNT or need_cnt[a]):
-                cnt = torch.zeros(alloc, dtype=torch.int64, device=device)
+                cnt = new(alloc, torch.int64, 0)
             self.acc.append(acc)
             self.cnt.append(cnt)
             self.state.acc[a] = acc.data_ptr() if acc is not None else 0
             self.state.cnt[a] = cnt.data_ptr() if cnt is not None else 0
-        self.rows = torch.zeros(alloc, dtype=torch.int64, device=device) if need_rows else None
+        self.rows = new(alloc, torch.int64, 0) if need_rows else None
         need_present = need_present and indicator is None
-        self.present = torch.zeros(bitmap_words(alloc), dtype=torch.int32, device=device) if need_present else None
+        self.present = new(bitmap_words(alloc), torch.int32, 0) if need_present else None
         self.state.rows = self.rows.data_ptr() if self.rows is not None else 0
         self.state.present = self.present.data_ptr() if self.present is not None else 0
 

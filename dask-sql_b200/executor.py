@@ -946,13 +946,13 @@ def _padded_slots(nslots: int, sharded: bool) -> int:
 class GroupState:
     """Accumulators + key storage of one GROUP BY, independent of how slots are found."""
 
-    def __init__(self, dev, nslots, plan: AggPlan, need_present, force_rows=False, alloc=None):
+    def __init__(self, dev, nslots, plan: AggPlan, need_present, force_rows=False, alloc=None, new=None):
         need_rows = plan.need_rows or force_rows
         specs = [(0, ka.op) for ka in plan.kaggs]
         self.table = D.GroupTable(dev, nslots, specs, [ka.dtype for ka in plan.kaggs],
                                   [ka.need_cnt for ka in plan.kaggs], need_rows,
                                   need_present and not need_rows,
-                                  indicator=None if need_rows else plan.indicator, alloc=alloc)
+                                  indicator=None if need_rows else plan.indicator, alloc=alloc, new=new)
         self.plan = plan
         self.nslots = nslots
 
@@ -1634,8 +1634,12 @@ class PreparedStar:
             ok = torch.tensor([1 if prep is not None else 0], dtype=torch.int64, device=dev)
             if int(P.allreduce_(ok, "min").item()) == 0:
                 prep = None
-            elif bcast:
-                prep.group = P.build_group()
+            else:
+                if bcast:
+                    prep.group = P.build_group()
+                if sharded and P.peer_memory_available():
+                    # collective (symmetric allocation + handle exchange): entered by all ranks or by none
+                    prep.enable_peer_merge()
         cache[key] = prep
         if prep is not None:
             src.__dict__["_prepared_last"] = ((P.world()[1], _dev().index), prep)
@@ -1688,20 +1692,14 @@ class PreparedStar:
             lk = L.StarLookup()
             lk.dense, lk.lookup, lk.kmin, lk.range = 1, buf.data_ptr(), self.pmin, self.prange
             self.lk.append(lk)
-        self.gs = GroupState(dev, self.nslots, self.plan, need_present=True, alloc=_padded_slots(self.nslots, sharded))
-        t = self.gs.table
-        self.refill = []          # (tensor, initial value) of every accumulator array
-        for a, acc in enumerate(t.acc):
-            if acc is not None:
-                self.refill.append((acc, float(acc[0].item()) if acc.dtype == torch.float64 else int(acc[0].item())))
-        for cnt in t.cnt:
-            if cnt is not None:
-                self.refill.append((cnt, 0))
-        if t.rows is not None:
-            self.refill.append((t.rows, 0))
-        if t.present is not None:
-            self.refill.append((t.present, 0))
-        self.dirty = False        # a fresh table is already initialised
+        # group tables: ONE (re-initialised per run) on the NCCL / single-GPU path; enable_peer_merge()
+        # replaces it with two in symmetric memory that alternate run by run
+        self.tabs = [GroupState(dev, self.nslots, self.plan, need_present=True,
+                                alloc=_padded_slots(self.nslots, sharded))]
+        self.refill = [self._refill_list(self.tabs[0].table)]
+        self.dirty = [False]      # a fresh table is already initialised
+        self.peer = None          # per-table b2_peer_merge descriptors once enabled
+        self.epoch = 0
         self.group = None         # set by get() once all ranks agreed on the prepared path
         self.build_stream = torch.cuda.Stream(device=dev)
         self.build_ptr = C.c_void_p(self.build_stream.cuda_stream)
@@ -1709,6 +1707,90 @@ class PreparedStar:
         self.free = [None, None]  # event after which ring buffer i may be overwritten
         self.merge_bufs = {}      # presence / reduce-scatter outputs, reused run after run
         self.runs = 0
+
+    @staticmethod
+    def _refill_list(t: D.GroupTable):
+        """(tensor, initial value) of every array of the table: what a run has to restore first."""
+        out = []
+        for acc in t.acc:
+            if acc is not None:
+                out.append((acc, float(acc[0].item()) if acc.dtype == torch.float64 else int(acc[0].item())))
+        for cnt in t.cnt:
+            if cnt is not None:
+                out.append((cnt, 0))
+        if t.rows is not None:
+            out.append((t.rows, 0))
+        if t.present is not None:
+            out.append((t.present, 0))
+        return out
+
+    def enable_peer_merge(self):
+        """Move the group tables into symmetric memory and describe the merge to b2_peer_merge: one
+        kernel per step (barrier + reduction of this rank's slot range over every peer's table + merge
+        of existence, csrc/peer.cuh) instead of a presence pass and two to five NCCL reduce-scatters.
+        Two tables alternate, so that a table is refilled only after all peers have read it (see peer.cuh)."""
+        rank, size = P.world()
+        dev = self.dev
+        alloc = _padded_slots(self.nslots, True)
+        proto = self.tabs[0].table
+        narr = sum(a is not None for a in proto.acc) + sum(c is not None for c in proto.cnt) + (proto.rows is not None)
+        per_table = (narr * alloc * 8 + D.bitmap_words(alloc) * 4) + (narr + 2) * P.PeerArena.ALIGN
+        arena = P.PeerArena(2 * per_table + 4 * P.PeerArena.ALIGN, dev)
+        _, sig_off = arena.carve(L.MAX_PEERS, torch.int64, 0)
+        chunk = alloc // size
+        self.tabs, self.refill, self.dirty, self.peer = [], [], [], []
+        self.local_ready = torch.zeros(1, dtype=torch.int64, device=dev)
+        for _ in range(2):
+            offs = {}
+
+            def new(n, dtype, fill, offs=offs):
+                t, off = arena.carve(n, dtype, fill)
+                offs[t.data_ptr()] = off
+                return t
+
+            gs = GroupState(dev, self.nslots, self.plan, need_present=True, alloc=alloc, new=new)
+            t = gs.table
+            m = L.PeerMerge()
+            m.world, m.rank, m.lo, m.count = size, rank, rank * chunk, chunk
+            m.signal_off = sig_off
+            m.local_ready = self.local_ready.data_ptr()
+            for p_, b in enumerate(arena.base):
+                m.peer_base[p_] = b
+            arrays, accs, cnts, rows = [], [], [], None      # arrays: (tensor, op) in the kernel's order
+            for ka, acc, cnt in zip(self.plan.kaggs, t.acc, t.cnt):
+                if acc is not None:
+                    op = {L.AGG_MIN: L.PEER_MIN_I64, L.AGG_MAX: L.PEER_MAX_I64}.get(
+                        ka.op, L.PEER_SUM_F64 if acc.dtype == torch.float64 else L.PEER_SUM_I64)
+                    arrays.append((acc, op))
+                if cnt is not None:
+                    arrays.append((cnt, L.PEER_SUM_I64))
+            if t.rows is not None:
+                arrays.append((t.rows, L.PEER_SUM_I64))
+            outs = {}
+            for a, (src, op) in enumerate(arrays):
+                m.ops[a], m.array_off[a] = op, offs[src.data_ptr()]
+                outs[src.data_ptr()] = torch.empty(chunk, dtype=src.dtype, device=dev)
+                m.out[a] = outs[src.data_ptr()].data_ptr()
+            m.narrays = len(arrays)
+            index = {src.data_ptr(): a for a, (src, _) in enumerate(arrays)}
+            if t.rows is not None:
+                m.presence_kind, m.presence_array = L.PEER_PRESENT_ROWS, index[t.rows.data_ptr()]
+            elif t.indicator is not None:
+                m.presence_kind, m.presence_array = L.PEER_PRESENT_INDICATOR, index[t.acc[t.indicator].data_ptr()]
+            else:
+                m.presence_kind, m.presence_array = L.PEER_PRESENT_BITMAP, 0
+                m.bitmap_off = offs[t.present.data_ptr()]
+            pres = torch.empty(chunk, dtype=torch.uint8, device=dev)
+            m.out_present = pres.data_ptr()
+            pick = lambda x: None if x is None else outs[x.data_ptr()]
+            view = SlotView(t.nslots, rank * chunk, chunk, [pick(a) for a in t.acc], [pick(c) for c in t.cnt],
+                            pick(t.rows), "bytes", pres, dist="keyrange")
+            self.tabs.append(gs)
+            self.refill.append(self._refill_list(t))
+            self.dirty.append(False)
+            self.peer.append((m, view))
+        self.arena = arena
+        stats["peer_merge_plans"] = stats.get("peer_merge_plans", 0) + 1
 
     @staticmethod
     def _resident_parts(table, needed):
@@ -1764,19 +1846,30 @@ class PreparedStar:
         # ---- probe side on the caller's stream
         with _Phase("wait_build"):
             main.wait_event(self.built[i])
-        t = self.gs.table
+        ti = i if self.peer is not None else 0
+        t = self.tabs[ti].table
         with _Phase("scan"):
-            if self.dirty:
-                for tensor, value in self.refill:
+            if self.dirty[ti]:
+                for tensor, value in self.refill[ti]:
                     tensor.fill_(value)
-            self.dirty = True
+            self.dirty[ti] = True
             sp = D.stream_ptr()
             for scan, fk_slot, aggs_arr, naggs, n in self.fact_launch:
                 stats["launches"] += 1
                 ev = _kernel_event_begin("b2_star_agg_kernel", n)
                 L.star_agg(C.byref(scan), fk_slot, C.byref(self.lk[i]), aggs_arr, naggs, C.byref(t.state), sp)
                 _kernel_event_end(ev)
-        view = _merge_dense(t, self.plan, self.sharded, self.dev, keep=self.merge_bufs)
+        if self.peer is not None:
+            m, view = self.peer[ti]
+            self.epoch += 1
+            m.epoch = self.epoch
+            with _Phase("peer_merge"):
+                stats["launches"] += 1
+                ev = _kernel_event_begin("b2_peer_merge_kernel", m.count)
+                L.peer_merge(C.byref(m), sp)
+                _kernel_event_end(ev)
+        else:
+            view = _merge_dense(t, self.plan, self.sharded, self.dev, keep=self.merge_bufs)
         stats["star_fused"] += 1
 
         def general():   # a duplicate build key showed up: the general path redoes the query
@@ -2015,13 +2108,15 @@ def try_star(src: AggSource, child: LazyFrame, gexprs, aggs, pred, sharded, allo
                            D.ptr(flags), D.stream_ptr())
         lk.dense, lk.lookup, lk.kmin, lk.range = 1, lookup.data_ptr(), pst.vmin, prange
     else:
-        lcap = D._pow2_at_least(max(1024, 2 * d.n))
-        ltk = torch.full((lcap,), L.EMPTY_KEY, dtype=torch.int64, device=dev)
-        lts = torch.full((lcap,), -1, dtype=torch.int32, device=dev)
+        # {key, slot} entries of 16 bytes, twice as many as build rows (any size: the home entry is a
+        # multiply-shift of the hash, not a mask)
+        lcap = max(1024, 2 * d.n)
+        ltab = torch.empty(2 * lcap, dtype=torch.int64, device=dev)
+        ltab[0::2] = L.EMPTY_KEY
         stats["launches"] += 1
-        L.star_build_hash(C.byref(pks), None, d.n, D.ptr(slot_of_row), D.ptr(ltk), D.ptr(lts), lcap,
-                          D.ptr(flags), D.stream_ptr())
-        lk.dense, lk.table_keys, lk.table_slots, lk.cap = 0, ltk.data_ptr(), lts.data_ptr(), lcap
+        L.star_build_hash(C.byref(pks), None, d.n, D.ptr(slot_of_row), D.ptr(ltab), lcap, D.ptr(flags),
+                          D.stream_ptr())
+        lk.dense, lk.table, lk.cap = 0, ltab.data_ptr(), lcap
     fl = flags.cpu().tolist()
     if fl[0] or fl[1]:
         return None  # duplicate build keys (or overflow): the general join path handles it

@@ -138,6 +138,54 @@ def build_group():
     return _BUILD_GROUP
 
 
+class PeerArena:
+    """One allocation per rank that EVERY rank of the job has mapped (NVLink / NVSwitch peer memory):
+    torch.distributed._symmetric_memory allocates it with the CUDA VMM API and exchanges the handles
+    through the process group's store -- memory and mapping only, no torch kernel ever touches it.
+    carve() hands out 256-byte aligned views of this rank's copy; `base[p]` is rank p's copy as mapped
+    into this process (what b2_peer_merge dereferences); offsets are identical on all ranks because
+    every rank carves in the same order."""
+
+    ALIGN = 256
+
+    def __init__(self, nbytes: int, device):
+        import torch.distributed._symmetric_memory as symm
+        nbytes = (int(nbytes) + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        self.buf = symm.empty(nbytes, dtype=torch.uint8, device=device)
+        self.buf.zero_()
+        self.hdl = symm.rendezvous(self.buf, dist.group.WORLD)
+        self.base = [int(p) for p in self.hdl.buffer_ptrs]
+        rank, size = world()
+        if len(self.base) != size or self.base[rank] != self.buf.data_ptr():
+            raise RuntimeError("symmetric memory rendezvous returned an unexpected mapping")
+        self.nbytes, self.used = nbytes, 0
+        torch.cuda.synchronize(device)
+        dist.barrier()                     # every rank's copy is zeroed before anyone signals into it
+
+    def carve(self, n: int, dtype, fill=0):
+        """(view of n elements of `dtype` in this rank's copy, filled; its byte offset in every copy)"""
+        width = torch.empty((), dtype=dtype).element_size()
+        off = self.used
+        nb = (n * width + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        if off + nb > self.nbytes:
+            raise MemoryError("peer arena exhausted")
+        self.used = off + nb
+        t = self.buf[off: off + n * width].view(dtype)
+        t.fill_(fill)
+        return t, off
+
+
+def peer_memory_available() -> bool:
+    """NCCL job on one node whose torch build has symmetric memory; B200SQL_PEER_MERGE=0 turns it off."""
+    if os.environ.get("B200SQL_PEER_MERGE") == "0" or world()[1] < 2 or _backend() != "nccl":
+        return False
+    try:
+        import torch.distributed._symmetric_memory  # noqa: F401
+    except Exception:
+        return False
+    return True
+
+
 def broadcast_(t: torch.Tensor, src: int = 0, group=None) -> torch.Tensor:
     if world()[1] > 1:
         _timed("broadcast", dist.broadcast, t, src=src, group=group)

@@ -284,6 +284,49 @@ int32_t b2_groupby_hashk(const b2_scan_t* scan, const int32_t* key_cols, int32_t
  * after an all-gather (NCCL has no bitwise reduction). */
 int32_t b2_bitmap_or(uint32_t* dst, const uint32_t* src, int64_t nwords, void* stream);
 
+/* ---- multi-GPU merge of dense partial tables over NVLink peer memory ----------------------
+ * Replaces dask's tree reduction of per-partition partial aggregates (aggregate.py:575-581,
+ * `groupby(...).agg(..., split_every)`; tests/integration/test_groupby.py:526-598) for
+ * direct-address tables, with split_out = world size: ONE kernel per GPU does the cross-GPU
+ * barrier, the reduction of this rank's slot range over all peers' tables (read through peer
+ * mappings of a symmetric allocation), and the merge of group existence.
+ *
+ * Every rank holds the same layout inside a buffer that all ranks have mapped: peer_base[p] is
+ * rank p's buffer as seen from THIS process.  array_off[a] = byte offset of 8-byte-per-slot array
+ * a, bitmap_off = offset of the presence bitmap (LSB order), signal_off = offset of
+ * uint64[B2_MAX_PEERS] zero-initialised signal words used by the in-kernel barrier.  epoch must
+ * increase by one per call on all ranks (same sequence everywhere); local_ready is a zero-
+ * initialised uint64 in this GPU's memory.  out[a] receives count merged elements (slots
+ * [lo, lo+count) of the table), out_present one byte per slot (1 = some rank saw the group).
+ * Arrays are combined in rank order 0..world-1 (bit-reproducible float sums).
+ * The caller double-buffers the tables: the table of call k may be rewritten once call k+1 has
+ * been enqueued on this rank's stream. */
+#define B2_MAX_PEERS        16
+#define B2_PEER_MAX_ARRAYS  (2 * B2_MAX_AGGS + 1)
+#define B2_PEER_SUM_F64 0
+#define B2_PEER_SUM_I64 1   /* wraps (two's complement), like the single-GPU accumulators */
+#define B2_PEER_MIN_I64 2   /* MIN / MAX accumulators hold int64 values or ordered images of doubles */
+#define B2_PEER_MAX_I64 3
+#define B2_PEER_PRESENT_ROWS      1   /* group exists iff merged array[presence_array] > 0 */
+#define B2_PEER_PRESENT_INDICATOR 2   /* ... iff some rank's array[presence_array] bits != B2_EMPTY_KEY (-0.0) */
+#define B2_PEER_PRESENT_BITMAP    3   /* ... iff some rank's bitmap bit is set */
+typedef struct b2_peer_merge {
+  int32_t   world, rank;
+  int32_t   narrays;
+  int32_t   presence_kind, presence_array;
+  int32_t   ops[B2_PEER_MAX_ARRAYS];
+  int64_t   array_off[B2_PEER_MAX_ARRAYS];
+  int64_t   bitmap_off;
+  int64_t   signal_off;
+  void*     peer_base[B2_MAX_PEERS];
+  void*     out[B2_PEER_MAX_ARRAYS];
+  uint8_t*  out_present;
+  int64_t   lo, count;                /* multiples of 32 */
+  uint64_t* local_ready;
+  uint64_t  epoch;
+} b2_peer_merge_t;
+int32_t b2_peer_merge(const b2_peer_merge_t* m, void* stream);
+
 /* bit-exact order-preserving double<->int64 images used by float MIN/MAX accumulators */
 int64_t b2_f64_to_ordered(double x);
 double  b2_ordered_to_f64(int64_t k);
@@ -475,11 +518,14 @@ int32_t b2_star_build_dense(const b2_col_t* pk, const int32_t* sel, int64_t n_se
 int32_t b2_star_build_scan(const b2_scan_t* scan, int32_t pk_col, int32_t grp_col, int64_t pk_min,
                            int64_t pk_range, int64_t grp_min, int32_t null_slot, int32_t* lookup,
                            int32_t* d_flags, void* stream);
-/* Hash variant: table_keys = int64[cap] pre-filled with B2_EMPTY_KEY, table_slots = int32[cap].
- * d_flags[0] = 1 on duplicate pk, d_flags[1] = 1 on overflow. */
+/* Hash variant (primary keys too sparse for a direct-address array): table = int64[2*cap], entry h =
+ * {table[2h] = key, table[2h+1] = slot}, every key word pre-filled with B2_EMPTY_KEY; cap >= 2 is ANY
+ * size (home entry = mulhi64(mix(key), cap), linear probing with wrap-around), typically 2x the build
+ * rows.  A probe is one 16-byte load.  d_flags[0] = 1 on duplicate pk, d_flags[1] = 1 on overflow or
+ * a key equal to B2_EMPTY_KEY. */
 int32_t b2_star_build_hash(const b2_col_t* pk, const int32_t* sel, int64_t n_sel,
-                           const int32_t* slot_of_row, int64_t* table_keys, int32_t* table_slots,
-                           int64_t cap, int32_t* d_flags, void* stream);
+                           const int32_t* slot_of_row, int64_t* table, int64_t cap,
+                           int32_t* d_flags, void* stream);
 
 typedef struct b2_starlookup {
   int32_t dense;
@@ -487,8 +533,7 @@ typedef struct b2_starlookup {
   const int32_t* lookup;   /* dense: int32[range], -1 = no partner */
   int64_t kmin;
   int64_t range;
-  const int64_t* table_keys;  /* hash */
-  const int32_t* table_slots;
+  const int64_t* table;    /* hash: int64[2*cap] {key, slot} entries, 16-byte aligned */
   int64_t cap;
 } b2_starlookup_t;
 

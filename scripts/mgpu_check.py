@@ -58,12 +58,24 @@ def main():
     before = executor.stats["star_fused"]
     q3 = """SELECT d.grp, SUM(f.val) AS rev FROM fact f JOIN dim d ON f.fk = d.pk
             WHERE f.x > 0 AND d.flag < 5 GROUP BY d.grp"""
-    got = c.sql(q3, return_futures=False)
-    assert executor.stats["star_fused"] == before + 1
     e = fact[fact.x > 0].merge(dim[dim.flag < 5], left_on="fk", right_on="pk")
     exp = e.groupby("grp", dropna=False).agg(rev=("val", "sum")).reset_index()
     assert len(exp) < 0.5 * 60_000, "the check needs never-hit group slots"
-    check(got, exp, ["grp"], ["rev"])
+    for rep in range(5):      # repeated: the prepared plan alternates its two lookup buffers / peer tables
+        got = c.sql(q3, return_futures=False)
+        assert executor.stats["star_fused"] == before + 1 + rep
+        check(got, exp, ["grp"], ["rev"])
+    from dask_sql_b200 import parallel as P
+    if P.peer_memory_available():
+        assert executor.stats.get("peer_merge_plans", 0) >= 1, "the NVLink peer merge was not used"
+    # the same through the NCCL reduce-scatter path (fresh Context: plans are prepared per Context)
+    os.environ["B200SQL_PEER_MERGE"] = "0"
+    c2 = Context()
+    c2.create_table("fact", fact.iloc[lo:hi], persist=True, npartitions=3, distribution="sharded")
+    c2.create_table("dim", dim if rank == 0 else dim.iloc[:0], persist=True, distribution="root")
+    for rep in range(2):
+        check(c2.sql(q3, return_futures=False), exp, ["grp"], ["rev"])
+    del os.environ["B200SQL_PEER_MERGE"]
     # 1b. the same with COUNT(*) (row counter instead of the -0.0 indicator) and an int SUM (bitmap)
     got = c.sql("""SELECT d.grp, COUNT(*) AS n, SUM(f.x) AS sx FROM fact f JOIN dim d ON f.fk = d.pk
                    WHERE d.flag < 5 GROUP BY d.grp""", return_futures=False)
