@@ -589,9 +589,15 @@ def run_e2e(args, torch, dist, dev, world, rank, fk, x, val, pk, flag, grp, fact
 # ---------------------------------------------------------------------------------------------
 def _time_query(torch, executor, c, sql, steps, warmup, kernel_names):
     """(ms per step, kernel events, parts of the last step) of c.sql(sql) executed on the device."""
+    # The warm-up runs exactly like the timed loop -- results are NOT resolved between steps, so a step
+    # allocates while the previous step's outputs are still alive -- or the caching allocator meets a new
+    # pattern inside the timed region and stalls the stream behind cudaMalloc / cudaFree (seen as a 1-19 ms
+    # hole in a phase that otherwise takes 0.04-2.4 ms).
     parts = None
-    for _ in range(warmup):
-        parts = executor.execute(c.sql(sql), top=True)
+    for _ in range(2):
+        for _ in range(max(warmup, steps)):
+            parts = executor.execute(c.sql(sql), top=True)
+        torch.cuda.synchronize()
         for p in parts:
             p.resolve()
     torch.cuda.synchronize()
@@ -639,9 +645,11 @@ def run_configs(args, torch, dev, peak_gbs, peak_src, traffic):
     steps, warmup = max(3, min(args.steps, 5)), max(3, min(args.warmup, 3))
     out = {}
 
-    # the SM -> L2 request path serves ~200 G random 4/8-byte requests per second on this part
+    # the L2 serves ~200 G REDG (reduction atomics without return value) per second on this part
     # (scripts/microbench/redg.cu "red_spread f64_1red", L2-resident table; profiles/r02_redg.jsonl): the
-    # second roofline of the hash stages ("random 32 B-sector throughput ... report it")
+    # second roofline of the group-by stage, which issues one per row ("random 32 B-sector
+    # throughput ... report it").  Plain random LOADS are served faster than that (C3f sustains 287 G/s), so
+    # the figure is attached to the REDG kernels only.
     L2_REQ_PEAK = 200.7
 
     def entry(name, rows, ms, kev, kernel, bytes_per_row, launches, query, verified, extra=None, random_per_row=None):
@@ -657,7 +665,7 @@ def run_configs(args, torch, dev, peak_gbs, peak_src, traffic):
             r = e["roofline"]
             rows_l = r["algorithmic_bytes_per_launch"] / r["algorithmic_bytes_per_row"]
             ach = rows_l * random_per_row / (r["avg_launch_ms"] * 1e-3) / 1e9
-            e["roofline_l2_requests"] = {"kernel": kernel, "bound": "SM->L2 random request rate", "unit": "G requests/s",
+            e["roofline_l2_requests"] = {"kernel": kernel, "bound": "L2 reduction-atomic (REDG) rate", "unit": "G requests/s",
                                          "random_requests_per_row": random_per_row, "achieved": ach, "peak": L2_REQ_PEAK,
                                          "frac": ach / L2_REQ_PEAK,
                                          "peak_source": "measured: scripts/microbench/redg.cu, one REDG.F64 per row into "
@@ -758,7 +766,7 @@ def run_configs(args, torch, dev, peak_gbs, peak_src, traffic):
             rel = abs(got - exp) / max(abs(exp), 1e-300)
             entry(name, n, ms, kev, "b2_join_agg_kernel", 16, nl, q, {"ok": rel <= 1e-9, "rel_err": rel},
                   {"match_rate": n_match / n, "dim_rows": ndim, "partitions": 8,
-                   "algorithmic_bytes": "16 B per fact row (fk, v) + 16 B per dim row"}, random_per_row=1.0)
+                   "algorithmic_bytes": "16 B per fact row (fk, v) + 16 B per dim row"})
         else:
             q = "SELECT f.fk, f.v, d.w FROM fact f JOIN dim d ON f.fk = d.pk"
             ms, kev, parts, nl = _time_query(torch, executor, c, q, steps, warmup, ())
@@ -802,8 +810,7 @@ def run_configs(args, torch, dev, peak_gbs, peak_src, traffic):
                    "checked": "row count, integer column checksums exact, float checksum 1e-9, partition 0's rows "
                               "one by one as a multiset"},
                   {"match_rate": n_match / n, "dim_rows": ndim, "partitions": 8,
-                   "algorithmic_bytes": "16 B read per fact row + 24 B written per output row (+16 B per dim row)"},
-                  random_per_row=1.0)
+                   "algorithmic_bytes": "16 B read per fact row + 24 B written per output row (+16 B per dim row)"})
 
     # ---- C4 with a sparse primary key: the pk -> slot lookup is a hash table, not a direct-address array
     def c4s():

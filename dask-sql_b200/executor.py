@@ -1260,8 +1260,6 @@ def _merge_dense(t: D.GroupTable, plan: AggPlan, sharded: bool, dev, keep=None) 
         return SlotView.whole(t)
     assert t.alloc % (32 * size) == 0, "sharded group tables are padded to 32 x world slots"
     chunk = t.alloc // size
-    if keep is None and os.environ.get("B200SQL_MERGE") == "rs_persist":
-        keep = t.__dict__.setdefault("_rs_out", {})
     # keep: buffers of a prepared query, reused run after run.  Tensors handed to a collective are tied
     # to the communicator's stream by the allocator; fresh ones every run cannot be recycled while the
     # host is ahead of the GPU, and every run then pays cudaMalloc for its lookup and table buffers.
@@ -1273,47 +1271,24 @@ def _merge_dense(t: D.GroupTable, plan: AggPlan, sharded: bool, dev, keep=None) 
                 pbuf = keep["pres_in"] = torch.empty(t.alloc, dtype=torch.uint8, device=dev)
         pres = _presence_bytes(t, dev, out=pbuf)
         stats["launches"] += 1
-    mode = os.environ.get("B200SQL_MERGE", "reduce_scatter")      # diagnostics: "allreduce" | "rs_persist"
-    with _Phase("reduce_scatter"):
-        if mode == "allreduce":
-            lo = rank * chunk
-            accs, cnts = [], []
-            for ka, acc, cnt in zip(plan.kaggs, t.acc, t.cnt):
-                accs.append(None if acc is None else
-                            P.allreduce_(acc, {L.AGG_MIN: "min", L.AGG_MAX: "max"}.get(ka.op, "sum"))[lo:lo + chunk])
-                cnts.append(None if cnt is None else P.allreduce_(cnt, "sum")[lo:lo + chunk])
-            rows = None if t.rows is None else P.allreduce_(t.rows, "sum")[lo:lo + chunk]
-            pres = P.allreduce_(pres, "max")[lo:lo + chunk]
-        elif mode == "allreduce_f64":
-            # diagnostics: existence as float64 counts, summed -- only f64 SUM collectives on the wire
-            lo = rank * chunk
-            accs, cnts = [], []
-            for ka, acc, cnt in zip(plan.kaggs, t.acc, t.cnt):
-                accs.append(None if acc is None else
-                            P.allreduce_(acc, {L.AGG_MIN: "min", L.AGG_MAX: "max"}.get(ka.op, "sum"))[lo:lo + chunk])
-                cnts.append(None if cnt is None else P.allreduce_(cnt, "sum")[lo:lo + chunk])
-            rows = None if t.rows is None else P.allreduce_(t.rows, "sum")[lo:lo + chunk]
-            pres = (P.allreduce_(pres.to(torch.float64), "sum")[lo:lo + chunk] > 0).to(torch.uint8)
-        else:
-            def kept(key, like):
-                if keep is None:
-                    return None
-                buf = keep.get(key)
-                if buf is None:
-                    buf = keep[key] = torch.empty(chunk, dtype=like.dtype, device=dev)
-                return buf
 
-            accs, cnts = [], []
-            for i, (ka, acc, cnt) in enumerate(zip(plan.kaggs, t.acc, t.cnt)):
-                accs.append(None if acc is None else
-                            P.reduce_scatter_(acc, {L.AGG_MIN: "min", L.AGG_MAX: "max"}.get(ka.op, "sum"),
-                                              out=kept(("a", i), acc)))
-                cnts.append(None if cnt is None else P.reduce_scatter_(cnt, "sum", out=kept(("c", i), cnt)))
-            rows = None if t.rows is None else P.reduce_scatter_(t.rows, "sum", out=kept("r", t.rows))
-            pres = P.reduce_scatter_(pres, "max", out=kept("p", pres))
-        if os.environ.get("B200SQL_PROBE_AFTER_NCCL") == "1":
-            probe = t.__dict__.setdefault("_probe", torch.zeros(4, dtype=torch.int32, device=dev))
-            L.memset(C.c_void_p(probe.data_ptr()), 0, 16, D.stream_ptr())
+    def kept(key, like):
+        if keep is None:
+            return None
+        buf = keep.get(key)
+        if buf is None:
+            buf = keep[key] = torch.empty(chunk, dtype=like.dtype, device=dev)
+        return buf
+
+    with _Phase("reduce_scatter"):
+        accs, cnts = [], []
+        for i, (ka, acc, cnt) in enumerate(zip(plan.kaggs, t.acc, t.cnt)):
+            accs.append(None if acc is None else
+                        P.reduce_scatter_(acc, {L.AGG_MIN: "min", L.AGG_MAX: "max"}.get(ka.op, "sum"),
+                                          out=kept(("a", i), acc)))
+            cnts.append(None if cnt is None else P.reduce_scatter_(cnt, "sum", out=kept(("c", i), cnt)))
+        rows = None if t.rows is None else P.reduce_scatter_(t.rows, "sum", out=kept("r", t.rows))
+        pres = P.reduce_scatter_(pres, "max", out=kept("p", pres))
     return SlotView(t.nslots, rank * chunk, chunk, accs, cnts, rows, "bytes", pres, dist="keyrange")
 
 
@@ -1638,8 +1613,20 @@ class PreparedStar:
                 if bcast:
                     prep.group = P.build_group()
                 if sharded and P.peer_memory_available():
-                    # collective (symmetric allocation + handle exchange): entered by all ranks or by none
-                    prep.enable_peer_merge()
+                    # collective (symmetric allocation + handle exchange): entered by all ranks or by none.
+                    # A rank on which it fails (no peer access, mapping refused) says so and ALL ranks stay
+                    # on the NCCL merge.
+                    state, why = None, None
+                    try:
+                        state = prep.build_peer_merge()
+                    except Exception as e:  # noqa: BLE001 -- any failure means "no peer path", never a wrong result
+                        why = f"{type(e).__name__}: {e}"
+                    ok = torch.tensor([1 if state is not None else 0], dtype=torch.int64, device=dev)
+                    if int(P.allreduce_(ok, "min").item()) == 1:
+                        prep.install_peer_merge(state)
+                    elif why is not None:
+                        import warnings
+                        warnings.warn(f"NVLink peer merge unavailable, using ncclReduceScatter: {why}")
         cache[key] = prep
         if prep is not None:
             src.__dict__["_prepared_last"] = ((P.world()[1], _dev().index), prep)
@@ -1724,11 +1711,16 @@ class PreparedStar:
             out.append((t.present, 0))
         return out
 
-    def enable_peer_merge(self):
-        """Move the group tables into symmetric memory and describe the merge to b2_peer_merge: one
+    def install_peer_merge(self, state):
+        self.tabs, self.refill, self.dirty, self.peer, self.arena, self.local_ready = state
+        stats["peer_merge_plans"] = stats.get("peer_merge_plans", 0) + 1
+
+    def build_peer_merge(self):
+        """Group tables in symmetric memory and the description of their merge for b2_peer_merge: one
         kernel per step (barrier + reduction of this rank's slot range over every peer's table + merge
         of existence, csrc/peer.cuh) instead of a presence pass and two to five NCCL reduce-scatters.
-        Two tables alternate, so that a table is refilled only after all peers have read it (see peer.cuh)."""
+        Two tables alternate, so that a table is refilled only after all peers have read it (see peer.cuh).
+        Returns the state install_peer_merge() takes; nothing of `self` is touched before that."""
         rank, size = P.world()
         dev = self.dev
         alloc = _padded_slots(self.nslots, True)
@@ -1738,8 +1730,8 @@ class PreparedStar:
         arena = P.PeerArena(2 * per_table + 4 * P.PeerArena.ALIGN, dev)
         _, sig_off = arena.carve(L.MAX_PEERS, torch.int64, 0)
         chunk = alloc // size
-        self.tabs, self.refill, self.dirty, self.peer = [], [], [], []
-        self.local_ready = torch.zeros(1, dtype=torch.int64, device=dev)
+        tabs, refill, dirty, peer = [], [], [], []
+        local_ready = torch.zeros(1, dtype=torch.int64, device=dev)
         for _ in range(2):
             offs = {}
 
@@ -1753,7 +1745,7 @@ class PreparedStar:
             m = L.PeerMerge()
             m.world, m.rank, m.lo, m.count = size, rank, rank * chunk, chunk
             m.signal_off = sig_off
-            m.local_ready = self.local_ready.data_ptr()
+            m.local_ready = local_ready.data_ptr()
             for p_, b in enumerate(arena.base):
                 m.peer_base[p_] = b
             arrays, accs, cnts, rows = [], [], [], None      # arrays: (tensor, op) in the kernel's order
@@ -1785,12 +1777,11 @@ class PreparedStar:
             pick = lambda x: None if x is None else outs[x.data_ptr()]
             view = SlotView(t.nslots, rank * chunk, chunk, [pick(a) for a in t.acc], [pick(c) for c in t.cnt],
                             pick(t.rows), "bytes", pres, dist="keyrange")
-            self.tabs.append(gs)
-            self.refill.append(self._refill_list(t))
-            self.dirty.append(False)
-            self.peer.append((m, view))
-        self.arena = arena
-        stats["peer_merge_plans"] = stats.get("peer_merge_plans", 0) + 1
+            tabs.append(gs)
+            refill.append(self._refill_list(t))
+            dirty.append(False)
+            peer.append((m, view))
+        return tabs, refill, dirty, peer, arena, local_ready
 
     @staticmethod
     def _resident_parts(table, needed):
@@ -2110,7 +2101,7 @@ def try_star(src: AggSource, child: LazyFrame, gexprs, aggs, pred, sharded, allo
     else:
         # {key, slot} entries of 16 bytes, twice as many as build rows (any size: the home entry is a
         # multiply-shift of the hash, not a mask)
-        lcap = max(1024, 2 * d.n)
+        lcap = max(1024, 2 * d.n)              # even; two entries = one 32-byte bucket
         ltab = torch.empty(2 * lcap, dtype=torch.int64, device=dev)
         ltab[0::2] = L.EMPTY_KEY
         stats["launches"] += 1

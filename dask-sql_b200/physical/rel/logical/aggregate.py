@@ -81,7 +81,7 @@ class DaskAggregatePlugin(BaseRelPlugin):
 
         def value_of(rex) -> LazySeries:
             field = rex.column_name(input_rel)
-            if field in known._frontend_backend_mapping:             # a plain input column
+            if known.knows(field):             # a plain input column
                 return child.df[known.get_backend_by_frontend_name(field)]
             return RexConverter.convert(input_rel, rex, child, context=context)
 

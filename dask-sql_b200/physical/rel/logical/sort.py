@@ -16,7 +16,7 @@ class DaskSortPlugin(BaseRelPlugin):
         sort_columns, extra = [], {}
         for expr in sort_expressions:
             name = expr.column_name(rel)
-            if name in cc._frontend_backend_mapping:
+            if cc.knows(name):
                 sort_columns.append(cc.get_backend_by_frontend_name(name))
             else:  # ORDER BY <expression over output columns>
                 tmp = new_temporary_column(df)
