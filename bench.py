@@ -61,6 +61,10 @@ def parse_args():
     ap.add_argument("--cpu-sample-rows", type=float,
                     default=float(os.environ.get("B200SQL_CPU_SAMPLE_ROWS", 128e6)))
     ap.add_argument("--cpu-budget-s", type=float, default=float(os.environ.get("B200SQL_CPU_BUDGET_S", 150)))
+    ap.add_argument("--dim-dist", default=os.environ.get("B200SQL_BENCH_DIM", "replicated"), choices=["replicated", "root"],
+                    help="N>1: 'replicated' = every GPU holds the 10M-row dim table (registered once, before the timed "
+                         "region) and builds its own lookup every step; 'root' = rows on rank 0 only, the finished "
+                         "lookup is broadcast every step (NCCL)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-configs", action="store_true")
@@ -184,10 +188,13 @@ def workload_config(args, n):
             "planning": "Context.sql() is called every step; its plan (not its result) is served from the "
                         "prepared-statement cache after the first call; build side, lookup and group table "
                         "are rebuilt every step",
-            "parallelism": (f"fact sharded over {n} GPU(s); dim on rank 0, its pk->slot lookup broadcast every step "
-                            "(NCCL, second stream + communicator: overlaps the previous step's scan); dense partial "
-                            "aggregates merged by key range -- " + merge_kind() + " -- every rank compacts and keeps "
-                            "the groups of its range") if n > 1 else "single GPU"}
+            "parallelism": (f"fact sharded over {n} GPU(s); " +
+                            ("dim replicated (registered on every GPU before the timed region, as a broadcast-join "
+                             "engine keeps small dimension tables), every GPU builds its pk->slot lookup every step; "
+                             if args.dim_dist == "replicated" else
+                             "dim on rank 0, its pk->slot lookup broadcast every step (NCCL); ") +
+                            "dense partial aggregates merged by key range -- " + merge_kind() + " -- every rank "
+                            "compacts and keeps the groups of its range") if n > 1 else "single GPU"}
 
 
 def merge_kind():
@@ -339,11 +346,11 @@ def main():
     pk = torch.randperm(DIM_ROWS, device=dev, generator=gd)
     flag = torch.randint(0, 10, (DIM_ROWS,), dtype=torch.int64, device=dev, generator=gd)
     grp = torch.randint(0, N_GROUPS, (DIM_ROWS,), dtype=torch.int64, device=dev, generator=gd)
-    nd = DIM_ROWS if (rank == 0 or world == 1) else 0
+    dim_dist = "local" if world == 1 else args.dim_dist
+    nd = DIM_ROWS if (rank == 0 or dim_dist != "root") else 0
 
     c = Context()
     fact_dist = "sharded" if world > 1 else "local"
-    dim_dist = "root" if world > 1 else "local"
     c.create_table("fact", {"fk": fk, "x": x, "val": val}, persist=True, npartitions=parts_per_gpu(world),
                    distribution=fact_dist)
     c.create_table("dim", {"pk": pk[:nd], "flag": flag[:nd], "grp": grp[:nd]}, persist=True, distribution=dim_dist)

@@ -1579,12 +1579,12 @@ class PreparedStar:
     re-allocated, per run).  A step of a repeated query then costs the host a few dozen calls instead
     of re-deriving all of it -- at 8 GPUs a step is ~1 ms of device work, so host time IS the step time.
 
-    Two streams: the build side (lookup fill -> b2_star_build_scan -> NCCL broadcast) runs on its own
-    stream into one of two lookup buffers, the fact scan / merge / compaction on the caller's stream
-    after an event.  Consecutive executions therefore overlap: the next query's build + broadcast
-    proceeds under the current query's scan.  Buffer i is refilled only after the whole run that last
-    read it has been enqueued AND finished (event), so nothing is overwritten while in use; results
-    are always freshly allocated and never alias the reused buffers."""
+    One stream, in order: lookup fill -> b2_star_build_scan (every rank that holds dim rows; a 'root' table
+    is followed by one NCCL broadcast of the finished lookup) -> b2_star_agg per fact partition -> merge ->
+    compaction.  Two lookup buffers (and, with the NVLink peer merge, two group tables) alternate between
+    consecutive executions; buffer i is refilled only after the run that last read it has FINISHED
+    (event), which also bounds the host's run-ahead to two executions; results are always freshly
+    allocated and never alias the reused buffers."""
 
     _live: "List[PreparedStar]" = []
     MAX_LIVE = 4          # prepared plans keep ~100 MB of HBM each: keep only the most recent ones
@@ -1610,8 +1610,6 @@ class PreparedStar:
             if int(P.allreduce_(ok, "min").item()) == 0:
                 prep = None
             else:
-                if bcast:
-                    prep.group = P.build_group()
                 if sharded and P.peer_memory_available():
                     # collective (symmetric allocation + handle exchange): entered by all ranks or by none.
                     # A rank on which it fails (no peer access, mapping refused) says so and ALL ranks stay
@@ -1687,11 +1685,7 @@ class PreparedStar:
         self.dirty = [False]      # a fresh table is already initialised
         self.peer = None          # per-table b2_peer_merge descriptors once enabled
         self.epoch = 0
-        self.group = None         # set by get() once all ranks agreed on the prepared path
-        self.build_stream = torch.cuda.Stream(device=dev)
-        self.build_ptr = C.c_void_p(self.build_stream.cuda_stream)
-        self.built = [torch.cuda.Event() for _ in range(2)]
-        self.free = [None, None]  # event after which ring buffer i may be overwritten
+        self.free = [None, None]  # event recorded at the end of the run that last used ring buffer i
         self.merge_bufs = {}      # presence / reduce-scatter outputs, reused run after run
         self.runs = 0
 
@@ -1809,34 +1803,31 @@ class PreparedStar:
         self.runs += 1
         buf = self.ring[i]
         main = D.cur_stream()
-        bs = self.build_stream
-        # ---- build side on its own stream (phase events recorded there: they overlap the previous run's scan).
+        sp = D.stream_ptr()
         # The host waits here until the run before the previous one has FINISHED: at most two executions
         # of this query are in flight.  That hides the host's issue latency, and no more: letting the host
         # run many collectives ahead of the GPUs measurably stretches the steps (ranks drift apart and the
         # allocator cannot recycle buffers the communicator still holds).
         if self.free[i] is not None:
             self.free[i].synchronize()
-        with _Phase("build", bs):
+        # ---- build side, in order on the caller's stream.  (Round 2 first ran it on a second stream and
+        # communicator so that the next step's build + broadcast overlapped the current scan.  Measured at
+        # N=2 that LOSES: the scan kernels are persistent grids that fill every SM, so the build kernels wait
+        # for a whole fact partition anyway (0.75 ms "build" for 0.08 ms of work) and then compete with the
+        # scan for HBM -- b2_star_agg went from 0.577 to 0.723 ms per 125M rows, the step from 2.6 to 3.4 ms.)
+        with _Phase("build"):
             # lookup := -1 everywhere (0xFF bytes), the 4 flag words behind it := 0
-            L.memset(C.c_void_p(buf.data_ptr()), 0xFF, 4 * self.prange, self.build_ptr)
-            L.memset(C.c_void_p(buf.data_ptr() + 4 * self.prange), 0, 16, self.build_ptr)
+            L.memset(C.c_void_p(buf.data_ptr()), 0xFF, 4 * self.prange, sp)
+            L.memset(C.c_void_p(buf.data_ptr() + 4 * self.prange), 0, 16, sp)
             for scan, pk_slot, g_slot in self.dim_launch:
                 stats["launches"] += 1
                 L.star_build_scan(C.byref(scan), pk_slot, g_slot, self.pmin, self.prange, self.gmin,
                                   self.nslots - 1, C.c_void_p(buf.data_ptr()),
-                                  C.c_void_p(buf.data_ptr() + 4 * self.prange), self.build_ptr)
+                                  C.c_void_p(buf.data_ptr() + 4 * self.prange), sp)
         if self.bcast:
-            with _Phase("bcast", bs):
-                torch.cuda.set_stream(bs)          # torch.distributed orders the collective after the CURRENT stream
-                try:
-                    P.broadcast_(buf, 0, group=self.group)
-                finally:
-                    torch.cuda.set_stream(main)
-        self.built[i].record(bs)
-        # ---- probe side on the caller's stream
-        with _Phase("wait_build"):
-            main.wait_event(self.built[i])
+            with _Phase("bcast"):
+                P.broadcast_(buf, 0)
+        # ---- probe side
         ti = i if self.peer is not None else 0
         t = self.tabs[ti].table
         with _Phase("scan"):
@@ -1844,7 +1835,6 @@ class PreparedStar:
                 for tensor, value in self.refill[ti]:
                     tensor.fill_(value)
             self.dirty[ti] = True
-            sp = D.stream_ptr()
             for scan, fk_slot, aggs_arr, naggs, n in self.fact_launch:
                 stats["launches"] += 1
                 ev = _kernel_event_begin("b2_star_agg_kernel", n)

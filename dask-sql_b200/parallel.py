@@ -3,9 +3,11 @@ GPUs, gloo in the CPU tests).  Only the two exchange steps of the path use it (S
 
   * join build side   : broadcast of the dimension table's columns from its owner rank
                         (replaces dask's merge(broadcast=True), join.py:228-246)
-  * group-by partials : all-reduce of dense accumulator arrays, or a tree of pairwise
-                        send/recv + merge for hash tables, fan-in = sql.aggregate.split_every
-                        (replaces dask's tree reduction, aggregate.py:321,581)
+  * group-by partials : dense tables -> merged by slot range, every rank keeps one range: ONE kernel over
+                        NVLink peer memory for prepared plans (PeerArena + b2_peer_merge), else
+                        ncclReduceScatter per array; hash tables -> a tree of pairwise send/recv + merge,
+                        fan-in = sql.aggregate.split_every (replaces dask's tree reduction,
+                        aggregate.py:321,581)
 """
 from typing import List, Sequence, Tuple
 
@@ -37,7 +39,6 @@ def world() -> Tuple[int, int]:
         if dist.is_initialized():
             return _WORLD[0], _WORLD[1]
         _WORLD = None                      # the group was destroyed
-        globals()["_BUILD_GROUP"] = None
     if dist.is_available() and dist.is_initialized():
         _WORLD = (dist.get_rank(), dist.get_world_size(), dist.get_backend())
         return _WORLD[0], _WORLD[1]
@@ -124,20 +125,6 @@ def all_gather_ints(values: Sequence[int], device) -> List[List[int]]:
     return torch.stack(bufs).cpu().tolist()
 
 
-_BUILD_GROUP = None
-
-
-def build_group():
-    """A second communicator over the same ranks, used only for build-side broadcasts.  Collectives of
-    ONE communicator execute in issue order on its stream; with its own communicator the next query's
-    lookup broadcast does not queue behind the current query's reduce-scatter (which waits for the
-    fact scan) and really overlaps that scan.  Created on first use (a collective call)."""
-    global _BUILD_GROUP
-    if _BUILD_GROUP is None and world()[1] > 1:
-        _BUILD_GROUP = dist.new_group(backend=_WORLD[2])
-    return _BUILD_GROUP
-
-
 class PeerArena:
     """One allocation per rank that EVERY rank of the job has mapped (NVLink / NVSwitch peer memory):
     torch.distributed._symmetric_memory allocates it with the CUDA VMM API and exchanges the handles
@@ -186,9 +173,9 @@ def peer_memory_available() -> bool:
     return True
 
 
-def broadcast_(t: torch.Tensor, src: int = 0, group=None) -> torch.Tensor:
+def broadcast_(t: torch.Tensor, src: int = 0) -> torch.Tensor:
     if world()[1] > 1:
-        _timed("broadcast", dist.broadcast, t, src=src, group=group)
+        _timed("broadcast", dist.broadcast, t, src=src)
     return t
 
 

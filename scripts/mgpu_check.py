@@ -76,6 +76,12 @@ def main():
     for rep in range(2):
         check(c2.sql(q3, return_futures=False), exp, ["grp"], ["rev"])
     del os.environ["B200SQL_PEER_MERGE"]
+    # the dim table replicated on every rank (no broadcast: every rank builds its own lookup)
+    c3 = Context()
+    c3.create_table("fact", fact.iloc[lo:hi], persist=True, npartitions=3, distribution="sharded")
+    c3.create_table("dim", dim, persist=True, distribution="replicated")
+    for rep in range(3):
+        check(c3.sql(q3, return_futures=False), exp, ["grp"], ["rev"])
     # 1b. the same with COUNT(*) (row counter instead of the -0.0 indicator) and an int SUM (bitmap)
     got = c.sql("""SELECT d.grp, COUNT(*) AS n, SUM(f.x) AS sx FROM fact f JOIN dim d ON f.fk = d.pk
                    WHERE d.flag < 5 GROUP BY d.grp""", return_futures=False)
