@@ -74,7 +74,8 @@ class JoinAgg(C.Structure):
 
 class StarLookup(C.Structure):
     _fields_ = [("dense", C.c_int32), ("pad_", C.c_int32), ("lookup", C.c_void_p), ("kmin", C.c_int64),
-                ("range", C.c_int64), ("table", C.c_void_p), ("cap", C.c_int64)]
+                ("range", C.c_int64), ("table_keys", C.c_void_p), ("table_slots", C.c_void_p),
+                ("cap", C.c_int64)]
 
 
 MAX_PEERS, PEER_MAX_ARRAYS = 16, 2 * MAX_AGGS + 1
@@ -93,7 +94,7 @@ class PeerMerge(C.Structure):
 
 assert C.sizeof(Col) == 24 and C.sizeof(Term) == 32 and C.sizeof(Scan) == 656
 assert C.sizeof(AggState) == 152 and C.sizeof(Instr) == 24 and C.sizeof(Prog) == 1544
-assert C.sizeof(JoinTable) == 152 and C.sizeof(StarLookup) == 48 and C.sizeof(PeerMerge) == 544
+assert C.sizeof(JoinTable) == 152 and C.sizeof(StarLookup) == 56 and C.sizeof(PeerMerge) == 544
 
 
 class B200SqlError(RuntimeError):
@@ -184,7 +185,7 @@ _SIGS = {
     "b2_star_build_dense": [C.POINTER(Col), _P, C.c_int64, _P, C.c_int64, C.c_int64, _P, _P, _P],
     "b2_star_build_scan": [C.POINTER(Scan), C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int32, _P,
                            _P, _P],
-    "b2_star_build_hash": [C.POINTER(Col), _P, C.c_int64, _P, _P, C.c_int64, _P, _P],
+    "b2_star_build_hash": [C.POINTER(Col), _P, C.c_int64, _P, _P, _P, C.c_int64, _P, _P],
     "b2_star_agg": [C.POINTER(Scan), C.c_int32, C.POINTER(StarLookup), C.POINTER(Agg), C.c_int32,
                     C.POINTER(AggState), _P],
 }

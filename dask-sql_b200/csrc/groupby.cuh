@@ -299,62 +299,39 @@ b2_star_build_scan_kernel(const __grid_constant__ b2_scan_t s, int pk_col, int g
   }
 }
 
-// Hash variant of the pk -> slot lookup (primary keys too sparse for a direct-address array).
-// Entries are 16 bytes, {key, slot}, and two consecutive entries (an even one and the odd one behind it)
-// form a 32-byte bucket = one DRAM / L2 sector: a probe reads its whole home bucket with two 16-byte loads
-// of ONE sector and only walks on -- to the next sector -- when both entries hold other keys.  (Separate
-// key / slot arrays cost two random sectors per row once the table outgrows L2.)  The capacity is any even
-// number, not a power of two: the home bucket is mulhi(mix64(key), cap / 2), so the table is sized at 2x
-// the build rows instead of the next power of two above that.  Insertion is linear probing over entries
-// starting at the home bucket's even entry, so a lookup that scans bucket after bucket sees the entries in
-// insertion-probe order and may stop at the first empty one.
-__device__ __forceinline__ uint64_t b2_star_home(int64_t key, uint64_t nbuckets) {
-  return __umul64hi(b2_mix64((uint64_t)key), nbuckets);
-}
-
 __global__ void __launch_bounds__(B2_BLOCK)
 b2_star_build_hash_kernel(const __grid_constant__ b2_col_t pk, const int32_t* __restrict__ sel, int64_t n_sel,
-                          const int32_t* __restrict__ slot_of_row, int64_t* __restrict__ tab, int64_t cap,
-                          int32_t* __restrict__ flags) {
+                          const int32_t* __restrict__ slot_of_row, int64_t* __restrict__ tk,
+                          int32_t* __restrict__ ts, int64_t cap, int32_t* __restrict__ flags) {
   for (int64_t i = (int64_t)blockIdx.x * B2_BLOCK + threadIdx.x; i < n_sel; i += (int64_t)gridDim.x * B2_BLOCK) {
     const int64_t r = sel ? sel[i] : i;
     const int64_t key = b2_load_raw(pk, r);
     if (b2_is_null(pk, r, key)) continue;
     if (key == B2_EMPTY_KEY) { flags[1] = 1; continue; }  // caller falls back to the general join
-    uint64_t h = 2 * b2_star_home(key, (uint64_t)cap >> 1);
+    uint64_t h = b2_mix64((uint64_t)key) & (uint64_t)(cap - 1);
     bool done = false;
     for (int probe = 0; probe < B2_MAX_PROBE && !done; ++probe) {
-      const unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long*>(tab + 2 * h),
+      const unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long*>(tk + h),
                                                (unsigned long long)B2_EMPTY_KEY, (unsigned long long)key);
-      if (old == (unsigned long long)B2_EMPTY_KEY) { tab[2 * h + 1] = slot_of_row[i]; done = true; }
+      if (old == (unsigned long long)B2_EMPTY_KEY) { ts[h] = slot_of_row[i]; done = true; }
       else if (old == (unsigned long long)key) { flags[0] = 1; done = true; }
-      else h = h + 1 == (uint64_t)cap ? 0 : h + 1;
+      else h = (h + 1) & (uint64_t)(cap - 1);
     }
     if (!done) flags[1] = 1;
   }
 }
 
-// one 16-byte entry, kept in L2 (evict_last) like the dense lookup
-__device__ __forceinline__ longlong2 b2_ld_keep_entry(const int64_t* tab, uint64_t h) {
-  longlong2 v;
-  asm("ld.global.nc.L2::cache_hint.v2.b64 {%0, %1}, [%2], %3;"
-      : "=l"(v.x), "=l"(v.y) : "l"(tab + 2 * h), "l"(b2_policy_keep()));
-  return v;
-}
-
-// scalar lookup (helper for non-batched callers)
 __device__ __forceinline__ int32_t b2_star_lookup(const b2_starlookup_t& lk, int64_t key) {
   if (lk.dense) {
     const uint64_t d = (uint64_t)key - (uint64_t)lk.kmin;
     return d < (uint64_t)lk.range ? b2_ld_keep_i32(lk.lookup + d) : -1;
   }
-  const uint64_t cap = (uint64_t)lk.cap;
-  uint64_t h = 2 * b2_star_home(key, cap >> 1);
+  uint64_t h = b2_mix64((uint64_t)key) & (uint64_t)(lk.cap - 1);
   for (int probe = 0; probe < B2_MAX_PROBE; ++probe) {
-    const longlong2 e = b2_ld_keep_entry(lk.table, h);
-    if (e.x == key) return (int32_t)e.y;
-    if (e.x == B2_EMPTY_KEY) return -1;
-    h = h + 1 == cap ? 0 : h + 1;
+    const int64_t cur = __ldg(reinterpret_cast<const long long*>(lk.table_keys) + h);
+    if (cur == key) return b2_ld_keep_i32(lk.table_slots + h);
+    if (cur == B2_EMPTY_KEY) return -1;
+    h = (h + 1) & (uint64_t)(lk.cap - 1);
   }
   return -1;
 }
@@ -362,8 +339,7 @@ __device__ __forceinline__ int32_t b2_star_lookup(const b2_starlookup_t& lk, int
 // rows per lane per batch of the direct star kernel: measured on B200, 16 beats 8 and 4 (6.86 vs
 // 7.42 ms per 1B rows) although it halves occupancy: more independent loads per thread win.
 #define B2_STAR_R 16
-#define B2_STAR_R_HASH 8     // hash lookup: two 16-byte entries per row in flight, so half the rows per lane
-template <int R, bool HASH, class LD>
+template <int R, class LD>
 __device__ __forceinline__ void b2_star_body(const b2_scan_t& s, const LD& ld, int fk_col, const b2_starlookup_t& lk,
                                              const b2_aggs_arg& aggs, const b2_aggstate_t& st) {
   // Two memory round trips per batch instead of four:
@@ -383,7 +359,7 @@ __device__ __forceinline__ void b2_star_body(const b2_scan_t& s, const LD& ld, i
   if (kc.valid) live &= b2_valid_bits<R>(kc.valid, ld.row0, bits);
   // all lookups of the batch are issued before the first one is consumed
   int32_t found[R];
-  if (!HASH) {
+  if (lk.dense) {
     const uint64_t range = (uint64_t)lk.range;
 #pragma unroll
     for (int j = 0; j < R; ++j) {
@@ -391,37 +367,10 @@ __device__ __forceinline__ void b2_star_body(const b2_scan_t& s, const LD& ld, i
       found[j] = (((live >> j) & 1) && d < range) ? b2_ld_keep_i32(lk.lookup + d) : -1;
     }
   } else {
-    // Round d reads bucket (home + d) of every row that is still looking: all loads of a round are issued
-    // before the first comparison (2 x 16 bytes of one sector per row, up to 2R requests in flight per lane);
-    // a row leaves as soon as it meets its key (found) or an empty entry (no partner).  At load factor 1/2
-    // three rows in four are done after round 0.
-    const uint64_t nb = (uint64_t)lk.cap >> 1;
-    uint32_t pend = 0;
 #pragma unroll
     for (int j = 0; j < R; ++j) {
       found[j] = -1;
-      if (((live >> j) & 1) && key[j] != B2_EMPTY_KEY) pend |= 1u << j;
-    }
-    for (int d = 0; pend != 0 && d <= B2_MAX_PROBE / 2; ++d) {
-      longlong2 ea[R], eb[R];
-#pragma unroll
-      for (int j = 0; j < R; ++j) {
-        if ((pend >> j) & 1) {
-          uint64_t bkt = b2_star_home(key[j], nb) + (uint64_t)d;
-          if (bkt >= nb) bkt -= nb;
-          ea[j] = b2_ld_keep_entry(lk.table, 2 * bkt);
-          eb[j] = b2_ld_keep_entry(lk.table, 2 * bkt + 1);
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < R; ++j) {
-        if ((pend >> j) & 1) {
-          if (ea[j].x == key[j]) { found[j] = (int32_t)ea[j].y; pend &= ~(1u << j); }
-          else if (ea[j].x == B2_EMPTY_KEY) pend &= ~(1u << j);
-          else if (eb[j].x == key[j]) { found[j] = (int32_t)eb[j].y; pend &= ~(1u << j); }
-          else if (eb[j].x == B2_EMPTY_KEY) pend &= ~(1u << j);
-        }
-      }
+      if (((live >> j) & 1) && key[j] != B2_EMPTY_KEY) found[j] = b2_star_lookup(lk, key[j]);
     }
   }
   const bool prefetch = aggs.n > 0 && aggs.a[0].col >= 0;
@@ -433,16 +382,13 @@ __device__ __forceinline__ void b2_star_body(const b2_scan_t& s, const LD& ld, i
   b2_apply_aggs<R>(s, ld, aggs.a, aggs.n, st, slot, prefetch ? pre : nullptr);
 }
 
-// HASH is a template parameter: the direct-address instance must not carry the hash probe's registers
-// (with both in one kernel it needs 140 registers -> one CTA per SM instead of two).
-template <bool PIPE, bool HASH>
-__global__ void __launch_bounds__(PIPE ? B2_PIPE_THREADS : B2_BLOCK, PIPE ? 1 : 2)
+template <bool PIPE>
+__global__ void __launch_bounds__(PIPE ? B2_PIPE_THREADS : B2_BLOCK)
 b2_star_agg_kernel(const __grid_constant__ b2_scan_t s, const __grid_constant__ b2_pipe_t pp, int fk_col,
                    const __grid_constant__ b2_starlookup_t lk, const __grid_constant__ b2_aggs_arg aggs,
                    const __grid_constant__ b2_aggstate_t st) {
-  if (PIPE) b2_tile_pipeline(s, pp, [&](const auto& ld) { b2_star_body<B2_PIPE_R, HASH>(s, ld, fk_col, lk, aggs, st); });
-  else if (HASH) b2_tile_direct<B2_STAR_R_HASH>(s, [&](const auto& ld) { b2_star_body<B2_STAR_R_HASH, true>(s, ld, fk_col, lk, aggs, st); });
-  else b2_tile_direct<B2_STAR_R>(s, [&](const auto& ld) { b2_star_body<B2_STAR_R, false>(s, ld, fk_col, lk, aggs, st); });
+  if (PIPE) b2_tile_pipeline(s, pp, [&](const auto& ld) { b2_star_body<B2_PIPE_R>(s, ld, fk_col, lk, aggs, st); });
+  else b2_tile_direct<B2_STAR_R>(s, [&](const auto& ld) { b2_star_body<B2_STAR_R>(s, ld, fk_col, lk, aggs, st); });
 }
 
 extern "C" {
@@ -670,13 +616,15 @@ int32_t b2_star_build_scan(const b2_scan_t* scan, int32_t pk_col, int32_t grp_co
 }
 
 int32_t b2_star_build_hash(const b2_col_t* pk, const int32_t* sel, int64_t n_sel, const int32_t* slot_of_row,
-                           int64_t* table, int64_t cap, int32_t* d_flags, void* stream) {
-  B2_REQUIRE(pk && slot_of_row && table && d_flags, "null argument");
+                           int64_t* table_keys, int32_t* table_slots, int64_t cap, int32_t* d_flags,
+                           void* stream) {
+  B2_REQUIRE(pk && slot_of_row && table_keys && table_slots && d_flags, "null argument");
   B2_REQUIRE(pk->dtype == B2_I64, "star lookup needs an int64 key");
-  B2_REQUIRE(cap >= 2 && cap % 2 == 0 && ((uintptr_t)table & 31) == 0, "an even cap >= 2 and a 32-byte aligned table");
+  B2_REQUIRE(b2_pow2(cap), "cap must be a power of two");
   if (n_sel <= 0) return B2_OK;
   int grid = b2_wave_grid(b2_star_build_hash_kernel, B2_BLOCK, (n_sel + B2_BLOCK - 1) / B2_BLOCK);
-  b2_star_build_hash_kernel<<<grid, B2_BLOCK, 0, (cudaStream_t)stream>>>(*pk, sel, n_sel, slot_of_row, table, cap, d_flags);
+  b2_star_build_hash_kernel<<<grid, B2_BLOCK, 0, (cudaStream_t)stream>>>(*pk, sel, n_sel, slot_of_row, table_keys,
+                                                                          table_slots, cap, d_flags);
   B2_CHECK_LAUNCH("b2_star_build_hash_kernel");
   return B2_OK;
 }
@@ -692,27 +640,19 @@ int32_t b2_star_agg(const b2_scan_t* scan, int32_t fk_col, const b2_starlookup_t
   B2_REQUIRE(fk_col >= 0 && fk_col < scan->ncols, "fk column out of range");
   B2_REQUIRE(scan->cols[fk_col].dtype == B2_I64, "fk must be int64");
   if (lk->dense) B2_REQUIRE(lk->lookup && lk->range > 0, "bad dense lookup");
-  else B2_REQUIRE(lk->table && lk->cap >= 2 && lk->cap % 2 == 0 && ((uintptr_t)lk->table & 31) == 0, "bad hash lookup");
+  else B2_REQUIRE(lk->table_keys && lk->table_slots && b2_pow2(lk->cap), "bad hash lookup");
   if (scan->n == 0) return B2_OK;
   b2_pipe_t pp;
   b2_make_pipe(*scan, &pp);
   // (A stream access-policy window pinning the lookup as "persisting" L2 was tried and measured no
   // difference against the per-load evict_last / evict_first hints: 5.589 vs 5.582 ms per 1B rows.)
-  const int64_t nblk = (scan->n + (int64_t)B2_BLOCK * B2_STAR_R - 1) / ((int64_t)B2_BLOCK * B2_STAR_R);
-  cudaStream_t cs = (cudaStream_t)stream;
-  if (pp.enabled && lk->dense) {
-    int grid = b2_pipe_grid(b2_star_agg_kernel<true, false>, pp, scan->n);
-    b2_star_agg_kernel<true, false><<<grid, B2_PIPE_THREADS, pp.smem_bytes, cs>>>(*scan, pp, fk_col, *lk, aa, *st);
-  } else if (pp.enabled) {
-    int grid = b2_pipe_grid(b2_star_agg_kernel<true, true>, pp, scan->n);
-    b2_star_agg_kernel<true, true><<<grid, B2_PIPE_THREADS, pp.smem_bytes, cs>>>(*scan, pp, fk_col, *lk, aa, *st);
-  } else if (lk->dense) {
-    int grid = b2_wave_grid(b2_star_agg_kernel<false, false>, B2_BLOCK, nblk);
-    b2_star_agg_kernel<false, false><<<grid, B2_BLOCK, 0, cs>>>(*scan, pp, fk_col, *lk, aa, *st);
+  if (pp.enabled) {
+    int grid = b2_pipe_grid(b2_star_agg_kernel<true>, pp, scan->n);
+    b2_star_agg_kernel<true><<<grid, B2_PIPE_THREADS, pp.smem_bytes, (cudaStream_t)stream>>>(*scan, pp, fk_col, *lk, aa, *st);
   } else {
-    const int64_t nblk_h = (scan->n + (int64_t)B2_BLOCK * B2_STAR_R_HASH - 1) / ((int64_t)B2_BLOCK * B2_STAR_R_HASH);
-    int grid = b2_wave_grid(b2_star_agg_kernel<false, true>, B2_BLOCK, nblk_h);
-    b2_star_agg_kernel<false, true><<<grid, B2_BLOCK, 0, cs>>>(*scan, pp, fk_col, *lk, aa, *st);
+    int64_t nblk = (scan->n + (int64_t)B2_BLOCK * B2_STAR_R - 1) / ((int64_t)B2_BLOCK * B2_STAR_R);
+    int grid = b2_wave_grid(b2_star_agg_kernel<false>, B2_BLOCK, nblk);
+    b2_star_agg_kernel<false><<<grid, B2_BLOCK, 0, (cudaStream_t)stream>>>(*scan, pp, fk_col, *lk, aa, *st);
   }
   B2_CHECK_LAUNCH("b2_star_agg_kernel");
   return B2_OK;

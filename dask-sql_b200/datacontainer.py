@@ -79,7 +79,7 @@ class ColumnContainer:
 
     def make_unique(self, prefix="col") -> "ColumnContainer":
         """Relabel the visible columns <prefix>_0, <prefix>_1, ... (datacontainer.py:161-171)."""
-        return self.rename_handle_duplicates(list(self._order), [f"{prefix}_{i}" for i in range(len(self._order))])
+        return self.rename({name: f"{prefix}_{i}" for i, name in enumerate(self._order)})
 
 
 class Statistics:

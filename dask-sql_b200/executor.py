@@ -735,8 +735,12 @@ class AggPlan:
         return len(self.kaggs) - 1
 
 
-def _nullable_fn(child: LazyFrame):
-    """Can an aggregate input be NULL?  bitmap present, float column (NaN), or computed."""
+def _nullable_fn(child: LazyFrame, sharded: bool = False):
+    """Can an aggregate input be NULL?  bitmap present, float column (NaN), or computed.
+    sharded: the answer decides which accumulator arrays a group table carries (count next to the sum,
+    -0.0 indicator or presence bitmap), and the ranks' partial tables are merged array by array -- so for
+    a sharded input the ranks agree on it (MAX over the ranks: NULL anywhere = nullable everywhere).
+    Every rank asks the same questions in the same order (same plan), one tiny all-reduce each."""
     src = child.source
 
     def nullable(e: Expr):
@@ -764,7 +768,14 @@ def _nullable_fn(child: LazyFrame):
             return True
         return E.may_be_null(e, lambda n: True)
 
-    return nullable
+    if not sharded or P.world()[1] == 1:
+        return nullable
+
+    def agreed(e: Expr):
+        t = torch.tensor([1 if nullable(e) else 0], dtype=torch.int64, device=_dev())
+        return bool(int(P.allreduce_(t, "max").item()))
+
+    return agreed
 
 
 def _one_row(value, dtype, logical, dev) -> DeviceColumn:
@@ -823,7 +834,7 @@ def run_aggregate(src: AggSource, allow_fast=True) -> Part:
     for p in pred:
         p.refs(needed)
     parts = [] if never else materialize(child.source, needed, pred=pred)
-    plan = AggPlan(aggs, _nullable_fn(child), _moment_shifts(aggs, parts, child, sharded))
+    plan = AggPlan(aggs, _nullable_fn(child, sharded), _moment_shifts(aggs, parts, child, sharded))
     if not gexprs:
         return global_aggregate(parts, pred, plan, sharded)
     return grouped_aggregate(parts, pred, gexprs, src.group_cols, plan, child, sharded, src.options)
@@ -1581,10 +1592,10 @@ class PreparedStar:
 
     One stream, in order: lookup fill -> b2_star_build_scan (every rank that holds dim rows; a 'root' table
     is followed by one NCCL broadcast of the finished lookup) -> b2_star_agg per fact partition -> merge ->
-    compaction.  Two lookup buffers (and, with the NVLink peer merge, two group tables) alternate between
-    consecutive executions; buffer i is refilled only after the run that last read it has FINISHED
-    (event), which also bounds the host's run-ahead to two executions; results are always freshly
-    allocated and never alias the reused buffers."""
+    compaction.  The lookup buffer is refilled in stream order; with the NVLink peer merge two group
+    tables alternate between consecutive executions (peers read a table while its owner has moved on).
+    The host issues run k + 2 only after run k has FINISHED (event): at most two executions in flight.
+    Results are always freshly allocated and never alias the reused buffers."""
 
     _live: "List[PreparedStar]" = []
     MAX_LIVE = 4          # prepared plans keep ~100 MB of HBM each: keep only the most recent ones
@@ -1641,7 +1652,7 @@ class PreparedStar:
         self.gexpr0 = gexpr0
         self.glog = dim.col_type(gexpr0.name)[1] if isinstance(gexpr0, ColRef) else "int64"
         self.plan = AggPlan([(E.substitute(e, fact.exprs) if e is not None else None, o, f) for e, o, f in aggs],
-                            _nullable_fn(fact))
+                            _nullable_fn(fact, sharded))
         if any(not isinstance(ka.expr, ColRef) for ka in self.plan.kaggs):
             raise _NotPreparable()
         # ---- launch descriptors (every referenced column must be resident and used as it is)
@@ -1671,12 +1682,14 @@ class PreparedStar:
             self.fact_launch.append((ctx.scan(), fk_slot, D.make_aggs(specs), len(specs), part.n))
             self.keep.append(ctx)
         # ---- reused device buffers
-        self.ring = [torch.empty(self.prange + 4, dtype=torch.int32, device=dev) for _ in range(2)]
-        self.lk = []
-        for buf in self.ring:
-            lk = L.StarLookup()
-            lk.dense, lk.lookup, lk.kmin, lk.range = 1, buf.data_ptr(), self.pmin, self.prange
-            self.lk.append(lk)
+        # ONE lookup buffer: every run refills it in stream order, after the previous run's scan.  (Two
+        # alternating buffers -- needed while the build ran on its own stream -- keep 2 x 40 MB of
+        # evict_last lines in a 126 MB L2 next to the group tables, and a step with one fact partition
+        # per GPU then meets a lookup that the other buffer's protected lines have half displaced:
+        # b2_star_agg measured 0.70-0.72 ms per 125M rows at N = 2 / 4 / 8 against 0.577 ms at N = 1.)
+        self.lookup = torch.empty(self.prange + 4, dtype=torch.int32, device=dev)
+        self.lk = L.StarLookup()
+        self.lk.dense, self.lk.lookup, self.lk.kmin, self.lk.range = 1, self.lookup.data_ptr(), self.pmin, self.prange
         # group tables: ONE (re-initialised per run) on the NCCL / single-GPU path; enable_peer_merge()
         # replaces it with two in symmetric memory that alternate run by run
         self.tabs = [GroupState(dev, self.nslots, self.plan, need_present=True,
@@ -1685,7 +1698,7 @@ class PreparedStar:
         self.dirty = [False]      # a fresh table is already initialised
         self.peer = None          # per-table b2_peer_merge descriptors once enabled
         self.epoch = 0
-        self.free = [None, None]  # event recorded at the end of the run that last used ring buffer i
+        self.free = [None, None]  # event recorded at the end of run k, waited for before run k + 2 is issued
         self.merge_bufs = {}      # presence / reduce-scatter outputs, reused run after run
         self.runs = 0
 
@@ -1801,7 +1814,7 @@ class PreparedStar:
     def run(self, src) -> Part:
         i = self.runs & 1
         self.runs += 1
-        buf = self.ring[i]
+        buf = self.lookup
         main = D.cur_stream()
         sp = D.stream_ptr()
         # The host waits here until the run before the previous one has FINISHED: at most two executions
@@ -1812,9 +1825,9 @@ class PreparedStar:
             self.free[i].synchronize()
         # ---- build side, in order on the caller's stream.  (Round 2 first ran it on a second stream and
         # communicator so that the next step's build + broadcast overlapped the current scan.  Measured at
-        # N=2 that LOSES: the scan kernels are persistent grids that fill every SM, so the build kernels wait
-        # for a whole fact partition anyway (0.75 ms "build" for 0.08 ms of work) and then compete with the
-        # scan for HBM -- b2_star_agg went from 0.577 to 0.723 ms per 125M rows, the step from 2.6 to 3.4 ms.)
+        # N=2 there is nothing to gain: the scan kernels are persistent grids that fill every SM, so the
+        # build kernels wait for a whole fact partition anyway -- 0.75 ms of "build" for 0.08 ms of work,
+        # 0.70 ms of "broadcast" for 40 MB -- and the extra stream, communicator and events only add cost.)
         with _Phase("build"):
             # lookup := -1 everywhere (0xFF bytes), the 4 flag words behind it := 0
             L.memset(C.c_void_p(buf.data_ptr()), 0xFF, 4 * self.prange, sp)
@@ -1838,7 +1851,7 @@ class PreparedStar:
             for scan, fk_slot, aggs_arr, naggs, n in self.fact_launch:
                 stats["launches"] += 1
                 ev = _kernel_event_begin("b2_star_agg_kernel", n)
-                L.star_agg(C.byref(scan), fk_slot, C.byref(self.lk[i]), aggs_arr, naggs, C.byref(t.state), sp)
+                L.star_agg(C.byref(scan), fk_slot, C.byref(self.lk), aggs_arr, naggs, C.byref(t.state), sp)
                 _kernel_event_end(ev)
         if self.peer is not None:
             m, view = self.peer[ti]
@@ -1938,7 +1951,7 @@ def _star_dense_fast(src, fact, dim, fk_e, pk_e, gexprs, aggs, fact_pred, dim_pr
         with _Phase("bcast"):
             P.broadcast_(buf, 0)
     plan = AggPlan([(E.substitute(e, fact.exprs) if e is not None else None, o, f) for e, o, f in aggs],
-                   _nullable_fn(fact))
+                   _nullable_fn(fact, sharded))
     gs = GroupState(dev, nslots, plan, need_present=True, alloc=_padded_slots(nslots, sharded))
     lk = L.StarLookup()
     lk.dense, lk.lookup, lk.kmin, lk.range = 1, lookup.data_ptr(), pmin, prange
@@ -2039,7 +2052,7 @@ def try_star(src: AggSource, child: LazyFrame, gexprs, aggs, pred, sharded, allo
     if pst.vmin is None:
         return None
     plan = AggPlan([(E.substitute(e, fact.exprs) if e is not None else None, o, f) for e, o, f in aggs],
-                   _nullable_fn(fact))
+                   _nullable_fn(fact, sharded))
     glog = [(e.logical if isinstance(e, ColRef) else _LOGICAL[e.dtype]) for e in gexprs]
     glog = [dim.col_type(e.name)[1] if isinstance(e, ColRef) else l for e, l in zip(gexprs, glog)]
 
@@ -2089,15 +2102,13 @@ def try_star(src: AggSource, child: LazyFrame, gexprs, aggs, pred, sharded, allo
                            D.ptr(flags), D.stream_ptr())
         lk.dense, lk.lookup, lk.kmin, lk.range = 1, lookup.data_ptr(), pst.vmin, prange
     else:
-        # {key, slot} entries of 16 bytes, twice as many as build rows (any size: the home entry is a
-        # multiply-shift of the hash, not a mask)
-        lcap = max(1024, 2 * d.n)              # even; two entries = one 32-byte bucket
-        ltab = torch.empty(2 * lcap, dtype=torch.int64, device=dev)
-        ltab[0::2] = L.EMPTY_KEY
+        lcap = D._pow2_at_least(max(1024, 2 * d.n))
+        ltk = torch.full((lcap,), L.EMPTY_KEY, dtype=torch.int64, device=dev)
+        lts = torch.full((lcap,), -1, dtype=torch.int32, device=dev)
         stats["launches"] += 1
-        L.star_build_hash(C.byref(pks), None, d.n, D.ptr(slot_of_row), D.ptr(ltab), lcap, D.ptr(flags),
-                          D.stream_ptr())
-        lk.dense, lk.table, lk.cap = 0, ltab.data_ptr(), lcap
+        L.star_build_hash(C.byref(pks), None, d.n, D.ptr(slot_of_row), D.ptr(ltk), D.ptr(lts), lcap,
+                          D.ptr(flags), D.stream_ptr())
+        lk.dense, lk.table_keys, lk.table_slots, lk.cap = 0, ltk.data_ptr(), lts.data_ptr(), lcap
     fl = flags.cpu().tolist()
     if fl[0] or fl[1]:
         return None  # duplicate build keys (or overflow): the general join path handles it

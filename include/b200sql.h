@@ -518,16 +518,11 @@ int32_t b2_star_build_dense(const b2_col_t* pk, const int32_t* sel, int64_t n_se
 int32_t b2_star_build_scan(const b2_scan_t* scan, int32_t pk_col, int32_t grp_col, int64_t pk_min,
                            int64_t pk_range, int64_t grp_min, int32_t null_slot, int32_t* lookup,
                            int32_t* d_flags, void* stream);
-/* Hash variant (primary keys too sparse for a direct-address array): table = int64[2*cap], 32-byte
- * aligned, entry h = {table[2h] = key, table[2h+1] = slot}, every key word pre-filled with B2_EMPTY_KEY.
- * cap is any EVEN number >= 2 (typically 2x the build rows): entries 2b and 2b+1 form bucket b = one
- * 32-byte sector, the home bucket is mulhi64(mix(key), cap/2), insertion probes linearly from the home
- * bucket's first entry with wrap-around, a lookup reads bucket after bucket (two 16-byte loads of one
- * sector each).  d_flags[0] = 1 on duplicate pk, d_flags[1] = 1 on overflow or a key equal to
- * B2_EMPTY_KEY. */
+/* Hash variant: table_keys = int64[cap] pre-filled with B2_EMPTY_KEY, table_slots = int32[cap].
+ * d_flags[0] = 1 on duplicate pk, d_flags[1] = 1 on overflow. */
 int32_t b2_star_build_hash(const b2_col_t* pk, const int32_t* sel, int64_t n_sel,
-                           const int32_t* slot_of_row, int64_t* table, int64_t cap,
-                           int32_t* d_flags, void* stream);
+                           const int32_t* slot_of_row, int64_t* table_keys, int32_t* table_slots,
+                           int64_t cap, int32_t* d_flags, void* stream);
 
 typedef struct b2_starlookup {
   int32_t dense;
@@ -535,7 +530,8 @@ typedef struct b2_starlookup {
   const int32_t* lookup;   /* dense: int32[range], -1 = no partner */
   int64_t kmin;
   int64_t range;
-  const int64_t* table;    /* hash: int64[2*cap] {key, slot} entries, 32-byte aligned, cap even */
+  const int64_t* table_keys;  /* hash */
+  const int32_t* table_slots;
   int64_t cap;
 } b2_starlookup_t;
 
