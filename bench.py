@@ -193,8 +193,10 @@ def workload_config(args, n):
                              "engine keeps small dimension tables), every GPU builds its pk->slot lookup every step; "
                              if args.dim_dist == "replicated" else
                              "dim on rank 0, its pk->slot lookup broadcast every step (NCCL); ") +
-                            "dense partial aggregates merged by key range -- " + merge_kind() + " -- every rank "
-                            "compacts and keeps the groups of its range") if n > 1 else "single GPU"}
+                            "dense partial aggregates merged by key range (b2_peer_merge over NVLink peer memory, "
+                            "ncclReduceScatter where symmetric memory is unavailable: the line's `merge` key says "
+                            "which ran), every rank compacts and keeps the groups of its range")
+            if n > 1 else "single GPU"}
 
 
 def merge_kind():
@@ -491,6 +493,7 @@ def main():
             "groups_out": n_groups_out, "verified_full_size": verified, "exchange": exchange,
             "wall_ms_per_step": wall / args.steps * 1e3,
             "fused_star_pipeline": executor.stats["star_fused"] > 0, "configs": configs,
+            "merge": merge_kind() if world > 1 else None,
         }
         os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:

@@ -16,7 +16,7 @@ try:
     d=json.loads(open('gpurun_out/r2j_${name}_$n.json').read().strip().splitlines()[-1])
     print('ms/step %.3f'%d['ms_per_step'], 'G rows/s %.1f'%(d['value']/1e9), 'ok', d['verified_full_size'].get('ok'), 'groups', d['verified_full_size'].get('groups'), d['verified_full_size'].get('groups_expected'))
     print({k:round(v,3) for k,v in (d['exchange'] or {}).items() if k.endswith('_ms')})
-    print('kernel', d['roofline']['avg_launch_ms'], 'share', round(d['roofline']['kernel_share_of_step'],3), d['config']['parallelism'][-120:])
+    print('kernel', d['roofline']['avg_launch_ms'], 'share', round(d['roofline']['kernel_share_of_step'],3), (d.get('merge') or '')[:60])
 except Exception as e:
     print('no result', e)
 PY

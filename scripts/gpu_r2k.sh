@@ -16,7 +16,7 @@ try:
     d=json.loads(open('gpurun_out/r2k_${name}_$n.json').read().strip().splitlines()[-1])
     print('ms/step %.3f'%d['ms_per_step'], 'G rows/s %.1f'%(d['value']/1e9), 'ok', d['verified_full_size'].get('ok'), 'groups', d['verified_full_size'].get('groups'), d['verified_full_size'].get('groups_expected'))
     print({k:round(v,3) for k,v in (d['exchange'] or {}).items() if k.endswith('_ms')})
-    print('kernel', round(d['roofline']['avg_launch_ms'],4), 'share', round(d['roofline']['kernel_share_of_step'],3), 'peer' if 'b2_peer_merge' in d['config']['parallelism'] else 'nccl', 'clocks', d['clocks'])
+    print('kernel', round(d['roofline']['avg_launch_ms'],4), 'share', round(d['roofline']['kernel_share_of_step'],3), (d.get('merge') or '')[:13], 'clocks', d['clocks'])
 except Exception as e:
     print('no result', e)
 PY
