@@ -157,6 +157,25 @@ def _dense_worker(rank, size, port, out_q):
         allp = merge.allgather_part(p, dev)
         assert allp["k"].data.tolist() == [1000 * r + i for r in range(size) for i in range(r)]
 
+        # --- "can this aggregate input be NULL?" is agreed across the ranks of a sharded plan (it decides
+        # which accumulator arrays a table carries; partial tables are merged array by array): NULL on
+        # any rank = nullable on every rank, and every rank gets the same answer
+        from dask_sql_b200.expr import Lit
+        from dask_sql_b200.frame import LazyFrame
+
+        class Src:
+            pass
+
+        X._dev = lambda: dev
+        frame = LazyFrame.__new__(LazyFrame)
+        frame.source = Src()
+        agreed = X._nullable_fn(frame, sharded=True)
+        local = X._nullable_fn(frame, sharded=False)
+        mine_null = Lit(None, I64) if rank == size - 1 else Lit(1, I64)
+        assert local(mine_null) == (rank == size - 1)
+        assert agreed(mine_null) is True                      # the last rank's NULL makes it nullable everywhere
+        assert agreed(Lit(2, I64)) is False
+
         # --- the dense merge: 1000 logical slots (+ NULL slot), float SUM whose accumulator doubles
         # as the local presence flag (-0.0 = untouched); 30 % of the slots are hit by NO rank
         nslots = 1001
