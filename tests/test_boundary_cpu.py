@@ -112,6 +112,18 @@ def test_column_container():
     assert c5.columns == ["x_0", "x_1", "x_2"] and c5.get_backend_by_frontend_name("x_2") == "c"
     c6 = c.rename_handle_duplicates(["a", "a"], ["p", "q"])
     assert c6.get_backend_by_frontend_name("p") == "a" and c6.get_backend_by_frontend_name("q") == "a"
+    # the reference's known answers, including the ORDER of mapping() (tests/unit/test_datacontainer.py:4-67)
+    ident = [("a", "a"), ("b", "b"), ("c", "c")]
+    assert ColumnContainer(["a", "b", "c"], {"a": "1", "b": "2", "c": "3"}).mapping() == [("a", "1"), ("b", "2"), ("c", "3")]
+    assert c2.mapping() == ident and c.mapping() == ident                     # limit_to keeps every name resolvable
+    assert c3.mapping() == [("a", "b"), ("b", "b"), ("c", "c"), ("A", "a")] and c.mapping() == ident
+    assert c.add("d").mapping() == ident + [("d", "d")]
+    assert c.add("d", "D").mapping() == ident + [("d", "D")] and c.add("d", "D").columns == ["a", "b", "c", "d"]
+    assert c.add("d", "a").mapping() == ident + [("d", "a")]
+    assert c.add("a", "b").columns == ["a", "b", "c"] and c.add("a", "b").mapping() == [("a", "b"), ("b", "b"), ("c", "c")]
+    assert c.columns == ["a", "b", "c"] and c.mapping() == ident              # nothing above touched the original
+    with pytest.raises(AssertionError):
+        ColumnContainer(["a", 1])
 
 
 # ---- planner shapes ---------------------------------------------------------------------------
