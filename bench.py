@@ -308,10 +308,6 @@ def main():
     json_fd = os.dup(1)
     os.dup2(2, 1)
 
-    # buffers handed to a collective stay owned by this code until the collective has been waited for
-    # (they are persistent or live to the end of the query), so the allocator need not tie them to the
-    # communicator's stream; without this their blocks cannot be recycled while the host runs ahead
-    os.environ.setdefault("TORCH_NCCL_AVOID_RECORD_STREAMS", "1")
     import torch
     import torch.distributed as dist
 

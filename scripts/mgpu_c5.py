@@ -13,7 +13,6 @@ import os
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-os.environ.setdefault("TORCH_NCCL_AVOID_RECORD_STREAMS", "1")
 import torch
 import torch.distributed as dist
 
