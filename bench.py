@@ -658,12 +658,15 @@ def run_configs(args, torch, dev, peak_gbs, peak_src, traffic):
     # the figure is attached to the REDG kernels only.
     L2_REQ_PEAK = 200.7
 
-    def entry(name, rows, ms, kev, kernel, bytes_per_row, launches, query, verified, extra=None, random_per_row=None):
+    def entry(name, rows, ms, kev, kernel, bytes_per_row, launches, query, verified, extra=None, random_per_row=None,
+              has_capture=True):
+        # has_capture=False: profiles/traffic.json holds no ncu capture of THIS variant of the kernel
+        tr = traffic if has_capture else {}
         e = {"rows": rows, "ms": ms, "rows_per_s": rows / (ms * 1e-3), "query": query,
              "breakdown_ms_per_step": getattr(_time_query, "breakdown", None),
              "algorithmic_gbs_whole_query": rows * bytes_per_row / (ms * 1e-3) / 1e9,
              "frac_of_peak_whole_query": rows * bytes_per_row / (ms * 1e-3) / 1e9 / peak_gbs,
-             "roofline": kernel_roofline(kev, kernel, bytes_per_row, peak_gbs, peak_src, traffic, ms * 1e-3, steps),
+             "roofline": kernel_roofline(kev, kernel, bytes_per_row, peak_gbs, peak_src, tr, ms * 1e-3, steps),
              "gpu_launches_per_step": launches, "verified": verified, "steps": steps, "warmup": warmup}
         if extra:
             e.update(extra)
@@ -703,7 +706,8 @@ def run_configs(args, torch, dev, peak_gbs, peak_src, traffic):
             got = int(parts[0]["s"].data[0].item())
             exp = int(xx[xx > 0].sum().item())
             entry(label, n, ms, kev, "b2_scan_agg_kernel", 8, nl, q, {"ok": got == exp, "sum": got, "expected": exp},
-                  {"partitions": nparts, "l2": "8 GB >> L2" if n > 5e7 else "80 MB fits L2: launch-latency bound"})
+                  {"partitions": nparts, "l2": "8 GB >> L2" if n > 5e7 else "80 MB fits L2: launch-latency bound"},
+                  has_capture=n > 5e7)
             del xx, c
 
     # ---- C2: GROUP BY key SUM(val), 200M rows, 1M keys, 8 partitions
@@ -743,7 +747,7 @@ def run_configs(args, torch, dev, peak_gbs, peak_src, traffic):
               {"keys": nkeys, "distribution": "Zipf(1.1), ranks scattered by a permutation" if kind == "zipf"
                else "uniform", "hottest_key_share": top, "val": "int64" if kind == "int" else "float64",
                "partitions": 8, "grouped_kernel": executor.stats.get("grouped_groupby", 0) > 0},
-              random_per_row=None if kind == "zipf" else 1.0)
+              random_per_row=None if kind == "zipf" else 1.0, has_capture=kind != "zipf")
 
     # ---- C3: INNER JOIN 1B-row fact x 10M-row dim, 80 % match; materialising and fused SUM(v*w)
     def c3(name, fused):
@@ -852,8 +856,8 @@ def run_configs(args, torch, dev, peak_gbs, peak_src, traffic):
         entry("C4_sparse_pk", n, ms, kev, "b2_star_agg_kernel", 24, nl, QUERY,
               {"ok": bool(ok_keys and err <= 1e-9), "groups": int(k_sorted.numel()), "max_rel_err": err,
                "checked": "every group against torch index_add_"},
-              {"lookup": "open-addressing hash table (b2_star_build_hash), 16 B/slot", "dim_rows": ndim,
-               "partitions": 4})
+              {"lookup": "open-addressing hash table (b2_star_build_hash): int64 keys + int32 slots, 12 B/slot",
+               "dim_rows": ndim, "partitions": 4}, has_capture=False)
 
     # ---- C5: one GPU's share (500M rows) of GROUP BY over 100M keys, SUM + AVG
     def c5():
